@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the qpwcnet hot path on B200 (contract: see DESIGN.md 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): the cost-volume / warp call pattern of one PWC-Net forward
+pass -- 1 plain cost volume + 4 fused warp->cost volumes -- on Sintel-shaped 436x1024 pairs
+(padded to 448x1024), batch 8, search range 4, fp32, synthetic inputs (seed 0).  One "step" = one
+pass over one batch of 8 frame pairs.  N > 1: every rank runs its own batch (independent frame
+pairs, no collective on the data path) => weak scaling; value = 8*N / max-over-ranks step time.
+
+Prints ONE JSON line on rank 0.  `value`: inputs resident in HBM.  `e2e`: the same metric through
+the public API with pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+`--impl reference`: the CPU restatement of the reference (oracle/, OpenMP over all host cores) on a
+bounded sample (one frame pair per step) -- TF/tfa cannot be installed in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frame-pairs/s at 436x1024 B=8 (PWC-Net pyramid hot path: 1 corr + 4 fused warp->corr, d=4)"
+UNIT = "frame-pairs/s"
+HEIGHT, WIDTH, BATCH, SEARCH = 436, 1024, 8, 4
+FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4, nominal FFMA peak at max clock
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU on a background thread (NVML)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.samples, self.reasons = [], set()
+        self.max_mhz, self.period, self._stop = None, period_s, threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self, note=None):
+        s = sorted(self.samples)
+        out = {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(s)}
+        if note:
+            out["note"] = note
+        return out
+
+
+# ------------------------------------------------------------------------------ CPU reference
+def cpu_reference_step(sample_batch=1, threads=None, repeats=1):
+    """Times the CPU oracle (restated reference) on `sample_batch` frame pairs of the workload."""
+    import numpy as np
+
+    import oracle
+    from qpwcnet_b200.pyramid import levels_for
+    if threads:
+        oracle.set_num_threads(threads)
+    r = np.random.default_rng(0)
+    data = []
+    for lv in levels_for(HEIGHT, WIDTH):
+        shp = (sample_batch, lv.H, lv.W, lv.C)
+        prv = r.standard_normal(shp, dtype=np.float32)
+        nxt = r.standard_normal(shp, dtype=np.float32)
+        flo = (r.standard_normal((sample_batch, lv.H, lv.W, 2), dtype=np.float32) * (SEARCH / 2.0)) if lv.fused else None
+        data.append((prv, nxt, flo))
+
+    def one():
+        for prv, nxt, flo in data:
+            if flo is None:
+                oracle.cost_volume(prv, nxt, SEARCH)
+            else:
+                oracle.warp_cost_volume(prv, nxt, flo, "tfa", SEARCH)
+
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        one()
+        best = min(best, time.perf_counter() - t0)
+    return best, oracle.num_threads(), one
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    t_warm, cores, one = cpu_reference_step(1)
+    for _ in range(max(0, args.warmup - 1)):
+        if t_warm * args.warmup > 30:
+            break
+        one()
+    steps = max(1, min(args.steps, int(90.0 / max(t_warm, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    value = 1.0 / dt
+    sample = ("1 frame pair (B=1) of the 436x1024 pyramid per step: 1 cost volume + 4 warp->cost "
+              "volumes, fp32, C oracle (oracle/qpwc_oracle.c) with OpenMP over all host cores")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "steps_requested": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "pwcnet-pyramid-hotpath 436x1024 (padded 448x1024) d=4, CPU sample B=1",
+                   "levels": "14x32x256 28x64x256 56x128x128 112x256x64 224x512x32"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "TensorFlow/tensorflow_addons are not installable here; the reference's algorithm is timed through its CPU restatement",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------- native
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from qpwcnet_b200 import ops
+    from qpwcnet_b200.pyramid import PyramidWorkload, algorithmic_bytes, algorithmic_flops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    assert ops.library_version() >= 100
+    K, Wm = args.steps, max(args.warmup, 3)
+    wl = PyramidWorkload(HEIGHT, WIDTH, BATCH, SEARCH, device=dev, seed=rank)
+    dom = max(range(len(wl.levels)), key=lambda k: algorithmic_bytes(wl.levels[k], BATCH, SEARCH))
+
+    for _ in range(Wm):
+        wl.step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dom_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    nlev = len(wl.levels)
+    ev0.record()
+    for s in range(K):
+        for k in range(nlev):
+            if k == dom:
+                dom_ev[s][0].record()
+                wl.run_level(k)
+                dom_ev[s][1].record()
+            else:
+                wl.run_level(k)
+    ev1.record()
+    barrier()
+    t_ms = ev0.elapsed_time(ev1)
+    note = None
+    if len(sampler.samples) < 5:
+        # the timed region is shorter than a few sampling periods: keep the identical load running
+        # (untimed) for ~0.5 s so that clocks/throttle reasons under this load are still observed
+        t_end = time.perf_counter() + 0.5
+        while time.perf_counter() < t_end:
+            wl.step()
+        torch.cuda.synchronize()
+        note = (f"timed region {t_ms:.1f} ms is shorter than the sampling window; clocks sampled over "
+                "it plus ~0.5 s of the identical untimed load")
+    sampler.stop()
+    t_ms = max_over_ranks(t_ms)
+    dom_ms = sum(a.elapsed_time(b) for a, b in dom_ev) / K
+    ms_per_step = t_ms / K
+    value = BATCH * world / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API with pinned host buffers, H2D + kernels + D2H inside the timed region
+    wl_h = PyramidWorkload(HEIGHT, WIDTH, BATCH, SEARCH, device="cpu", seed=rank)
+    Ke = max(3, min(K, 20))
+    for _ in range(2):
+        wl_h.step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        wl_h.step()
+        _ = float(wl_h.outputs[0][0, 0, 0, 0])      # host-side read of the step's result
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / Ke)
+    barrier()
+    e2e = {"value": BATCH * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": wl_h.h2d_bytes(),
+           "d2h_bytes_per_step": wl_h.d2h_bytes(), "steps": Ke, "ms_per_step": e2e_s * 1e3,
+           "path": "ops.*_into(pinned host tensors) -> qpwc_*_host (3-slot H2D/kernel/D2H pipeline)"}
+
+    # ---- roofline of the dominant kernel (finest fused level)
+    peak, peak_src = load_peaks()
+    lv = wl.levels[dom]
+    abytes = algorithmic_bytes(lv, BATCH, SEARCH)
+    aflops = algorithmic_flops(lv, BATCH, SEARCH)
+    achieved = abytes / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": load_traffic(), "peak_source": peak_src,
+        "kernel": f"fused warp->corr level {lv.H}x{lv.W}x{lv.C} B={BATCH} d={SEARCH}",
+        "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": dom_ms,
+        "share_of_step": dom_ms / ms_per_step,
+        "fp32": {"achieved_tflops": aflops / (dom_ms * 1e-3) / 1e12, "peak_tflops": FP32_PEAK_TFLOPS,
+                 "frac": aflops / (dom_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                 "note": "nominal FFMA peak 148 SM x 128 lanes x 2 x 1.965 GHz"},
+        "whole_step": {"algorithmic_bytes": wl.algorithmic_bytes(), "algorithmic_flops": wl.algorithmic_flops(),
+                       "gbs": wl.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9,
+                       "tflops": wl.algorithmic_flops() / (ms_per_step * 1e-3) / 1e12},
+    }
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t_cpu, cores, _ = cpu_reference_step(1, repeats=2)
+        cpu_baseline = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "1 frame pair (B=1) of the same pyramid, best of 2, C oracle + OpenMP on all host cores"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "pwcnet-pyramid-hotpath 436x1024 (padded 448x1024) B=8 per GPU, d=4, warp mode tfa",
+                       "levels": "14x32x256(corr) 28x64x256 56x128x128 112x256x64 224x512x32 (fused warp->corr)",
+                       "l2": "inputs larger than L2: each step streams 853 MB of distinct tensors (126 MB L2)",
+                       "parallelism": f"batch-sharded replicas x{world}, no collective on the data path"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": wl.launches_per_step * K, "clocks": sampler.summary(note),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

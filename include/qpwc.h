@@ -1,0 +1,102 @@
+/* qpwc.h -- C ABI of libqpwc.so: B200 (sm_100a) kernels for the QPWCNet per-pyramid-level hot path.
+ *
+ * The reference (yycho0108/qpwcnet) has no FFI boundary of its own: the hot path is the Python call
+ * surface of four Keras layers / functors and one function.  Each entry point below is what a
+ * binding for that surface would call; the interface it replaces is cited as file:line relative to
+ * the reference checkout.  INTEGRATION.md shows the TF2-side stub (tf.custom_gradient + DLPack)
+ * and the in-repo PyTorch/ctypes host layer (qpwcnet_b200/) that already binds them.
+ *
+ * Conventions
+ *  - All tensors: dense fp32, NHWC ("channels_last"): index ((b*H + i)*W + j)*C + c.  Flow is
+ *    (B,H,W,2) with channel 0 = x (width) and channel 1 = y (height) displacement, in pixels
+ *    (qpwcnet/core/warp.py:102,109-111).
+ *  - Device entry points take DEVICE pointers of the current CUDA device and enqueue on `stream`
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream).  No implicit synchronisation.
+ *    The `_host` entry points take HOST pointers (pageable or pinned), stage through an internal,
+ *    lazily grown per-device workspace and return after the results are in the host buffers.
+ *  - Ownership: the caller allocates every buffer, outputs and workspaces included; the library
+ *    keeps no pointer past the call.  Scatter-add targets (g_img, g_nxt) are zero-filled by the
+ *    library with a stream-ordered memset.
+ *  - Errors: no exception crosses the ABI.  Every function returns QPWC_OK (0) or a non-zero code
+ *    and records a message retrievable (per calling thread) with qpwc_last_error().
+ *  - Threading: stateless and re-entrant; concurrent calls from several host threads / devices are
+ *    legal.  ctypes releases the GIL for the duration of a call.
+ *  - `search_range` d >= 1: D = (2d+1)^2 output channels, channel = (di+d)*(2d+1) + (dj+d), row
+ *    displacement outer (qpwcnet/core/layers.py:80-81).  `out_pixel_stride` (in floats, >= D) lets
+ *    the cost volume be written straight into its slice of a wider concat buffer
+ *    (qpwcnet/core/non_layers.py:381-382); pass D for the dense reference layout.
+ *  - warp `mode`: QPWC_WARP_TF  = Warp / tf_warp (truncate + clip + weights from clipped corners),
+ *                 QPWC_WARP_TFA = WarpV2 / tfa.image.dense_image_warp (floor, edge clamp).
+ */
+#ifndef QPWC_H_
+#define QPWC_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPWC_OK 0
+#define QPWC_ERR_INVALID 1     /* null / misaligned pointer, bad shape, bad mode            */
+#define QPWC_ERR_UNSUPPORTED 2 /* valid request this build cannot serve                      */
+#define QPWC_ERR_CUDA 3        /* CUDA runtime / launch error (message holds the CUDA string) */
+
+#define QPWC_WARP_TF 0
+#define QPWC_WARP_TFA 1
+
+/* Library version (major*10000 + minor*100 + patch). */
+int qpwc_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+const char* qpwc_last_error(void);
+
+/* CostVolume.call / CostVolumeV2.call -- qpwcnet/core/layers.py:72-100, 117-132
+ * (functors: qpwcnet/core/non_layers.py:72-104, 112-123), leaky_relu(slope) included. */
+int qpwc_corr_fwd(const float* prv, const float* nxt, float* out, int B, int H, int W, int C,
+                  int search_range, float leaky_slope, long long out_pixel_stride, void* stream);
+
+/* Gradient of the above (TF autodiff of layers.py:77-99 / tfa CorrelationCostGrad + LeakyReluGrad).
+ * `out` is the forward result (sign gives the leaky mask); g_out shares its pixel stride. */
+int qpwc_corr_bwd(const float* prv, const float* nxt, const float* out, const float* g_out,
+                  float* g_prv, float* g_nxt, int B, int H, int W, int C, int search_range,
+                  float leaky_slope, long long out_pixel_stride, void* stream);
+
+/* Warp.call -> tf_warp (qpwcnet/core/warp.py:63-153; layers.py:166-168) and
+ * WarpV2.call -> tfa.image.dense_image_warp(img, -flo[..., ::-1]) (layers.py:177-186). */
+int qpwc_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                  int mode, void* stream);
+
+/* Gradient of the above: g_img (zero-filled here, then scatter-added) and g_flow. */
+int qpwc_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
+                  float* g_flow, int B, int H, int W, int C, int mode, void* stream);
+
+/* UpFlow's  CostVolumeV2((prv, WarpV2((nxt, flo))))  -- qpwcnet/core/non_layers.py:377-380
+ * (layers.py:478-481) as ONE kernel: the warped second frame never reaches HBM. */
+int qpwc_warp_corr_fwd(const float* prv, const float* nxt, const float* flow, float* out, int B,
+                       int H, int W, int C, int search_range, float leaky_slope, int mode,
+                       long long out_pixel_stride, void* stream);
+
+/* Gradient of the fused op: g_prv, g_nxt (zero-filled here), g_flow.  `workspace` must hold
+ * qpwc_warp_corr_bwd_workspace(B,H,W,C) bytes of device memory. */
+size_t qpwc_warp_corr_bwd_workspace(int B, int H, int W, int C);
+int qpwc_warp_corr_bwd(const float* prv, const float* nxt, const float* flow, const float* out,
+                       const float* g_out, float* g_prv, float* g_nxt, float* g_flow,
+                       void* workspace, size_t workspace_bytes, int B, int H, int W, int C,
+                       int search_range, float leaky_slope, int mode, long long out_pixel_stride,
+                       void* stream);
+
+/* Host-buffer variants of the forward ops (what a TF-CPU caller of the layers would use): copy in,
+ * run the device kernels, copy out, batch-sliced so that H2D, kernels and D2H overlap on three
+ * streams.  `device` = CUDA device ordinal. */
+int qpwc_corr_fwd_host(const float* prv, const float* nxt, float* out, int B, int H, int W, int C,
+                       int search_range, float leaky_slope, int device);
+int qpwc_warp_fwd_host(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                       int mode, int device);
+int qpwc_warp_corr_fwd_host(const float* prv, const float* nxt, const float* flow, float* out,
+                            int B, int H, int W, int C, int search_range, float leaky_slope,
+                            int mode, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPWC_H_ */

@@ -1,0 +1,174 @@
+"""ctypes binding of libqpwc.so (include/qpwc.h) and the DLPack -> raw pointer bridge.
+
+Tensors cross the Python/C boundary as DLPack capsules: the producer (PyTorch here; anything that
+implements ``__dlpack__``, e.g. ``tf.experimental.dlpack.to_dlpack`` on the reference side) exports
+a ``DLManagedTensor``; this module reads pointer / shape / strides / device straight out of that
+struct with ctypes and hands plain pointers and sizes to the C ABI.  There is no CPU fallback and no
+alternative backend: if the CUDA library is missing the import of any op fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong,
+                    c_size_t, c_uint8, c_uint16, c_uint32, c_uint64, c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libqpwc.so")
+
+QPWC_OK, QPWC_ERR_INVALID, QPWC_ERR_UNSUPPORTED, QPWC_ERR_CUDA = 0, 1, 2, 3
+WARP_MODES = {"tf": 0, "tfa": 1}
+
+# DLPack device types
+kDLCPU, kDLCUDA, kDLCUDAHost, kDLCUDAManaged = 1, 2, 3, 13
+
+
+class QpwcError(RuntimeError):
+    """Non-zero status from libqpwc (message from qpwc_last_error())."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libqpwc error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded C-ABI library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m qpwcnet_b200.build` "
+            "(qpwcnet_b200 has no CPU or non-CUDA path)")
+    L = ctypes.CDLL(LIB_PATH)
+    fp, vp, i, f, ll = c_void_p, c_void_p, c_int, c_float, c_longlong
+    sigs = {
+        "qpwc_version": ([], c_int),
+        "qpwc_last_error": ([], c_char_p),
+        "qpwc_corr_fwd": ([fp, fp, fp, i, i, i, i, i, f, ll, vp], c_int),
+        "qpwc_corr_bwd": ([fp, fp, fp, fp, fp, fp, i, i, i, i, i, f, ll, vp], c_int),
+        "qpwc_warp_fwd": ([fp, fp, fp, i, i, i, i, i, vp], c_int),
+        "qpwc_warp_bwd": ([fp, fp, fp, fp, fp, i, i, i, i, i, vp], c_int),
+        "qpwc_warp_corr_fwd": ([fp, fp, fp, fp, i, i, i, i, i, f, i, ll, vp], c_int),
+        "qpwc_warp_corr_bwd_workspace": ([i, i, i, i], c_size_t),
+        "qpwc_warp_corr_bwd": ([fp, fp, fp, fp, fp, fp, fp, fp, vp, c_size_t, i, i, i, i, i, f, i, ll, vp], c_int),
+        "qpwc_corr_fwd_host": ([fp, fp, fp, i, i, i, i, i, f, i], c_int),
+        "qpwc_warp_fwd_host": ([fp, fp, fp, i, i, i, i, i, i], c_int),
+        "qpwc_warp_corr_fwd_host": ([fp, fp, fp, fp, i, i, i, i, i, f, i, i], c_int),
+    }
+    for name, (argtypes, restype) in sigs.items():
+        fn = getattr(L, name)          # AttributeError here = header/library mismatch: be loud
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "qpwc_version", "qpwc_last_error", "qpwc_corr_fwd", "qpwc_corr_bwd", "qpwc_warp_fwd",
+    "qpwc_warp_bwd", "qpwc_warp_corr_fwd", "qpwc_warp_corr_bwd_workspace", "qpwc_warp_corr_bwd",
+    "qpwc_corr_fwd_host", "qpwc_warp_fwd_host", "qpwc_warp_corr_fwd_host",
+)
+
+
+def check(rc: int) -> None:
+    if rc != QPWC_OK:
+        msg = lib().qpwc_last_error()
+        raise QpwcError(rc, msg.decode() if msg else "")
+
+
+# --------------------------------------------------------------------------------------- DLPack
+class _DLDevice(Structure):
+    _fields_ = [("device_type", c_int32), ("device_id", c_int32)]
+
+
+class _DLDataType(Structure):
+    _fields_ = [("code", c_uint8), ("bits", c_uint8), ("lanes", c_uint16)]
+
+
+class _DLTensor(Structure):
+    _fields_ = [("data", c_void_p), ("device", _DLDevice), ("ndim", c_int32),
+                ("dtype", _DLDataType), ("shape", POINTER(c_int64)),
+                ("strides", POINTER(c_int64)), ("byte_offset", c_uint64)]
+
+
+class _DLManagedTensor(Structure):
+    _fields_ = [("dl_tensor", _DLTensor), ("manager_ctx", c_void_p), ("deleter", c_void_p)]
+
+
+class _DLPackVersion(Structure):
+    _fields_ = [("major", c_uint32), ("minor", c_uint32)]
+
+
+class _DLManagedTensorVersioned(Structure):
+    _fields_ = [("version", _DLPackVersion), ("manager_ctx", c_void_p), ("deleter", c_void_p),
+                ("flags", c_uint64), ("dl_tensor", _DLTensor)]
+
+
+_capi = ctypes.pythonapi
+_capi.PyCapsule_GetName.restype = c_char_p
+_capi.PyCapsule_GetName.argtypes = [ctypes.py_object]
+_capi.PyCapsule_GetPointer.restype = c_void_p
+_capi.PyCapsule_GetPointer.argtypes = [ctypes.py_object, c_char_p]
+
+
+class DLView:
+    """Pointer/shape/device of a tensor read out of its DLPack capsule.  Holds the capsule (and so
+    the producer's memory) alive for as long as the view lives."""
+
+    __slots__ = ("ptr", "shape", "strides", "device_type", "device_id", "_capsule")
+
+    def __init__(self, capsule):
+        name = _capi.PyCapsule_GetName(capsule)
+        if name == b"dltensor":
+            raw = _capi.PyCapsule_GetPointer(capsule, b"dltensor")
+            t = ctypes.cast(raw, POINTER(_DLManagedTensor)).contents.dl_tensor
+        elif name == b"dltensor_versioned":
+            raw = _capi.PyCapsule_GetPointer(capsule, b"dltensor_versioned")
+            t = ctypes.cast(raw, POINTER(_DLManagedTensorVersioned)).contents.dl_tensor
+        else:
+            raise TypeError(f"not an unconsumed DLPack capsule (name={name!r})")
+        if (t.dtype.code, t.dtype.bits, t.dtype.lanes) != (2, 32, 1):
+            raise TypeError("libqpwc takes float32 tensors "
+                            f"(DLPack dtype code={t.dtype.code} bits={t.dtype.bits})")
+        nd = t.ndim
+        self.shape = tuple(int(t.shape[k]) for k in range(nd))
+        self.strides = None if not t.strides else tuple(int(t.strides[k]) for k in range(nd))
+        self.ptr = (t.data or 0) + int(t.byte_offset)
+        self.device_type = int(t.device.device_type)
+        self.device_id = int(t.device.device_id)
+        self._capsule = capsule
+
+    def is_contiguous(self) -> bool:
+        if self.strides is None:
+            return True
+        expect = 1
+        for n, s in zip(reversed(self.shape), reversed(self.strides)):
+            if n != 1 and s != expect:
+                return False
+            expect *= n
+        return True
+
+    @property
+    def on_cuda(self) -> bool:
+        return self.device_type in (kDLCUDA, kDLCUDAManaged)
+
+    @property
+    def on_host(self) -> bool:
+        return self.device_type in (kDLCPU, kDLCUDAHost)
+
+
+def dlview(x) -> DLView:
+    """DLPack view of a tensor-like (torch.Tensor, or any object with ``__dlpack__``)."""
+    try:
+        import torch
+        if isinstance(x, torch.Tensor):
+            return DLView(torch.utils.dlpack.to_dlpack(x.detach()))
+    except ImportError:  # pragma: no cover
+        pass
+    if hasattr(x, "__dlpack__"):
+        return DLView(x.__dlpack__())
+    raise TypeError(f"cannot export {type(x).__name__} through DLPack")

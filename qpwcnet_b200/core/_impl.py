@@ -1,0 +1,43 @@
+"""Layout plumbing shared by the layer classes and the functors."""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from ..backend import get_axis, image_data_format
+
+
+def resolve_format(data_format):
+    fmt = image_data_format() if data_format is None else data_format
+    get_axis(fmt)  # raises ValueError('Unsupported data format : ...') like the reference
+    return fmt
+
+
+def to_nhwc(x: torch.Tensor, fmt: str) -> torch.Tensor:
+    return x.permute(0, 2, 3, 1) if fmt == "channels_first" else x
+
+
+def from_nhwc(x: torch.Tensor, fmt: str) -> torch.Tensor:
+    return x.permute(0, 3, 1, 2).contiguous() if fmt == "channels_first" else x
+
+
+def cost_volume(inputs, search_range, fmt, leaky_slope=0.1):
+    prv, nxt = inputs
+    out = ops.cost_volume(to_nhwc(prv, fmt), to_nhwc(nxt, fmt), search_range, leaky_slope)
+    return from_nhwc(out, fmt)
+
+
+def warp(inputs, mode, fmt):
+    img, flo = inputs
+    if img.dim() != 4:
+        # tf_warp only defines `is_batch` for rank-4 input (qpwcnet/core/warp.py:75-80)
+        raise ValueError("warp expects batched rank-4 input, got shape {}".format(tuple(img.shape)))
+    out = ops.warp(to_nhwc(img, fmt), to_nhwc(flo, fmt), mode)
+    return from_nhwc(out, fmt)
+
+
+def warp_cost_volume(inputs, mode, search_range, fmt, leaky_slope=0.1):
+    prv, nxt, flo = inputs
+    out = ops.warp_cost_volume(to_nhwc(prv, fmt), to_nhwc(nxt, fmt), to_nhwc(flo, fmt), mode,
+                               search_range, leaky_slope)
+    return from_nhwc(out, fmt)

@@ -1,0 +1,56 @@
+"""Plain-callable twins of the layer classes -- the ones the reference's models actually use
+(qpwcnet/core/non_layers.py:51-158, imported by qpwcnet/core/pwcnet.py:7-17)."""
+from __future__ import annotations
+
+from . import _impl
+from ..backend import get_axis
+
+_get_axis = get_axis
+
+
+class _Functor:
+    def __init__(self, *args, data_format=None, **kwargs):
+        self.data_format = _impl.resolve_format(data_format)
+        self.axis = get_axis(self.data_format)
+
+
+class CostVolume(_Functor):
+    """qpwcnet/core/non_layers.py:51-104."""
+
+    def __init__(self, search_range=4, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.search_range = int(search_range)
+
+    def __call__(self, inputs):
+        return _impl.cost_volume(inputs, self.search_range, self.data_format)
+
+
+class CostVolumeV2(CostVolume):
+    """qpwcnet/core/non_layers.py:107-123."""
+
+
+class Warp(_Functor):
+    """qpwcnet/core/non_layers.py:126-134."""
+
+    mode = "tf"
+
+    def __call__(self, inputs):
+        return _impl.warp(inputs, self.mode, self.data_format)
+
+
+class WarpV2(Warp):
+    """qpwcnet/core/non_layers.py:137-158."""
+
+    mode = "tfa"
+
+
+class WarpCostVolume(_Functor):
+    """Fused UpFlow pair (non_layers.py:377-380); call with ``(prv, nxt, flo)``."""
+
+    def __init__(self, search_range=4, warp_mode="tfa", *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.search_range = int(search_range)
+        self.warp_mode = warp_mode
+
+    def __call__(self, inputs):
+        return _impl.warp_cost_volume(inputs, self.warp_mode, self.search_range, self.data_format)

@@ -1,0 +1,296 @@
+// qpwc_api.cu -- extern "C" entry points of libqpwc.so (declared in include/qpwc.h):
+// argument validation, kernel selection, error plumbing, and the host-buffer (staged) variants.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "qpwc_common.cuh"
+#include "../../include/qpwc.h"
+
+namespace qpwc {
+
+// kernels (qpwc_warp.cu, qpwc_corr_direct.cu, qpwc_corr_tiled.cu)
+int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+int launch_corr_fwd_direct(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t);
+int launch_corr_bwd_direct(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
+// returns QPWC_ERR_UNSUPPORTED (without setting an error) when the shape is outside its domain
+int launch_corr_fwd_tiled(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t);
+int launch_corr_bwd_tiled(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return QPWC_OK;
+}
+
+static int check_shape(const char* fn, int B, int H, int W, int C) {
+  if (B < 0 || H < 0 || W < 0 || C < 0) return set_error(QPWC_ERR_INVALID, "%s: negative dimension (B=%d H=%d W=%d C=%d)", fn, B, H, W, C);
+  if ((long long)H * W >= (1LL << 31) || (long long)H * W * (long long)(C > 0 ? C : 1) >= (1LL << 40))
+    return set_error(QPWC_ERR_INVALID, "%s: image too large (H=%d W=%d C=%d)", fn, H, W, C);
+  return QPWC_OK;
+}
+static bool empty(int B, int H, int W, int C) { return B == 0 || H == 0 || W == 0 || C == 0; }
+
+static int check_ptr(const char* fn, const char* name, const void* p) {
+  if (!p) return set_error(QPWC_ERR_INVALID, "%s: %s is NULL", fn, name);
+  if (reinterpret_cast<uintptr_t>(p) % sizeof(float)) return set_error(QPWC_ERR_INVALID, "%s: %s is not 4-byte aligned", fn, name);
+  return QPWC_OK;
+}
+#define QPWC_TRY(expr) do { const int rc_ = (expr); if (rc_ != QPWC_OK) return rc_; } while (0)
+
+static int check_corr_args(const char* fn, int d, long long ops) {
+  if (d < 1 || d > 32) return set_error(QPWC_ERR_INVALID, "%s: search_range %d outside [1,32]", fn, d);
+  const long long D = (long long)(2 * d + 1) * (2 * d + 1);
+  if (ops < D) return set_error(QPWC_ERR_INVALID, "%s: out_pixel_stride %lld < (2d+1)^2 = %lld", fn, ops, D);
+  return QPWC_OK;
+}
+static int check_mode(const char* fn, int mode, int H, int W) {
+  if (mode != QPWC_WARP_TF && mode != QPWC_WARP_TFA) return set_error(QPWC_ERR_INVALID, "%s: unknown warp mode %d", fn, mode);
+  if (mode == QPWC_WARP_TFA && (H < 2 || W < 2))
+    return set_error(QPWC_ERR_INVALID, "%s: Grid must be at least 2x2 for the tfa bilinear mode (H=%d W=%d)", fn, H, W);
+  return QPWC_OK;
+}
+
+static int corr_fwd_any(const float* prv, const float* nxt, const float* flow, int mode, float* out,
+                        int B, int H, int W, int C, int d, float slope, long long ops, cudaStream_t st) {
+  const int rc = launch_corr_fwd_tiled(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st);
+  if (rc != QPWC_ERR_UNSUPPORTED) return rc;
+  return launch_corr_fwd_direct(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st);
+}
+static int corr_bwd_any(const float* prv, const float* nxt, const float* out, const float* g_out,
+                        float* g_prv, float* g_nxt, int B, int H, int W, int C, int d, float slope,
+                        long long ops, cudaStream_t st) {
+  const int rc = launch_corr_bwd_tiled(prv, nxt, out, g_out, g_prv, g_nxt, B, H, W, C, d, slope, ops, st);
+  if (rc != QPWC_ERR_UNSUPPORTED) return rc;
+  return launch_corr_bwd_direct(prv, nxt, out, g_out, g_prv, g_nxt, B, H, W, C, d, slope, ops, st);
+}
+
+// ------------------------------------------------------------------------------- host staging
+// One workspace per device: NSLOT independent (stream, device buffer) slots.  A slot's stream runs
+// H2D -> kernel -> D2H for one batch slice; different slots overlap (both copy engines + SMs).
+struct HostStage {
+  static const int NSLOT = 3;
+  cudaStream_t stream[NSLOT] = {nullptr, nullptr, nullptr};
+  float* buf[NSLOT] = {nullptr, nullptr, nullptr};
+  size_t cap[NSLOT] = {0, 0, 0};
+  std::mutex mu;
+};
+static HostStage g_stage[16];
+
+static int stage_reserve(HostStage& hs, int slot, size_t bytes) {
+  if (!hs.stream[slot]) {
+    const cudaError_t e = cudaStreamCreateWithFlags(&hs.stream[slot], cudaStreamNonBlocking);
+    if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "host stage: stream create: %s", cudaGetErrorString(e));
+  }
+  if (hs.cap[slot] < bytes) {
+    if (hs.buf[slot]) cudaFree(hs.buf[slot]);
+    hs.buf[slot] = nullptr; hs.cap[slot] = 0;
+    const cudaError_t e = cudaMalloc(&hs.buf[slot], bytes);
+    if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "host stage: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    hs.cap[slot] = bytes;
+  }
+  return QPWC_OK;
+}
+
+// kind: 0 = corr(prv,nxt)  1 = warp(img=a, flow=f)  2 = warp_corr(prv=a, nxt=b, flow=f)
+static int run_host(int kind, const float* a, const float* b, const float* f, float* out, int B,
+                    int H, int W, int C, int d, float slope, int mode, int device) {
+  if (device < 0 || device >= 16) return set_error(QPWC_ERR_INVALID, "host call: device ordinal %d outside [0,16)", device);
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "host call: cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  const size_t D = (size_t)(2 * d + 1) * (2 * d + 1);
+  const size_t px = (size_t)H * W;
+  const size_t n_a = px * C, n_b = (kind == 1) ? 0 : px * C, n_f = (kind == 0) ? 0 : px * 2;
+  const size_t n_o = (kind == 1) ? px * C : px * D;
+  const size_t item = (n_a + n_b + n_f + n_o) * sizeof(float);
+  // slice the batch so that one slice moves >= ~8 MiB (amortises per-slice launch/copy latency)
+  int per = (int)((((size_t)8 << 20) + item - 1) / item);
+  if (per < 1) per = 1;
+  if (per > B) per = B;
+  HostStage& hs = g_stage[device];
+  std::lock_guard<std::mutex> lock(hs.mu);
+  int rc = QPWC_OK, slot = 0;
+  for (int b0 = 0; b0 < B && rc == QPWC_OK; b0 += per, slot = (slot + 1) % HostStage::NSLOT) {
+    const int nb = (B - b0 < per) ? (B - b0) : per;
+    rc = stage_reserve(hs, slot, item * per);
+    if (rc != QPWC_OK) break;
+    cudaStream_t st = hs.stream[slot];
+    float* da = hs.buf[slot];
+    float* db = da + n_a * per;
+    float* df = db + n_b * per;
+    float* dout = df + n_f * per;
+    e = cudaMemcpyAsync(da, a + n_a * b0, n_a * nb * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_b) e = cudaMemcpyAsync(db, b + n_b * b0, n_b * nb * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_f) e = cudaMemcpyAsync(df, f + n_f * b0, n_f * nb * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = set_error(QPWC_ERR_CUDA, "host call: H2D: %s", cudaGetErrorString(e)); break; }
+    if (kind == 0) rc = corr_fwd_any(da, db, nullptr, 0, dout, nb, H, W, C, d, slope, (long long)D, st);
+    else if (kind == 1) rc = launch_warp_fwd(da, df, dout, nb, H, W, C, mode, st);
+    else rc = corr_fwd_any(da, db, df, mode, dout, nb, H, W, C, d, slope, (long long)D, st);
+    if (rc != QPWC_OK) break;
+    e = cudaMemcpyAsync(out + n_o * b0, dout, n_o * nb * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { rc = set_error(QPWC_ERR_CUDA, "host call: D2H: %s", cudaGetErrorString(e)); break; }
+  }
+  for (int s = 0; s < HostStage::NSLOT; ++s)
+    if (hs.stream[s]) {
+      e = cudaStreamSynchronize(hs.stream[s]);
+      if (e != cudaSuccess && rc == QPWC_OK) rc = set_error(QPWC_ERR_CUDA, "host call: sync: %s", cudaGetErrorString(e));
+    }
+  return rc;
+}
+
+}  // namespace qpwc
+
+using namespace qpwc;
+
+extern "C" {
+
+int qpwc_version(void) { return 100; /* 0.1.0 */ }
+const char* qpwc_last_error(void) { return g_err; }
+
+int qpwc_corr_fwd(const float* prv, const float* nxt, float* out, int B, int H, int W, int C,
+                  int search_range, float leaky_slope, long long out_pixel_stride, void* stream) {
+  const char* fn = "qpwc_corr_fwd";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_corr_args(fn, search_range, out_pixel_stride));
+  if (B == 0 || H == 0 || W == 0) return QPWC_OK;
+  if (C == 0) return set_error(QPWC_ERR_INVALID, "%s: C == 0 (mean over an empty channel axis)", fn);
+  QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt)); QPWC_TRY(check_ptr(fn, "out", out));
+  return corr_fwd_any(prv, nxt, nullptr, 0, out, B, H, W, C, search_range, leaky_slope, out_pixel_stride, (cudaStream_t)stream);
+}
+
+int qpwc_corr_bwd(const float* prv, const float* nxt, const float* out, const float* g_out,
+                  float* g_prv, float* g_nxt, int B, int H, int W, int C, int search_range,
+                  float leaky_slope, long long out_pixel_stride, void* stream) {
+  const char* fn = "qpwc_corr_bwd";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_corr_args(fn, search_range, out_pixel_stride));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt)); QPWC_TRY(check_ptr(fn, "out", out));
+  QPWC_TRY(check_ptr(fn, "g_out", g_out)); QPWC_TRY(check_ptr(fn, "g_prv", g_prv)); QPWC_TRY(check_ptr(fn, "g_nxt", g_nxt));
+  return corr_bwd_any(prv, nxt, out, g_out, g_prv, g_nxt, B, H, W, C, search_range, leaky_slope, out_pixel_stride, (cudaStream_t)stream);
+}
+
+int qpwc_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                  int mode, void* stream) {
+  const char* fn = "qpwc_warp_fwd";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
+  if (reinterpret_cast<uintptr_t>(flow) % 8) return set_error(QPWC_ERR_INVALID, "%s: flow must be 8-byte aligned", fn);
+  return launch_warp_fwd(img, flow, out, B, H, W, C, mode, (cudaStream_t)stream);
+}
+
+int qpwc_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
+                  float* g_flow, int B, int H, int W, int C, int mode, void* stream) {
+  const char* fn = "qpwc_warp_bwd";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  if (B == 0 || H == 0 || W == 0) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "g_flow", g_flow));
+  if (reinterpret_cast<uintptr_t>(flow) % 8 || reinterpret_cast<uintptr_t>(g_flow) % 8)
+    return set_error(QPWC_ERR_INVALID, "%s: flow and g_flow must be 8-byte aligned", fn);
+  if (C == 0) {
+    const cudaError_t e = cudaMemsetAsync(g_flow, 0, sizeof(float) * 2 * (size_t)B * H * W, (cudaStream_t)stream);
+    return e == cudaSuccess ? QPWC_OK : set_error(QPWC_ERR_CUDA, "%s: memset: %s", fn, cudaGetErrorString(e));
+  }
+  QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "g_out", g_out)); QPWC_TRY(check_ptr(fn, "g_img", g_img));
+  return launch_warp_bwd(img, flow, g_out, g_img, g_flow, B, H, W, C, mode, (cudaStream_t)stream);
+}
+
+int qpwc_warp_corr_fwd(const float* prv, const float* nxt, const float* flow, float* out, int B,
+                       int H, int W, int C, int search_range, float leaky_slope, int mode,
+                       long long out_pixel_stride, void* stream) {
+  const char* fn = "qpwc_warp_corr_fwd";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_corr_args(fn, search_range, out_pixel_stride));
+  if (B == 0 || H == 0 || W == 0) return QPWC_OK;
+  if (C == 0) return set_error(QPWC_ERR_INVALID, "%s: C == 0", fn);
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt));
+  QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
+  if (reinterpret_cast<uintptr_t>(flow) % 8) return set_error(QPWC_ERR_INVALID, "%s: flow must be 8-byte aligned", fn);
+  return corr_fwd_any(prv, nxt, flow, mode, out, B, H, W, C, search_range, leaky_slope, out_pixel_stride, (cudaStream_t)stream);
+}
+
+size_t qpwc_warp_corr_bwd_workspace(int B, int H, int W, int C) {
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
+  return 2 * sizeof(float) * (size_t)B * H * W * C;  // warped second frame + its gradient
+}
+
+int qpwc_warp_corr_bwd(const float* prv, const float* nxt, const float* flow, const float* out,
+                       const float* g_out, float* g_prv, float* g_nxt, float* g_flow,
+                       void* workspace, size_t workspace_bytes, int B, int H, int W, int C,
+                       int search_range, float leaky_slope, int mode, long long out_pixel_stride,
+                       void* stream) {
+  const char* fn = "qpwc_warp_corr_bwd";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_corr_args(fn, search_range, out_pixel_stride));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt)); QPWC_TRY(check_ptr(fn, "flow", flow));
+  QPWC_TRY(check_ptr(fn, "out", out)); QPWC_TRY(check_ptr(fn, "g_out", g_out)); QPWC_TRY(check_ptr(fn, "g_prv", g_prv));
+  QPWC_TRY(check_ptr(fn, "g_nxt", g_nxt)); QPWC_TRY(check_ptr(fn, "g_flow", g_flow)); QPWC_TRY(check_ptr(fn, "workspace", workspace));
+  if (reinterpret_cast<uintptr_t>(flow) % 8 || reinterpret_cast<uintptr_t>(g_flow) % 8)
+    return set_error(QPWC_ERR_INVALID, "%s: flow and g_flow must be 8-byte aligned", fn);
+  const size_t need = qpwc_warp_corr_bwd_workspace(B, H, W, C);
+  if (workspace_bytes < need) return set_error(QPWC_ERR_INVALID, "%s: workspace %zu B < required %zu B", fn, workspace_bytes, need);
+  if (reinterpret_cast<uintptr_t>(workspace) % 16) return set_error(QPWC_ERR_INVALID, "%s: workspace must be 16-byte aligned", fn);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* nxt_w = static_cast<float*>(workspace);
+  float* g_nxt_w = nxt_w + (size_t)B * H * W * C;
+  // chain rule over the two stages; the warped frame is rebuilt in the workspace, never kept
+  QPWC_TRY(launch_warp_fwd(nxt, flow, nxt_w, B, H, W, C, mode, st));
+  QPWC_TRY(corr_bwd_any(prv, nxt_w, out, g_out, g_prv, g_nxt_w, B, H, W, C, search_range, leaky_slope, out_pixel_stride, st));
+  return launch_warp_bwd(nxt, flow, g_nxt_w, g_nxt, g_flow, B, H, W, C, mode, st);
+}
+
+int qpwc_corr_fwd_host(const float* prv, const float* nxt, float* out, int B, int H, int W, int C,
+                       int search_range, float leaky_slope, int device) {
+  const char* fn = "qpwc_corr_fwd_host";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_corr_args(fn, search_range, (long long)(2 * search_range + 1) * (2 * search_range + 1)));
+  if (B == 0 || H == 0 || W == 0) return QPWC_OK;
+  if (C == 0) return set_error(QPWC_ERR_INVALID, "%s: C == 0", fn);
+  QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt)); QPWC_TRY(check_ptr(fn, "out", out));
+  return run_host(0, prv, nxt, nullptr, out, B, H, W, C, search_range, leaky_slope, 0, device);
+}
+
+int qpwc_warp_fwd_host(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                       int mode, int device) {
+  const char* fn = "qpwc_warp_fwd_host";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
+  return run_host(1, img, nullptr, flow, out, B, H, W, C, 0, 0.f, mode, device);
+}
+
+int qpwc_warp_corr_fwd_host(const float* prv, const float* nxt, const float* flow, float* out,
+                            int B, int H, int W, int C, int search_range, float leaky_slope,
+                            int mode, int device) {
+  const char* fn = "qpwc_warp_corr_fwd_host";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_corr_args(fn, search_range, (long long)(2 * search_range + 1) * (2 * search_range + 1)));
+  if (B == 0 || H == 0 || W == 0) return QPWC_OK;
+  if (C == 0) return set_error(QPWC_ERR_INVALID, "%s: C == 0", fn);
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt));
+  QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
+  return run_host(2, prv, nxt, flow, out, B, H, W, C, search_range, leaky_slope, mode, device);
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+// qpwc_warp.cu -- bilinear backward warp, forward and backward, NHWC fp32.
+//
+// Replaces  tf_warp / Warp   (qpwcnet/core/warp.py:63-153, layers.py:144-168)   -> MODE_TF
+//           WarpV2 / tfa dense_image_warp (qpwcnet/core/layers.py:171-186)        -> MODE_TFA
+//
+// Gather-bound (HBM/L2): algorithmic bytes per output pixel 4*(2C+2) forward, 4*(3C+4) backward.
+// Forward : one thread per (pixel, V-channel vector), V = 4/2/1 by C and pointer alignment; the
+//           V-lanes of one pixel share the flow load (warp broadcast) and the tap set-up.
+// Backward: sub-warp groups of G lanes own one pixel at a time (G = pow2 >= C/V, <= 32); each lane
+//           scatter-adds its channel vector into the four taps (vector red.global.add) and the
+//           flow gradient is reduced across the group with xor-shuffles in a fixed order.
+#include "qpwc_common.cuh"
+
+namespace qpwc {
+
+template <int V> struct Vec;
+template <> struct Vec<4> { typedef float4 type; };
+template <> struct Vec<2> { typedef float2 type; };
+template <> struct Vec<1> { typedef float type; };
+
+template <int V> __device__ __forceinline__ void vload(const float* p, float (&v)[V]);
+template <> __device__ __forceinline__ void vload<4>(const float* p, float (&v)[4]) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void vload<2>(const float* p, float (&v)[2]) {
+  const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+  v[0] = t.x; v[1] = t.y;
+}
+template <> __device__ __forceinline__ void vload<1>(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
+
+template <int V> __device__ __forceinline__ void vstore(float* p, const float (&v)[V]);
+template <> __device__ __forceinline__ void vstore<4>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void vstore<2>(float* p, const float (&v)[2]) {
+  *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+}
+template <> __device__ __forceinline__ void vstore<1>(float* p, const float (&v)[1]) { *p = v[0]; }
+
+template <int V> __device__ __forceinline__ void vatomic_add(float* p, const float (&v)[V]);
+template <> __device__ __forceinline__ void vatomic_add<4>(float* p, const float (&v)[4]) {
+#ifdef QPWC_EMU
+  for (int k = 0; k < 4; ++k) atomicAdd(p + k, v[k]);
+#else
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));  // red.global.add.v4.f32
+#endif
+}
+template <> __device__ __forceinline__ void vatomic_add<2>(float* p, const float (&v)[2]) {
+#ifdef QPWC_EMU
+  for (int k = 0; k < 2; ++k) atomicAdd(p + k, v[k]);
+#else
+  atomicAdd(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+#endif
+}
+template <> __device__ __forceinline__ void vatomic_add<1>(float* p, const float (&v)[1]) { atomicAdd(p, v[0]); }
+
+// ------------------------------------------------------------------------------------------ fwd
+template <int MODE, int V>
+__global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__ img,
+                                                       const float* __restrict__ flow,
+                                                       float* __restrict__ out, int H, int W, int C,
+                                                       long long total /* B*H*W*(C/V) */) {
+  const int CV = C / V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int cv = (int)(idx % CV);
+    const long long pix = idx / CV;  // b*H*W + i*W + j
+    const int j = (int)(pix % W);
+    const long long bi = pix / W;
+    const int i = (int)(bi % H);
+    const long long b = bi / H;
+    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);  // ch0 = x, ch1 = y
+    const Taps t = make_taps<MODE>(i, j, f.x, f.y, H, W);
+    const float* base = img + (size_t)b * H * W * C + (size_t)cv * V;
+    float v00[V], v01[V], v10[V], v11[V], o[V];
+    vload<V>(base + (size_t)t.o00 * C, v00);
+    vload<V>(base + (size_t)t.o01 * C, v01);
+    vload<V>(base + (size_t)t.o10 * C, v10);
+    vload<V>(base + (size_t)t.o11 * C, v11);
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = blend<MODE>(t, v00[k], v01[k], v10[k], v11[k]);
+    vstore<V>(out + (size_t)pix * C + (size_t)cv * V, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ bwd
+// G lanes per pixel (power of two, <= 32).  Lane l of a group handles channel vectors l, l+G, ...
+template <int MODE, int V>
+__global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__ img,
+                                                       const float* __restrict__ flow,
+                                                       const float* __restrict__ g_out,
+                                                       float* __restrict__ g_img,
+                                                       float* __restrict__ g_flow, int H, int W, int C,
+                                                       int G, long long npix) {
+  const int CV = C / V;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);           // lane inside the group
+  const int groups_per_block = blockDim.x / G;
+  const int gid = threadIdx.x / G;
+  const long long gstride = (long long)gridDim.x * groups_per_block;
+  // every lane of a warp runs the same number of iterations (shuffles below need the full warp)
+  const long long iters = cdivll(npix, gstride);
+  for (long long it = 0; it < iters; ++it) {
+    const long long pix = (long long)blockIdx.x * groups_per_block + gid + it * gstride;
+    const bool live = pix < npix;
+    float gx = 0.f, gy = 0.f;
+    bool px = true, py = true;
+    if (live) {
+      const int j = (int)(pix % W);
+      const long long bi = pix / W;
+      const int i = (int)(bi % H);
+      const long long b = bi / H;
+      const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);
+      Taps t;
+      if (MODE == QPWC_MODE_TF) t = taps_tf(i, j, f.x, f.y, H, W);
+      else t = taps_tfa(i, j, f.x, f.y, H, W, &px, &py);
+      const size_t boff = (size_t)b * H * W * C;
+      for (int cv = gl; cv < CV; cv += G) {
+        const size_t co = (size_t)cv * V;
+        float v00[V], v01[V], v10[V], v11[V], g[V], a00[V], a01[V], a10[V], a11[V];
+        vload<V>(img + boff + (size_t)t.o00 * C + co, v00);
+        vload<V>(img + boff + (size_t)t.o01 * C + co, v01);
+        vload<V>(img + boff + (size_t)t.o10 * C + co, v10);
+        vload<V>(img + boff + (size_t)t.o11 * C + co, v11);
+        vload<V>(g_out + (size_t)pix * C + co, g);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          if (MODE == QPWC_MODE_TF) {
+            // gather_nd grad: scatter w*g into the four clipped taps
+            a00[k] = t.w00 * g[k]; a10[k] = t.w10 * g[k]; a01[k] = t.w01 * g[k]; a11[k] = t.w11 * g[k];
+          } else {
+            const float ax = t.w00, ay = t.w01;
+            const float top = __fadd_rn(__fmul_rn(ax, __fsub_rn(v01[k], v00[k])), v00[k]);
+            const float bot = __fadd_rn(__fmul_rn(ax, __fsub_rn(v11[k], v10[k])), v10[k]);
+            gy += g[k] * (bot - top);
+            const float g_bot = ay * g[k];
+            const float g_top = g[k] - g_bot;
+            gx += g_top * (v01[k] - v00[k]) + g_bot * (v11[k] - v10[k]);
+            const float g_tr = ax * g_top, g_br = ax * g_bot;
+            a01[k] = g_tr; a00[k] = g_top - g_tr; a11[k] = g_br; a10[k] = g_bot - g_br;
+          }
+        }
+        if (MODE == QPWC_MODE_TF) {
+          // d/dx = g*[-(y1-y)Ia - (y-y0)Ib + (y1-y)Ic + (y-y0)Id], d/dy analogous (Ia=v00 Ib=v10
+          // Ic=v01 Id=v11); the 1-D factors are recomputed exactly as taps_tf does.
+          const float x = __fadd_rn((float)j, f.x), y = __fadd_rn((float)i, f.y);
+          const int x0 = t.o00 % W, y0 = t.o00 / W, x1 = t.o11 % W, y1 = t.o11 / W;
+          const float ax1 = __fsub_rn((float)x1, x), ax0 = __fsub_rn(x, (float)x0);
+          const float ay1 = __fsub_rn((float)y1, y), ay0 = __fsub_rn(y, (float)y0);
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            gx += g[k] * (((-ay1 * v00[k] + -ay0 * v10[k]) + ay1 * v01[k]) + ay0 * v11[k]);
+            gy += g[k] * (((-ax1 * v00[k] + ax1 * v10[k]) + -ax0 * v01[k]) + ax0 * v11[k]);
+          }
+        }
+        vatomic_add<V>(g_img + boff + (size_t)t.o00 * C + co, a00);
+        vatomic_add<V>(g_img + boff + (size_t)t.o01 * C + co, a01);
+        vatomic_add<V>(g_img + boff + (size_t)t.o10 * C + co, a10);
+        vatomic_add<V>(g_img + boff + (size_t)t.o11 * C + co, a11);
+      }
+    }
+    // fixed-order butterfly over the G lanes of the group
+    for (int o = G >> 1; o > 0; o >>= 1) {
+      gx += __shfl_xor_sync(0xffffffffu, gx, o);
+      gy += __shfl_xor_sync(0xffffffffu, gy, o);
+    }
+    if (live && gl == 0) {
+      reinterpret_cast<float2*>(g_flow)[pix] = make_float2(px ? gx : 0.f, py ? gy : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ launchers
+static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+static int pick_vec(int C, const void* a, const void* b, const void* c = nullptr, const void* d = nullptr) {
+  const void* ps[4] = {a, b, c, d};
+  int v = (C % 4 == 0) ? 4 : (C % 2 == 0 ? 2 : 1);
+  for (int k = 0; k < 4; ++k)
+    if (ps[k]) while (v > 1 && !aligned(ps[k], sizeof(float) * v)) v >>= 1;
+  return v;
+}
+
+template <int MODE, int V>
+static void run_warp_fwd(const float* img, const float* flow, float* out, int H, int W, int C,
+                         long long total, cudaStream_t stream) {
+  const int block = 256;
+  const long long want = cdivll(total, block);
+  const int grid = (int)(want < 148LL * 32 ? want : 148LL * 32);
+  auto k = warp_fwd_kernel<MODE, V>;
+  QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, out, H, W, C, total);
+}
+
+int launch_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                    int mode, cudaStream_t stream) {
+  const int V = pick_vec(C, img, out);
+  const long long total = (long long)B * H * W * (C / V);
+  if (total == 0) return QPWC_OK;
+  if (mode == QPWC_MODE_TF) {
+    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, out, H, W, C, total, stream);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, out, H, W, C, total, stream);
+    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, out, H, W, C, total, stream);
+  } else {
+    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, out, H, W, C, total, stream);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, out, H, W, C, total, stream);
+    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, out, H, W, C, total, stream);
+  }
+  return check_launch("warp_fwd");
+}
+
+template <int MODE, int V>
+static void run_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
+                         float* g_flow, int H, int W, int C, long long npix, cudaStream_t stream) {
+  const int CV = C / V;
+  int G = 1;
+  while (G < CV && G < 32) G <<= 1;
+  const int block = 256;
+  const int groups_per_block = block / G;
+  const long long want = cdivll(npix, groups_per_block);
+  const int grid = (int)(want < 148LL * 16 ? want : 148LL * 16);
+  auto k = warp_bwd_kernel<MODE, V>;
+  QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, g_out, g_img, g_flow, H, W, C, G, npix);
+}
+
+int launch_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
+                    float* g_flow, int B, int H, int W, int C, int mode, cudaStream_t stream) {
+  const long long npix = (long long)B * H * W;
+  if (npix == 0) return QPWC_OK;
+  cudaError_t e = cudaMemsetAsync(g_img, 0, sizeof(float) * (size_t)npix * C, stream);
+  if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "warp_bwd: memset g_img: %s", cudaGetErrorString(e));
+  const int V = pick_vec(C, img, g_out, g_img);
+  if (mode == QPWC_MODE_TF) {
+    if (V == 4) run_warp_bwd<QPWC_MODE_TF, 4>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
+    else if (V == 2) run_warp_bwd<QPWC_MODE_TF, 2>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
+    else run_warp_bwd<QPWC_MODE_TF, 1>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
+  } else {
+    if (V == 4) run_warp_bwd<QPWC_MODE_TFA, 4>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
+    else if (V == 2) run_warp_bwd<QPWC_MODE_TFA, 2>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
+    else run_warp_bwd<QPWC_MODE_TFA, 1>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
+  }
+  return check_launch("warp_bwd");
+}
+
+}  // namespace qpwc

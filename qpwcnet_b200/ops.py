@@ -1,0 +1,278 @@
+"""Functional ops over libqpwc: cost volume, warp, fused warp->cost volume (NHWC, fp32).
+
+``torch.autograd.Function``s whose forward/backward hand DLPack-exported pointers to the C ABI on
+torch's current CUDA stream.  CPU (host) tensors are routed to the library's host-buffer entry
+points (H2D -> kernels -> D2H, pipelined inside the library); they are inference-only.  Nothing
+here computes on the CPU.
+
+Reference semantics (citations relative to the reference checkout):
+  cost_volume       qpwcnet/core/layers.py:72-100, 117-132
+  warp mode 'tf'    qpwcnet/core/warp.py:63-153        mode 'tfa'  qpwcnet/core/layers.py:171-186
+  warp_cost_volume  qpwcnet/core/non_layers.py:377-380
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+from ._cabi import WARP_MODES, check, dlview, lib
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _prep(t: torch.Tensor, name: str, last: int | None = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if t.dim() != 4:
+        raise ValueError(f"{name}: expected a rank-4 NHWC tensor, got shape {tuple(t.shape)}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    if last is not None and t.shape[-1] != last:
+        raise ValueError(f"{name}: last dimension must be {last}, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _same(a: torch.Tensor, b: torch.Tensor, what: str):
+    if a.shape != b.shape:
+        raise ValueError(f"{what}: shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+    if a.device != b.device:
+        raise ValueError(f"{what}: device mismatch {a.device} vs {b.device}")
+
+
+def _views(*ts):
+    vs = [dlview(t) for t in ts]
+    for v in vs:
+        if not v.is_contiguous():
+            raise ValueError("libqpwc needs dense NHWC tensors")
+    return vs
+
+
+def _mode(mode) -> int:
+    if mode in WARP_MODES:
+        return WARP_MODES[mode]
+    if mode in (0, 1):
+        return int(mode)
+    raise ValueError(f"warp mode must be 'tf' or 'tfa', got {mode!r}")
+
+
+# ------------------------------------------------------------------------------- raw launchers
+def _corr_fwd(prv, nxt, d, slope, out=None, out_stride=None):
+    B, H, W, C = prv.shape
+    D = (2 * d + 1) ** 2
+    ops = D if out_stride is None else int(out_stride)
+    if out is None:
+        out = torch.empty((B, H, W, ops), dtype=torch.float32, device=prv.device)
+    vp, vn, vo = _views(prv, nxt, out)
+    if vp.on_cuda:
+        with torch.cuda.device(prv.device):
+            check(lib().qpwc_corr_fwd(vp.ptr, vn.ptr, vo.ptr, B, H, W, C, d, slope, ops,
+                                      _stream_ptr(prv.device)))
+    else:
+        if ops != D:
+            raise ValueError("strided output is only available on the device path")
+        check(lib().qpwc_corr_fwd_host(vp.ptr, vn.ptr, vo.ptr, B, H, W, C, d, slope,
+                                       torch.cuda.current_device()))
+    return out
+
+
+def _corr_bwd(prv, nxt, out, g_out, d, slope):
+    B, H, W, C = prv.shape
+    ops = out.shape[-1]
+    g_prv = torch.empty_like(prv)
+    g_nxt = torch.empty_like(nxt)
+    vp, vn, vo, vg, vgp, vgn = _views(prv, nxt, out, g_out, g_prv, g_nxt)
+    with torch.cuda.device(prv.device):
+        check(lib().qpwc_corr_bwd(vp.ptr, vn.ptr, vo.ptr, vg.ptr, vgp.ptr, vgn.ptr, B, H, W, C, d,
+                                  slope, ops, _stream_ptr(prv.device)))
+    return g_prv, g_nxt
+
+
+def _warp_fwd(img, flow, mode):
+    B, H, W, C = img.shape
+    out = torch.empty_like(img)
+    vi, vf, vo = _views(img, flow, out)
+    if vi.on_cuda:
+        with torch.cuda.device(img.device):
+            check(lib().qpwc_warp_fwd(vi.ptr, vf.ptr, vo.ptr, B, H, W, C, mode,
+                                      _stream_ptr(img.device)))
+    else:
+        check(lib().qpwc_warp_fwd_host(vi.ptr, vf.ptr, vo.ptr, B, H, W, C, mode,
+                                       torch.cuda.current_device()))
+    return out
+
+
+def _warp_bwd(img, flow, g_out, mode):
+    B, H, W, C = img.shape
+    g_img = torch.empty_like(img)
+    g_flow = torch.empty_like(flow)
+    vi, vf, vg, vgi, vgf = _views(img, flow, g_out, g_img, g_flow)
+    with torch.cuda.device(img.device):
+        check(lib().qpwc_warp_bwd(vi.ptr, vf.ptr, vg.ptr, vgi.ptr, vgf.ptr, B, H, W, C, mode,
+                                  _stream_ptr(img.device)))
+    return g_img, g_flow
+
+
+def _warp_corr_fwd(prv, nxt, flow, mode, d, slope, out=None, out_stride=None):
+    B, H, W, C = prv.shape
+    D = (2 * d + 1) ** 2
+    ops = D if out_stride is None else int(out_stride)
+    if out is None:
+        out = torch.empty((B, H, W, ops), dtype=torch.float32, device=prv.device)
+    vp, vn, vf, vo = _views(prv, nxt, flow, out)
+    if vp.on_cuda:
+        with torch.cuda.device(prv.device):
+            check(lib().qpwc_warp_corr_fwd(vp.ptr, vn.ptr, vf.ptr, vo.ptr, B, H, W, C, d, slope,
+                                           mode, ops, _stream_ptr(prv.device)))
+    else:
+        if ops != D:
+            raise ValueError("strided output is only available on the device path")
+        check(lib().qpwc_warp_corr_fwd_host(vp.ptr, vn.ptr, vf.ptr, vo.ptr, B, H, W, C, d, slope,
+                                            mode, torch.cuda.current_device()))
+    return out
+
+
+def _warp_corr_bwd(prv, nxt, flow, out, g_out, mode, d, slope):
+    B, H, W, C = prv.shape
+    ops = out.shape[-1]
+    g_prv, g_nxt, g_flow = torch.empty_like(prv), torch.empty_like(nxt), torch.empty_like(flow)
+    nbytes = int(lib().qpwc_warp_corr_bwd_workspace(B, H, W, C))
+    ws = torch.empty((max(nbytes, 16) + 3) // 4, dtype=torch.float32, device=prv.device)
+    vp, vn, vf, vo, vg, vgp, vgn, vgf, vw = _views(prv, nxt, flow, out, g_out, g_prv, g_nxt, g_flow, ws)
+    with torch.cuda.device(prv.device):
+        check(lib().qpwc_warp_corr_bwd(vp.ptr, vn.ptr, vf.ptr, vo.ptr, vg.ptr, vgp.ptr, vgn.ptr,
+                                       vgf.ptr, vw.ptr, ws.numel() * 4, B, H, W, C, d, slope, mode,
+                                       ops, _stream_ptr(prv.device)))
+    return g_prv, g_nxt, g_flow
+
+
+def _no_host_grad(*ts):
+    if any(t.requires_grad and not t.is_cuda for t in ts) and torch.is_grad_enabled():
+        raise RuntimeError("host (CPU) tensors take the inference-only staged path of libqpwc; "
+                           "move them to the GPU to differentiate")
+
+
+# -------------------------------------------------------------------------------------- autograd
+class _CostVolume(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prv, nxt, d, slope):
+        out = _corr_fwd(prv, nxt, d, slope)
+        ctx.save_for_backward(prv, nxt, out)
+        ctx.cfg = (d, slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        prv, nxt, out = ctx.saved_tensors
+        d, slope = ctx.cfg
+        g_prv, g_nxt = _corr_bwd(prv, nxt, out, g_out.contiguous(), d, slope)
+        return g_prv, g_nxt, None, None
+
+
+class _Warp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, flow, mode):
+        out = _warp_fwd(img, flow, mode)
+        ctx.save_for_backward(img, flow)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        img, flow = ctx.saved_tensors
+        g_img, g_flow = _warp_bwd(img, flow, g_out.contiguous(), ctx.mode)
+        return g_img, g_flow, None
+
+
+class _WarpCostVolume(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prv, nxt, flow, mode, d, slope):
+        out = _warp_corr_fwd(prv, nxt, flow, mode, d, slope)
+        ctx.save_for_backward(prv, nxt, flow, out)
+        ctx.cfg = (mode, d, slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        prv, nxt, flow, out = ctx.saved_tensors
+        mode, d, slope = ctx.cfg
+        g = _warp_corr_bwd(prv, nxt, flow, out, g_out.contiguous(), mode, d, slope)
+        return g[0], g[1], g[2], None, None, None
+
+
+# ------------------------------------------------------------------------------------ public API
+def cost_volume(prv, nxt, search_range: int = 4, leaky_slope: float = 0.1):
+    """``leaky_relu(mean_c(prv * shift(nxt, di, dj)))`` for all |di|,|dj| <= search_range; NHWC in,
+    ``(B,H,W,(2d+1)^2)`` out, channel = (di+d)*(2d+1)+(dj+d)."""
+    prv, nxt = _prep(prv, "prv"), _prep(nxt, "nxt")
+    _same(prv, nxt, "cost_volume(prv, nxt)")
+    _no_host_grad(prv, nxt)
+    if not prv.is_cuda:
+        return _corr_fwd(prv, nxt, int(search_range), float(leaky_slope))
+    return _CostVolume.apply(prv, nxt, int(search_range), float(leaky_slope))
+
+
+def warp(img, flow, mode="tfa"):
+    """Bilinear backward warp: ``out[b,i,j] = img[b, i+flow[...,1], j+flow[...,0]]``; ``mode`` picks
+    the reference's border rule ('tf' = Warp/tf_warp, 'tfa' = WarpV2)."""
+    img = _prep(img, "img")
+    flow = _prep(flow, "flow", last=2)
+    if img.shape[:3] != flow.shape[:3] or img.device != flow.device:
+        raise ValueError(f"warp: img {tuple(img.shape)}@{img.device} vs flow {tuple(flow.shape)}@{flow.device}")
+    m = _mode(mode)
+    if m == 1 and (img.shape[1] < 2 or img.shape[2] < 2):
+        raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
+    _no_host_grad(img, flow)
+    if not img.is_cuda:
+        return _warp_fwd(img, flow, m)
+    return _Warp.apply(img, flow, m)
+
+
+def warp_cost_volume(prv, nxt, flow, mode="tfa", search_range: int = 4, leaky_slope: float = 0.1):
+    """Fused ``cost_volume(prv, warp(nxt, flow))`` (UpFlow): one kernel, the warped frame never
+    reaches HBM."""
+    prv, nxt = _prep(prv, "prv"), _prep(nxt, "nxt")
+    flow = _prep(flow, "flow", last=2)
+    _same(prv, nxt, "warp_cost_volume(prv, nxt)")
+    if prv.shape[:3] != flow.shape[:3] or prv.device != flow.device:
+        raise ValueError(f"warp_cost_volume: prv {tuple(prv.shape)} vs flow {tuple(flow.shape)}")
+    m = _mode(mode)
+    if m == 1 and (prv.shape[1] < 2 or prv.shape[2] < 2):
+        raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
+    _no_host_grad(prv, nxt, flow)
+    if not prv.is_cuda:
+        return _warp_corr_fwd(prv, nxt, flow, m, int(search_range), float(leaky_slope))
+    return _WarpCostVolume.apply(prv, nxt, flow, m, int(search_range), float(leaky_slope))
+
+
+def cost_volume_into(out, prv, nxt, search_range: int = 4, leaky_slope: float = 0.1):
+    """Inference-only ``cost_volume`` into a caller-owned ``out`` of shape (B,H,W,S), S >= (2d+1)^2:
+    the cost volume lands in channels [0, (2d+1)^2) of every pixel (concat-buffer epilogue,
+    qpwcnet/core/non_layers.py:335-336).  Host tensors take the staged path (S must be dense)."""
+    prv, nxt = _prep(prv, "prv"), _prep(nxt, "nxt")
+    _same(prv, nxt, "cost_volume_into(prv, nxt)")
+    _check_out(out, prv)
+    return _corr_fwd(prv, nxt, int(search_range), float(leaky_slope), out=out, out_stride=out.shape[-1])
+
+
+def warp_cost_volume_into(out, prv, nxt, flow, mode="tfa", search_range: int = 4,
+                          leaky_slope: float = 0.1):
+    """Inference-only fused ``warp_cost_volume`` into a caller-owned (possibly wider) ``out``."""
+    prv, nxt = _prep(prv, "prv"), _prep(nxt, "nxt")
+    flow = _prep(flow, "flow", last=2)
+    _same(prv, nxt, "warp_cost_volume_into(prv, nxt)")
+    _check_out(out, prv)
+    return _warp_corr_fwd(prv, nxt, flow, _mode(mode), int(search_range), float(leaky_slope),
+                          out=out, out_stride=out.shape[-1])
+
+
+def _check_out(out, prv):
+    if out.dtype != torch.float32 or out.dim() != 4 or out.shape[:3] != prv.shape[:3] \
+            or out.device != prv.device or not out.is_contiguous():
+        raise ValueError(f"out must be a dense float32 (B,H,W,S) tensor on {prv.device}, "
+                         f"got {tuple(out.shape)} {out.dtype} @ {out.device}")
+
+
+def library_version() -> int:
+    return int(lib().qpwc_version())

@@ -1,0 +1,102 @@
+"""Benchmark harness: the cost-volume / warp call pattern of the reference's flow network at the
+named shapes (BASELINE.json configs 2-5), with synthetic inputs.
+
+``flower()`` (qpwcnet/core/pwcnet.py:28-67) runs, per forward pass, one plain cost volume at 1/32
+scale (``Flow``, non_layers.py:332-338) and four warp -> cost-volume pairs at 1/16 .. 1/2 scale
+(``UpFlow``, non_layers.py:366-387).  Feature widths follow the reference encoder/decoder
+(pwcnet.py:145,179-207): 256 @1/32, then decoder outputs 256,128,64,32 @ 1/16,1/8,1/4,1/2.  The
+network needs H, W divisible by 32, so 436x1024 is padded to 448x1024.
+The conv stacks between the calls are out of scope (cuDNN territory); the harness feeds each level
+synthetic features and flow of the right shape, which is exactly what the hot path sees.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+
+LEVEL_CHANNELS = (256, 256, 128, 64, 32)      # coarse -> fine
+LEVEL_SCALES = (32, 16, 8, 4, 2)
+
+
+@dataclass(frozen=True)
+class Level:
+    H: int
+    W: int
+    C: int
+    fused: bool        # False: Flow (plain cost volume); True: UpFlow (warp -> cost volume)
+
+
+def levels_for(height: int, width: int):
+    Hp, Wp = -(-height // 32) * 32, -(-width // 32) * 32
+    return tuple(Level(Hp // s, Wp // s, c, k > 0)
+                 for k, (s, c) in enumerate(zip(LEVEL_SCALES, LEVEL_CHANNELS)))
+
+
+def algorithmic_bytes(level: Level, B: int, d: int = 4) -> int:
+    """4*(2C + D) per pixel (plain), 4*(2C + 2 + D) per pixel (fused)."""
+    D = (2 * d + 1) ** 2
+    return 4 * (2 * level.C + D + (2 if level.fused else 0)) * level.H * level.W * B
+
+
+def algorithmic_flops(level: Level, B: int, d: int = 4) -> int:
+    return 2 * (2 * d + 1) ** 2 * level.C * level.H * level.W * B
+
+
+class PyramidWorkload:
+    """Synthetic inputs + output buffers for one batch of frame pairs, on ``device`` ('cuda:N') or
+    in pinned host memory (``device='cpu'``), and the 5-call hot path over them."""
+
+    def __init__(self, height=436, width=1024, batch=8, search_range=4, device="cuda", seed=0,
+                 flow_sigma=None, warp_mode="tfa"):
+        self.levels = levels_for(height, width)
+        self.B, self.d, self.mode = batch, search_range, warp_mode
+        self.D = (2 * search_range + 1) ** 2
+        sigma = search_range / 2.0 if flow_sigma is None else flow_sigma
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        on_host = torch.device(device).type == "cpu"
+        self.inputs, self.outputs = [], []
+        for lv in self.levels:
+            shp = (batch, lv.H, lv.W, lv.C)
+            prv = torch.randn(shp, generator=g)
+            nxt = torch.randn(shp, generator=g)
+            flo = torch.randn((batch, lv.H, lv.W, 2), generator=g) * sigma if lv.fused else None
+            out = torch.empty((batch, lv.H, lv.W, self.D))
+            if on_host:
+                ts = [t.pin_memory() if t is not None else None for t in (prv, nxt, flo)]
+                out = out.pin_memory()
+            else:
+                ts = [t.to(device) if t is not None else None for t in (prv, nxt, flo)]
+                out = out.to(device)
+            self.inputs.append(tuple(ts))
+            self.outputs.append(out)
+
+    # bytes per step
+    def h2d_bytes(self):
+        return sum(sum(t.numel() * 4 for t in ts if t is not None) for ts in self.inputs)
+
+    def d2h_bytes(self):
+        return sum(o.numel() * 4 for o in self.outputs)
+
+    def algorithmic_bytes(self):
+        return sum(algorithmic_bytes(lv, self.B, self.d) for lv in self.levels)
+
+    def algorithmic_flops(self):
+        return sum(algorithmic_flops(lv, self.B, self.d) for lv in self.levels)
+
+    def run_level(self, k):
+        lv = self.levels[k]
+        prv, nxt, flo = self.inputs[k]
+        if lv.fused:
+            return ops.warp_cost_volume_into(self.outputs[k], prv, nxt, flo, self.mode, self.d)
+        return ops.cost_volume_into(self.outputs[k], prv, nxt, self.d)
+
+    def step(self):
+        """One pass of the hot path over the batch: 1 cost volume + 4 fused warp->cost volumes."""
+        for k in range(len(self.levels)):
+            self.run_level(k)
+        return self.outputs
+
+    launches_per_step = 5

@@ -1,0 +1,93 @@
+"""Runs the CUDA kernel bodies on the CPU emulation harness (tests/emu) and checks them against the
+oracle.  This validates index arithmetic / tiling / epilogues in the GPU-less container; the real
+parity tests (tests/test_gpu_parity.py, -m gpu) run the sm_100a build through the C ABI."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import emu_lib  # noqa: E402
+
+
+def rng(s):
+    return np.random.default_rng(s)
+
+
+def cv_tol(ref64, prv, nxt):
+    return 1e-5 * np.abs(ref64).max()
+
+
+@pytest.mark.parametrize("B,H,W,C,d", [(2, 6, 7, 3, 4), (1, 5, 9, 8, 2), (1, 4, 5, 5, 1)])
+def test_emu_corr_fwd_direct(B, H, W, C, d):
+    r = rng(0)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    ref = oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), d)
+    got = emu_lib.corr_fwd(prv, nxt, d)
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    got_s = emu_lib.corr_fwd(prv, nxt, d, ops=(2 * d + 1) ** 2 + 5)
+    np.testing.assert_array_equal(got_s[..., :(2 * d + 1) ** 2], got)
+    assert np.isnan(got_s[..., (2 * d + 1) ** 2:]).all()      # padding lanes untouched
+
+
+@pytest.mark.parametrize("B,H,W,C,d", [(2, 6, 7, 3, 4), (1, 5, 9, 8, 2)])
+def test_emu_corr_bwd_direct(B, H, W, C, d):
+    r = rng(1)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    out = oracle.cost_volume(prv, nxt, d)
+    g = r.standard_normal(out.shape).astype(np.float32)
+    gp, gn = oracle.cost_volume_bwd(*(a.astype(np.float64) for a in (prv, nxt, out, g)), d)
+    gp2, gn2 = emu_lib.corr_bwd(prv, nxt, out, g, d)
+    assert np.abs(gp2 - gp).max() <= 1e-5 * np.abs(gp).max()
+    assert np.abs(gn2 - gn).max() <= 1e-5 * np.abs(gn).max()
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,H,W,C", [(2, 6, 7, 3), (1, 5, 9, 8), (1, 4, 6, 2), (1, 3, 5, 12)])
+def test_emu_warp_fwd_bwd(mode, B, H, W, C):
+    r = rng(2)
+    img = r.random((B, H, W, C)).astype(np.float32)
+    flow = (r.standard_normal((B, H, W, 2)) * 2.5).astype(np.float32)
+    np.testing.assert_array_equal(emu_lib.warp_fwd(img, flow, mode), oracle.warp(img, flow, mode))
+    g = r.standard_normal(img.shape).astype(np.float32)
+    gi, gf = oracle.warp_bwd(*(a.astype(np.float64) for a in (img, flow, g)), mode)
+    gi2, gf2 = emu_lib.warp_bwd(img, flow, g, mode)
+    np.testing.assert_allclose(gi2, gi, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(gf2, gf, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+def test_emu_fused_fwd_bwd_direct(mode):
+    r = rng(3)
+    B, H, W, C, d = 1, 6, 7, 3, 4
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    flo = (r.standard_normal((B, H, W, 2)) * 2).astype(np.float32)
+    a64 = [a.astype(np.float64) for a in (prv, nxt, flo)]
+    ref = oracle.warp_cost_volume(*a64, mode, d)
+    got = emu_lib.warp_corr_fwd(prv, nxt, flo, mode, d)
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    g = r.standard_normal(ref.shape).astype(np.float32)
+    gp, gn, gf = oracle.warp_cost_volume_bwd(*a64, g.astype(np.float64), mode, d)
+    gp2, gn2, gf2 = emu_lib.warp_corr_bwd(prv, nxt, flo, got, g, mode, d)
+    assert np.abs(gp2 - gp).max() <= 1e-5 * np.abs(gp).max()
+    assert np.abs(gn2 - gn).max() <= 1e-5 * max(np.abs(gn).max(), 1.0)
+    assert np.abs(gf2 - gf).max() <= 1e-5 * max(np.abs(gf).max(), 1.0)
+
+
+def test_emu_host_entry_and_errors():
+    r = rng(4)
+    prv = r.standard_normal((5, 4, 5, 3)).astype(np.float32)
+    nxt = r.standard_normal((5, 4, 5, 3)).astype(np.float32)
+    np.testing.assert_array_equal(emu_lib.corr_fwd_host(prv, nxt, 2), emu_lib.corr_fwd(prv, nxt, 2))
+    with pytest.raises(RuntimeError, match="search_range"):
+        emu_lib.corr_fwd(prv, nxt, 0)
+    with pytest.raises(RuntimeError, match="out_pixel_stride"):
+        emu_lib.corr_fwd(prv, nxt, 4, ops=80)
+    with pytest.raises(RuntimeError, match="2x2"):
+        emu_lib.warp_fwd(np.zeros((1, 1, 4, 2), np.float32), np.zeros((1, 1, 4, 2), np.float32), "tfa")

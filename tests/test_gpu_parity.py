@@ -1,0 +1,330 @@
+"""GPU parity tests proper: the sm_100a build of libqpwc, called through the C ABI (ctypes + DLPack
+via qpwcnet_b200.ops / the drop-in layers), against the CPU oracle and the committed golden
+fixtures.  Tolerances (BASELINE.json north_star): cost volume <= 1e-5 relative (evaluated as
+max|delta| <= 1e-5 * max|ref| against the fp64 oracle), warp forward/backward <= 1e-6 absolute
+(flow gradients, which sum C terms, are graded condition-aware: 1e-6 * max(1, sum_c |term|))."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from qpwcnet_b200 import _cabi, ops
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda:0"
+
+
+def rng(s):
+    return np.random.default_rng(s)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(DEV)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def assert_rel(got, ref64, rel=1e-5, floor=0.0):
+    scale = max(float(np.abs(ref64).max()), floor)
+    err = float(np.abs(got.astype(np.float64) - ref64).max())
+    assert err <= rel * scale, f"max|delta|={err:.3e} > {rel:g} * {scale:.3e}"
+
+
+def test_native_library_is_the_one_loaded():
+    L = _cabi.lib()
+    assert os.path.samefile(L._name, os.path.join(os.path.dirname(_cabi.__file__), "lib", "libqpwc.so"))
+    assert ops.library_version() >= 100
+
+
+CV_SHAPES = [
+    (4, 32, 64, 3, 4),      # config 1: test/test_cost_volume.py:20-21
+    (1, 128, 256, 3, 4),    # app/test/test_cvol_equal.py:10
+    (2, 14, 32, 256, 4), (1, 28, 64, 256, 4), (1, 56, 128, 128, 4), (1, 33, 70, 64, 4),
+    (1, 40, 72, 32, 4), (1, 17, 19, 16, 4), (1, 9, 9, 5, 4), (1, 3, 2, 4, 4), (1, 1, 1, 7, 4),
+    (1, 20, 30, 32, 8), (1, 12, 13, 6, 2), (1, 7, 16, 196, 4), (2, 11, 61, 96, 4),
+]
+
+
+@pytest.mark.parametrize("B,H,W,C,d", CV_SHAPES)
+def test_cost_volume_forward(B, H, W, C, d):
+    r = rng(B * 1000 + C)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    ref = oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), d)
+    got = host(ops.cost_volume(dev(prv), dev(nxt), d))
+    assert got.shape == ref.shape
+    assert_rel(got, ref)
+
+
+@pytest.mark.parametrize("B,H,W,C,d", [(4, 32, 64, 3, 4), (1, 28, 64, 256, 4), (1, 40, 72, 32, 4),
+                                       (1, 17, 19, 16, 4), (1, 9, 9, 5, 4), (1, 12, 13, 6, 2),
+                                       (1, 20, 30, 32, 8)])
+def test_cost_volume_backward(B, H, W, C, d):
+    r = rng(7 + C)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    tp, tn = dev(prv).requires_grad_(), dev(nxt).requires_grad_()
+    out = ops.cost_volume(tp, tn, d)
+    g = r.standard_normal(tuple(out.shape)).astype(np.float32)
+    gp, gn = torch.autograd.grad(out, (tp, tn), dev(g))
+    o64 = oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), d)
+    # the leaky mask comes from the GPU's own forward output (sign of the pre-activation)
+    rp, rn = oracle.cost_volume_bwd(prv.astype(np.float64), nxt.astype(np.float64),
+                                    host(out).astype(np.float64), g.astype(np.float64), d)
+    assert_rel(host(gp), rp)
+    assert_rel(host(gn), rn)
+    assert np.array_equal(host(out) > 0, o64 > 0) or np.abs(o64[(host(out) > 0) != (o64 > 0)]).max() < 1e-6
+
+
+WARP_SHAPES = [(4, 32, 64, 3), (2, 28, 64, 256), (1, 56, 128, 128), (1, 33, 35, 32), (1, 9, 11, 2),
+               (1, 2, 2, 1), (1, 5, 6, 7), (1, 16, 18, 96), (1, 8, 8, 196)]
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,H,W,C", WARP_SHAPES)
+def test_warp_forward_bit_exact(mode, B, H, W, C):
+    r = rng(11 + C)
+    img = r.random((B, H, W, C)).astype(np.float32)
+    flow = (r.standard_normal((B, H, W, 2)) * 3.0).astype(np.float32)
+    ref32 = oracle.warp(img, flow, mode)
+    got = host(ops.warp(dev(img), dev(flow), mode))
+    np.testing.assert_array_equal(got, ref32)                  # same op order, no contraction
+    ref64 = oracle.warp(img.astype(np.float64), flow.astype(np.float64), mode)
+    np.testing.assert_allclose(got, ref64, rtol=0, atol=1e-6)  # the stated tolerance
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,H,W,C", WARP_SHAPES)
+def test_warp_backward(mode, B, H, W, C):
+    r = rng(13 + C)
+    img = r.random((B, H, W, C)).astype(np.float32)
+    flow = (r.standard_normal((B, H, W, 2)) * 2.0).astype(np.float32)
+    g = r.standard_normal((B, H, W, C)).astype(np.float32)
+    ti, tf = dev(img).requires_grad_(), dev(flow).requires_grad_()
+    out = ops.warp(ti, tf, mode)
+    gi, gf = torch.autograd.grad(out, (ti, tf), dev(g))
+    ri, rf = oracle.warp_bwd(img.astype(np.float64), flow.astype(np.float64), g.astype(np.float64), mode)
+    # g_img: each element sums a handful of weight*g terms (|g| ~ N(0,1)); allow 1e-6 per unit scale
+    np.testing.assert_allclose(host(gi), ri, rtol=0, atol=1e-6 * max(1.0, float(np.abs(ri).max())))
+    # g_flow sums C products: condition-aware bound 1e-6 * max(1, sum_c |g|*|img| ) <= 1e-6*max(1, 4*C)
+    np.testing.assert_allclose(host(gf), rf, rtol=0, atol=1e-6 * max(1.0, 0.5 * C))
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,H,W,C,d", [(2, 28, 64, 256, 4), (1, 56, 128, 128, 4), (1, 40, 72, 32, 4),
+                                       (1, 33, 70, 64, 4), (1, 9, 11, 3, 4), (1, 17, 19, 16, 4),
+                                       (1, 20, 30, 32, 8)])
+def test_fused_warp_cost_volume_forward_backward(mode, B, H, W, C, d):
+    r = rng(17 + C)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    flo = (r.standard_normal((B, H, W, 2)) * 2.0).astype(np.float32)
+    a64 = [a.astype(np.float64) for a in (prv, nxt, flo)]
+    ref = oracle.warp_cost_volume(*a64, mode, d)
+    tp, tn, tf = (dev(a).requires_grad_() for a in (prv, nxt, flo))
+    out = ops.warp_cost_volume(tp, tn, tf, mode, d)
+    assert_rel(host(out), ref)
+    # fused == unfused composition of our own two ops (same warped values, same correlation)
+    comp = ops.cost_volume(dev(prv), ops.warp(dev(nxt), dev(flo), mode), d)
+    assert_rel(host(out), host(comp).astype(np.float64), rel=2e-6)
+    g = r.standard_normal(ref.shape).astype(np.float32)
+    gp, gn, gf = torch.autograd.grad(out, (tp, tn, tf), dev(g))
+    # reference gradients with the leaky mask of the GPU forward
+    nxt_w = oracle.warp(a64[1], a64[2], mode)
+    rp, rnw = oracle.cost_volume_bwd(a64[0], nxt_w, host(out).astype(np.float64), g.astype(np.float64), d)
+    rn, rf = oracle.warp_bwd(a64[1], a64[2], rnw, mode)
+    assert_rel(host(gp), rp)
+    assert_rel(host(gn), rn, floor=1e-3)
+    assert_rel(host(gf), rf, floor=1e-3)
+
+
+def test_golden_fixtures():
+    g = np.load(os.path.join(GOLD, "qpwc_golden.npz"))
+    for name in ("cv_a", "cv_b", "cv_c", "cv_d"):
+        d = int(g[f"{name}/d"])
+        tp, tn = dev(g[f"{name}/prv"]).requires_grad_(), dev(g[f"{name}/nxt"]).requires_grad_()
+        out = ops.cost_volume(tp, tn, d)
+        assert_rel(host(out), g[f"{name}/out"])
+        gp, gn = torch.autograd.grad(out, (tp, tn), dev(g[f"{name}/g_out"]))
+        assert_rel(host(gp), g[f"{name}/g_prv"])
+        assert_rel(host(gn), g[f"{name}/g_nxt"])
+    for name in ("warp_a", "warp_b", "warp_c"):
+        for mode in ("tf", "tfa"):
+            ti, tf = dev(g[f"{name}/img"]).requires_grad_(), dev(g[f"{name}/flow"]).requires_grad_()
+            out = ops.warp(ti, tf, mode)
+            np.testing.assert_allclose(host(out), g[f"{name}/{mode}/out"], rtol=0, atol=1e-6)
+            gi, gf = torch.autograd.grad(out, (ti, tf), dev(g[f"{name}/g_out"]))
+            np.testing.assert_allclose(host(gi), g[f"{name}/{mode}/g_img"], rtol=0, atol=2e-6)
+            np.testing.assert_allclose(host(gf), g[f"{name}/{mode}/g_flow"], rtol=0, atol=4e-6)
+    for name in ("fused_a", "fused_b"):
+        d = int(g[f"{name}/d"])
+        for mode in ("tf", "tfa"):
+            tp, tn, tf = (dev(g[f"{name}/{k}"]).requires_grad_() for k in ("prv", "nxt", "flow"))
+            out = ops.warp_cost_volume(tp, tn, tf, mode, d)
+            assert_rel(host(out), g[f"{name}/{mode}/out"])
+            gp, gn, gf = torch.autograd.grad(out, (tp, tn, tf), dev(g[f"{name}/g_out"]))
+            assert_rel(host(gp), g[f"{name}/{mode}/g_prv"])
+            assert_rel(host(gn), g[f"{name}/{mode}/g_nxt"], floor=1e-3)
+            assert_rel(host(gf), g[f"{name}/{mode}/g_flow"], floor=1e-3)
+
+
+def test_golden_cfg1():
+    c = np.load(os.path.join(GOLD, "qpwc_cfg1.npz"))
+    r1 = np.random.default_rng(int(c["seed"]))
+    prv = r1.standard_normal((4, 32, 64, 3)).astype(np.float32)
+    nxt = r1.standard_normal((4, 32, 64, 3)).astype(np.float32)
+    img = r1.random((4, 32, 64, 3)).astype(np.float32)
+    flo = r1.standard_normal((4, 32, 64, 2)).astype(np.float32)
+    cv = host(ops.cost_volume(dev(prv), dev(nxt), 4))
+    assert_rel(cv[:, ::5, ::7], c["cv/sample"])
+    assert abs(cv.astype(np.float64).sum() - float(c["cv/sum"])) < 1e-2
+    for mode in ("tf", "tfa"):
+        w = host(ops.warp(dev(img), dev(flo), mode))
+        np.testing.assert_allclose(w[:, ::5, ::7], c[f"warp/{mode}/sample"], rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------------------ the reference's own test scripts
+def test_reference_test_cost_volume_script():
+    """test/test_cost_volume.py:7-24 read against this package: CostVolume == CostVolumeV2."""
+    from qpwcnet.core.layers import CostVolume, CostVolumeV2
+    for fmt, shape in (("channels_last", (4, 32, 64, 3)), ("channels_first", (4, 3, 32, 64))):
+        c1 = CostVolume(search_range=4, data_format=fmt)
+        c2 = CostVolumeV2(search_range=4, data_format=fmt)
+        torch.manual_seed(0)
+        prv, nxt = torch.randn(shape, device=DEV), torch.randn(shape, device=DEV)
+        a, b = c1((prv, nxt)), c2((prv, nxt))
+        assert float((a - b).sum()) == 0.0                       # "diff 0.0"
+        nh = (lambda t: t.permute(0, 2, 3, 1)) if fmt == "channels_first" else (lambda t: t)
+        ref = oracle.cost_volume(host(nh(prv)).astype(np.float64), host(nh(nxt)).astype(np.float64), 4)
+        assert_rel(host(nh(a)), ref)
+        assert a.shape == ((4, 32, 64, 81) if fmt == "channels_last" else (4, 81, 32, 64))
+
+
+def test_reference_test_warp_script():
+    """test/test_warp.py:10-28: Warp vs WarpV2 differ only through the border rule."""
+    from qpwcnet.core.layers import Warp, WarpV2
+    from qpwcnet.core.util import disable_gpu
+    disable_gpu()
+    w1, w2 = Warp(data_format="channels_last"), WarpV2(data_format="channels_last")
+    torch.manual_seed(0)
+    img, flo = torch.rand((4, 32, 64, 3), device=DEV), torch.randn((4, 32, 64, 2), device=DEV)
+    c1, c2 = w1((img, flo)), w2((img, flo))
+    np.testing.assert_array_equal(host(c1), oracle.warp(host(img), host(flo), "tf"))
+    np.testing.assert_array_equal(host(c2), oracle.warp(host(img), host(flo), "tfa"))
+    inner = (host(c1) - host(c2))[:, 4:-4, 4:-4]
+    assert np.abs(inner).max() < 1e-5          # same interior sampling, different borders only
+    # channels_first goes through the same kernels
+    w2f = WarpV2(data_format="channels_first")
+    c2f = w2f((img.permute(0, 3, 1, 2).contiguous(), flo.permute(0, 3, 1, 2).contiguous()))
+    np.testing.assert_array_equal(host(c2f.permute(0, 2, 3, 1)), host(c2))
+
+
+def test_reference_onehot_3x3_convention():
+    """app/optical_flow/test_warp.py:25-33: flow (x=+1, y=0) broadcast from (1,1,1,2)."""
+    from qpwcnet.core.layers import WarpV2
+    from qpwcnet_b200 import set_image_data_format
+    set_image_data_format("channels_last")
+    nxt = torch.tensor([[0., 0, 0], [0, 1, 0], [0, 0, 0]], device=DEV).reshape(1, 3, 3, 1)
+    flo = torch.tensor([1., 0.], device=DEV).reshape(1, 1, 1, 2).expand(1, 3, 3, 2)
+    prv = host(WarpV2()((nxt, flo)))[0, :, :, 0]
+    assert prv[1, 0] == 1.0 and prv[1, 1] == 0.0
+
+
+def test_tf_warp_function_and_functors():
+    from qpwcnet.core import non_layers
+    from qpwcnet.core.warp import tf_warp
+    r = rng(5)
+    img = dev(r.random((1, 6, 7, 4)))
+    flo = dev(r.standard_normal((1, 6, 7, 2)))
+    np.testing.assert_array_equal(host(tf_warp(img, flo, "channels_last")), oracle.warp(host(img), host(flo), "tf"))
+    np.testing.assert_array_equal(host(non_layers.WarpV2()((img, flo))), oracle.warp(host(img), host(flo), "tfa"))
+    cv = non_layers.CostVolumeV2(search_range=2)((img, img))
+    assert cv.shape == (1, 6, 7, 25)
+    fused = non_layers.WarpCostVolume(search_range=4)((img, img, flo))
+    assert fused.shape == (1, 6, 7, 81)
+
+
+# --------------------------------------------------------------- size-independent properties
+def test_properties_at_full_pyramid_sizes():
+    """BASELINE.json config 2, finest level (B=8, 224x512, C=32): too big for the oracle in seconds,
+    checked through properties: integer shift -> peak channel, positive homogeneity, zero-flow fused
+    == unfused, and a strided sample against the oracle."""
+    B, H, W, C, d = 8, 224, 512, 32, 4
+    g = torch.Generator(device=DEV).manual_seed(0)
+    prv = torch.randn((B, H, W, C), device=DEV, generator=g)
+    di, dj = 3, -2
+    nxt = torch.zeros_like(prv)
+    nxt[:, di:, :W + dj] = prv[:, :H - di, -dj:]               # nxt[i+di, j+dj] = prv[i, j]
+    out = ops.cost_volume(prv, nxt, d)
+    k = (di + d) * 9 + (dj + d)
+    inner = out[:, 8:-8, 8:-8]
+    assert bool((inner.argmax(-1) == k).all())
+    torch.testing.assert_close(inner[..., k], (prv[:, 8:-8, 8:-8] ** 2).mean(-1), rtol=1e-5, atol=1e-6)
+    # positive homogeneity: cv(2a, n) = 2 cv(a, n) exactly (power-of-two scaling commutes with fp32)
+    nx2 = torch.randn((B, H, W, C), device=DEV, generator=g)
+    o1 = ops.cost_volume(prv, nx2, d)
+    o2 = ops.cost_volume(prv * 2.0, nx2, d)
+    assert torch.equal(o2, o1 * 2.0)
+    # zero flow: tfa warp is the identity in the interior => fused == unfused there
+    zf = torch.zeros((B, H, W, 2), device=DEV)
+    of = ops.warp_cost_volume(prv, nx2, zf, "tfa", d)
+    torch.testing.assert_close(of[:, :H - 6, :W - 6], o1[:, :H - 6, :W - 6], rtol=0, atol=2e-6)
+    # random flow: fused vs composition of the two stand-alone ops
+    fl = torch.randn((B, H, W, 2), device=DEV, generator=g) * 2
+    of = ops.warp_cost_volume(prv, nx2, fl, "tfa", d)
+    oc = ops.cost_volume(prv, ops.warp(nx2, fl, "tfa"), d)
+    torch.testing.assert_close(of, oc, rtol=0, atol=5e-6)
+    # strided sample against the oracle
+    sl = (slice(0, 1), slice(100, 124), slice(200, 232))
+    ref = oracle.cost_volume(host(prv[0:1, 92:132, 192:240]).astype(np.float64),
+                             host(nx2[0:1, 92:132, 192:240]).astype(np.float64), d)[:, 8:32, 8:40]
+    assert_rel(host(o1[sl]), ref)
+
+
+def test_empty_and_error_behaviour():
+    e = torch.empty((0, 4, 5, 3), device=DEV)
+    assert ops.cost_volume(e, e, 4).shape == (0, 4, 5, 81)
+    assert ops.warp(e, torch.empty((0, 4, 5, 2), device=DEV), "tf").shape == (0, 4, 5, 3)
+    x = torch.zeros((1, 4, 5, 3), device=DEV)
+    with pytest.raises(_cabi.QpwcError, match="search_range"):
+        ops.cost_volume(x, x, 0)
+    with pytest.raises(ValueError, match="2x2"):
+        ops.warp(torch.zeros((1, 1, 5, 3), device=DEV), torch.zeros((1, 1, 5, 2), device=DEV), "tfa")
+    with pytest.raises(ValueError):
+        ops.cost_volume(x, torch.zeros((1, 4, 6, 3), device=DEV), 4)
+    with pytest.raises(TypeError):
+        ops.cost_volume(x.double(), x.double(), 4)
+
+
+def test_host_buffer_entry_points_match_device_path():
+    r = rng(23)
+    prv = torch.from_numpy(r.standard_normal((5, 24, 40, 32)).astype(np.float32)).pin_memory()
+    nxt = torch.from_numpy(r.standard_normal((5, 24, 40, 32)).astype(np.float32))   # pageable
+    flo = torch.from_numpy(r.standard_normal((5, 24, 40, 2)).astype(np.float32)).pin_memory()
+    out_h = ops.cost_volume(prv, nxt, 4)
+    assert not out_h.is_cuda
+    assert torch.equal(out_h, ops.cost_volume(prv.to(DEV), nxt.to(DEV), 4).cpu())
+    assert torch.equal(ops.warp(nxt, flo, "tfa"), ops.warp(nxt.to(DEV), flo.to(DEV), "tfa").cpu())
+    assert torch.equal(ops.warp_cost_volume(prv, nxt, flo, "tfa", 4),
+                       ops.warp_cost_volume(prv.to(DEV), nxt.to(DEV), flo.to(DEV), "tfa", 4).cpu())
+
+
+def test_non_default_stream_and_noncontiguous_inputs():
+    r = rng(29)
+    prv = dev(r.standard_normal((2, 12, 14, 16)))
+    nxt = dev(r.standard_normal((2, 12, 14, 16)))
+    ref = ops.cost_volume(prv, nxt, 4)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        o = ops.cost_volume(prv, nxt, 4)
+    s.synchronize()
+    assert torch.equal(o, ref)
+    nc = prv.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)     # NHWC view of NCHW storage
+    assert not nc.is_contiguous()
+    assert torch.equal(ops.cost_volume(nc, nxt, 4), ref)
