@@ -1,0 +1,154 @@
+// qpwc_async.cuh -- thin wrappers over the sm_90+/sm_100a asynchronous machinery used by the tiled
+// kernels: mbarrier, TMA tensor loads (cp.async.bulk.tensor), named barriers, setmaxnreg.
+// Under -DQPWC_EMU (tests/emu, CPU harness) each wrapper has a functional stand-in so that the same
+// kernel body -- pipeline phases, swizzled addressing, barrier protocol -- runs on the CPU.
+#pragma once
+#include "qpwc_common.cuh"
+
+#ifndef QPWC_EMU
+#include <cuda.h>  // CUtensorMap, CU_TENSOR_MAP_*
+#endif
+
+namespace qpwc {
+
+// TMA SWIZZLE_32B: byte-address bit 4 ^= bit 7 (pattern repeats every 256 B; buffers 256-B aligned)
+__host__ __device__ __forceinline__ uint32_t swz32(uint32_t byte_off) {
+  return byte_off ^ (((byte_off >> 7) & 1u) << 4);
+}
+
+#ifndef QPWC_EMU
+// =============================================================================== real hardware
+typedef CUtensorMap TensorMap;
+#define QPWC_GRID_CONSTANT __grid_constant__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const TensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+// 4-D tiled load global -> shared, completion signalled on `bar` as transaction bytes
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const TensorMap* tm, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// Host: encode a 4-D tiled tensor map over a dense NHWC fp32 tensor, dims (C, W, H, B), box
+// (boxC, boxW, boxH, 1), SWIZZLE_32B, zero fill out of bounds, 128-B L2 promotion.
+// Returns false (and sets the error) on failure.
+bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C, int boxC, int boxW, int boxH);
+
+#else
+// ============================================================================ CPU emulation
+#define QPWC_GRID_CONSTANT
+struct TensorMap {
+  const float* base;
+  long long dim[4];      // C, W, H, B
+  long long stride[4];   // element strides
+  int box[4];
+};
+struct EmuMbar { uint16_t init; uint16_t pending; int32_t tx; };  // init bit 15 = phase parity
+static_assert(sizeof(EmuMbar) == 8, "mbarrier is 8 bytes");
+
+namespace emu_detail {
+inline std::mutex& mu() { static std::mutex m; return m; }
+inline std::condition_variable& cv() { static std::condition_variable c; return c; }
+inline void settle(EmuMbar* b) {
+  if (b->pending == 0 && b->tx == 0) {
+    b->init ^= 0x8000u;
+    b->pending = b->init & 0x7fffu;
+    cv().notify_all();
+  }
+}
+}  // namespace emu_detail
+
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  b->init = (uint16_t)count; b->pending = (uint16_t)count; b->tx = 0;
+}
+inline void fence_mbar_init() {}
+inline void mbar_arrive(uint64_t* bar) {
+  std::lock_guard<std::mutex> lk(emu_detail::mu());
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  b->pending--; emu_detail::settle(b);
+}
+inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  std::lock_guard<std::mutex> lk(emu_detail::mu());
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  b->tx += (int32_t)bytes; b->pending--; emu_detail::settle(b);
+}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  qpwc_emu::mark("mbar_wait", (int)(reinterpret_cast<uintptr_t>(bar) & 0xff) * 10 + (int)parity);
+  std::unique_lock<std::mutex> lk(emu_detail::mu());
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  if (!emu_detail::cv().wait_for(lk, std::chrono::seconds(20), [&] { return (uint32_t)((b->init >> 15) & 1u) != parity; }))
+    qpwc_emu::watchdog_abort("mbar_wait", (int)parity, (int)b->pending * 1000000 + b->tx);
+}
+inline void tma_prefetch_desc(const TensorMap*) {}
+inline void tma_load_4d(void* smem_dst, const TensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  const int co[4] = {c0, c1, c2, c3};
+  unsigned char* dst = static_cast<unsigned char*>(smem_dst);
+  uint32_t lin = 0, bytes = 0;
+  for (int e3 = 0; e3 < tm->box[3]; ++e3)
+    for (int e2 = 0; e2 < tm->box[2]; ++e2)
+      for (int e1 = 0; e1 < tm->box[1]; ++e1)
+        for (int e0 = 0; e0 < tm->box[0]; ++e0, lin += 4, bytes += 4) {
+          const long long x[4] = {co[0] + e0, co[1] + e1, co[2] + e2, co[3] + e3};
+          float v = 0.f;
+          bool in = true;
+          for (int k = 0; k < 4; ++k) in = in && x[k] >= 0 && x[k] < tm->dim[k];
+          if (in) v = tm->base[x[0] * tm->stride[0] + x[1] * tm->stride[1] + x[2] * tm->stride[2] + x[3] * tm->stride[3]];
+          // hardware swizzles on absolute shared-memory address bits
+          const uintptr_t abs = reinterpret_cast<uintptr_t>(dst) + lin;
+          const uintptr_t phys = abs ^ (((abs >> 7) & 1u) << 4);
+          *reinterpret_cast<float*>(phys) = v;
+        }
+  std::lock_guard<std::mutex> lk(emu_detail::mu());
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  b->tx -= (int32_t)bytes; emu_detail::settle(b);
+}
+inline void named_bar_sync(int id, int nthreads) { qpwc_emu_named_barrier(id, nthreads); }
+template <int N> inline void setmaxnreg_inc() {}
+template <int N> inline void setmaxnreg_dec() {}
+
+inline bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C, int boxC, int boxW, int boxH) {
+  tm->base = base;
+  tm->dim[0] = C; tm->dim[1] = W; tm->dim[2] = H; tm->dim[3] = B;
+  tm->stride[0] = 1; tm->stride[1] = C; tm->stride[2] = (long long)W * C; tm->stride[3] = (long long)H * W * C;
+  tm->box[0] = boxC; tm->box[1] = boxW; tm->box[2] = boxH; tm->box[3] = 1;
+  return true;
+}
+#endif
+
+}  // namespace qpwc

@@ -28,7 +28,7 @@
 #else
 #define QPWC_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-#define QPWC_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define QPWC_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #endif
 
 namespace qpwc {

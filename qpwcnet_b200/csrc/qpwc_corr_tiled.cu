@@ -1,12 +1,333 @@
-// qpwc_corr_tiled.cu -- register-tiled correlation kernels (placeholder: filled in next commit).
-#include "qpwc_common.cuh"
+// qpwc_corr_tiled.cu -- register-tiled FFMA local correlation for sm_100a, plain and fused with
+// the bilinear warp of the second frame (the warped tensor lives only in shared memory).
+//
+//   out[b,i,j,(di+d)*(2d+1)+(dj+d)] = lrelu( (1/C) sum_c P[b,i,j,c] * N[b,i+di,j+dj,c] ),  N == 0 outside
+//   P = prv;  N = nxt (CostVolume, qpwcnet/core/layers.py:72-100)  or  N = warp(nxt, flow)
+//   (UpFlow, qpwcnet/core/non_layers.py:377-380).
+//
+// Why FFMA and not tcgen05: the contraction is banded -- every output pixel contracts against its
+// own (2d+1)^2 neighbourhood -- and fp32 parity (<= 1e-5 rel) rules out tf32/bf16 operands.
+//
+// Decomposition (d = 4): one persistent CTA per SM walks tiles of TH x 56 first-frame pixels.
+//   * consumer thread (ti, tc), tc in [0,64): second-frame column s = j0-4+tc of tile row ti.  Per
+//     channel it forms the 9x9 outer product  acc[m][k] += P[i, s-(k-4)] * N[i+(m-4), s]
+//     (a = 9 first-frame pixels left/right of s in row i, b = 9 second-frame pixels above/below
+//     in column s): 18 shared-memory operands feed 81 FFMAs, every product is a valid
+//     displacement pair.  acc[m][k] is output channel m*9+k of pixel column s-(k-4).
+//   * operands are streamed through shared memory in chunks of 8 channels, 3 stages, TMA tensor
+//     loads (zero fill outside the image == ZeroPadding2D) with SWIZZLE_32B so that the 16-byte
+//     operand loads of 8 neighbouring pixels hit 8 distinct bank groups.
+//   * a producer warpgroup drives the pipeline over mbarriers (full/empty per stage), across tile
+//     boundaries.  Plain: one thread issues the two TMA loads per chunk.  Fused: the second-frame
+//     stage is produced by the warpgroup itself -- 4 gathers + blend per halo pixel, bit-identical
+//     to the stand-alone warp kernel -- so warped features never reach HBM.
+//   * epilogue: accumulators -> (x 1/C, leaky relu) -> per-row staging in shared memory (transposes
+//     the per-thread 9x9 blocks into the NHWC 81-vector) -> coalesced 16-byte row stores.
+#include "qpwc_async.cuh"
 
 namespace qpwc {
 
-int launch_corr_fwd_tiled(const float*, const float*, const float*, int, float*, int, int, int, int,
-                          int, float, long long, cudaStream_t) {
-  return QPWC_ERR_UNSUPPORTED;
+template <int TH_, int WARP_, int MODE_>
+struct TiledCfg {
+  static constexpr int D = 4, Q = 2 * D + 1, NDISP = Q * Q;
+  static constexpr int TH = TH_, TWT = 64, TW = TWT - 2 * D;  // 56 pixel columns per tile
+  static constexpr int WARP = WARP_, MODE = MODE_;
+  static constexpr int KC = 8, PXB = KC * 4;                   // 32 bytes per pixel per stage
+  static constexpr int NROW = TH + 2 * D, NCOL = TWT, PCOL = TW + 4 * D;  // 72
+  static constexpr int NST = 3;
+  static constexpr int P_BYTES = TH * PCOL * PXB, N_BYTES = NROW * NCOL * PXB;
+  static constexpr int STAGE_BYTES = P_BYTES + N_BYTES;
+  static constexpr int NCONS = TH * TWT, NPROD = 128, NTHREADS = NCONS + NPROD;
+  static constexpr int NG = TH / 2;                            // epilogue groups: rows g and g+NG
+  static constexpr int SLOT_BYTES = ((TW * NDISP * 4 + 127) / 128) * 128;
+  static constexpr int TAPS_BYTES = WARP ? NROW * NCOL * 32 : 0;
+  static constexpr int OFF_STAGING = NST * STAGE_BYTES;
+  static constexpr int OFF_TAPS = OFF_STAGING + NG * SLOT_BYTES;
+  static constexpr int OFF_BARS = OFF_TAPS + TAPS_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BARS + 2 * NST * 8;
+  static constexpr int FULL_COUNT = 1 + (WARP ? NPROD / 32 : 0);
+  static constexpr int EMPTY_COUNT = NCONS / 32;
+  static constexpr int REG_CONS = 152, REG_PROD = 56;         // 384*152 + 128*56 == 65536
+  static_assert(TH % 2 == 0 && P_BYTES % 256 == 0 && N_BYTES % 256 == 0, "tile shape");
+  static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536 || TH != 6, "register budget");
+};
+
+struct TapsEntry { int o00, o01, o10, o11; float w00, w01, w10, w11; };  // 32 bytes
+
+// ---------------------------------------------------------------------------------------------
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::NTHREADS, 1)
+corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CONSTANT TensorMap tmN,
+                      const float* __restrict__ nxt, const float* __restrict__ flow,
+                      float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
+                      int tiles_x, int tiles_y, int ntiles) {
+  constexpr int D = Cfg::D, Q = Cfg::Q, NDISP = Cfg::NDISP, TH = Cfg::TH, TW = Cfg::TW;
+  constexpr int NCOL = Cfg::NCOL, PCOL = Cfg::PCOL, NROW = Cfg::NROW, NST = Cfg::NST, KC = Cfg::KC;
+  constexpr int NCONS = Cfg::NCONS, NPROD = Cfg::NPROD, NG = Cfg::NG;
+
+  // dynamic shared memory starts at the CTA's window base (no static __shared__ in this kernel):
+  // 1024-byte aligned, which the swizzle arithmetic relies on (checked below, once per CTA)
+  QPWC_DYN_SMEM(smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
+  uint64_t* empty = full + NST;
+
+  const int tid = threadIdx.x;
+  const int nchunks = (C + KC - 1) / KC;
+
+  if (tid == 0) {
+#ifndef QPWC_EMU
+    if (smem_u32(smem) & 255u) __trap();
+#endif
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], Cfg::FULL_COUNT); mbar_init(&empty[s], Cfg::EMPTY_COUNT); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (tid >= NCONS) {
+    // ========================================================================== producers
+    setmaxnreg_dec<Cfg::REG_PROD>();
+    const int ptid = tid - NCONS;
+    if (ptid == 0) { tma_prefetch_desc(&tmP); if (!Cfg::WARP) tma_prefetch_desc(&tmN); }
+    // Plain variant: the pipeline is driven by one thread.  The other producer threads must NOT
+    // idle along on the empty barriers: nothing would gate on them, so a slow one could fall two
+    // phases behind and alias the parity wait (found by the CPU emulation harness).  In the fused
+    // variant every producer warp arrives on `full`, which keeps all of them within one phase.
+    if (!Cfg::WARP && ptid != 0) return;
+    TapsEntry* taps = reinterpret_cast<TapsEntry*>(smem + Cfg::OFF_TAPS);
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int tx = tile % tiles_x;
+      const int ty = (tile / tiles_x) % tiles_y;
+      const int b = tile / (tiles_x * tiles_y);
+      const int i0 = ty * TH, j0 = tx * TW;
+      if (Cfg::WARP) {
+        // per-tile table of sampling taps for every halo pixel of the warped second frame
+        named_bar_sync(15, NPROD);  // previous tile's last chunk no longer reads the table
+        for (int p = ptid; p < NROW * NCOL; p += NPROD) {
+          const int r = i0 - D + p / NCOL, s = j0 - D + p % NCOL;
+          TapsEntry e;
+          e.o00 = -1; e.o01 = e.o10 = e.o11 = 0; e.w00 = e.w01 = e.w10 = e.w11 = 0.f;
+          if (r >= 0 && r < H && s >= 0 && s < W) {  // outside: zero padding of the warped frame
+            const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)b * H * W + (size_t)r * W + s));
+            const Taps t = make_taps<Cfg::MODE>(r, s, f.x, f.y, H, W);
+            e.o00 = t.o00; e.o01 = t.o01; e.o10 = t.o10; e.o11 = t.o11;
+            e.w00 = t.w00; e.w01 = t.w01; e.w10 = t.w10; e.w11 = t.w11;
+          }
+          taps[p] = e;
+        }
+        named_bar_sync(15, NPROD);
+      }
+      for (int c = 0; c < nchunks; ++c, ++g) {
+        const int stage = g % NST;
+        const uint32_t ph = (g / NST) & 1u;
+        mbar_wait(&empty[stage], ph ^ 1u);  // consumers released this stage
+        unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
+        if (ptid == 0) {
+          mbar_arrive_expect_tx(&full[stage], Cfg::P_BYTES + (Cfg::WARP ? 0 : Cfg::N_BYTES));
+          tma_load_4d(sb, &tmP, &full[stage], c * KC, j0 - 2 * D, i0, b);
+          if (!Cfg::WARP) tma_load_4d(sb + Cfg::P_BYTES, &tmN, &full[stage], c * KC, j0 - D, i0 - D, b);
+        }
+        if (Cfg::WARP) {
+          // units: (halo pixel, 16-byte channel quad); lane pairs share a pixel => 32-byte reads
+          const float* nb = nxt + (size_t)b * H * W * C + (size_t)c * KC;
+          unsigned char* ns = sb + Cfg::P_BYTES;
+          for (int u = ptid; u < NROW * NCOL * 2; u += NPROD) {
+            const int pix = u >> 1, qd = u & 1;
+            const TapsEntry e = taps[pix];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.o00 >= 0 && c * KC + qd * 4 < C) {
+              const float* base = nb + qd * 4;
+              const float4 v00 = __ldg(reinterpret_cast<const float4*>(base + (size_t)e.o00 * C));
+              const float4 v01 = __ldg(reinterpret_cast<const float4*>(base + (size_t)e.o01 * C));
+              const float4 v10 = __ldg(reinterpret_cast<const float4*>(base + (size_t)e.o10 * C));
+              const float4 v11 = __ldg(reinterpret_cast<const float4*>(base + (size_t)e.o11 * C));
+              Taps t;
+              t.o00 = t.o01 = t.o10 = t.o11 = 0;
+              t.w00 = e.w00; t.w01 = e.w01; t.w10 = e.w10; t.w11 = e.w11;
+              v.x = blend<Cfg::MODE>(t, v00.x, v01.x, v10.x, v11.x);
+              v.y = blend<Cfg::MODE>(t, v00.y, v01.y, v10.y, v11.y);
+              v.z = blend<Cfg::MODE>(t, v00.z, v01.z, v10.z, v11.z);
+              v.w = blend<Cfg::MODE>(t, v00.w, v01.w, v10.w, v11.w);
+            }
+            *reinterpret_cast<float4*>(ns + swz32((uint32_t)(pix * Cfg::PXB + qd * 16))) = v;
+          }
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(&full[stage]);
+        }
+      }
+    }
+  } else {
+    // ========================================================================== consumers
+    setmaxnreg_inc<Cfg::REG_CONS>();
+    const int ti = tid / NCOL, tc = tid % NCOL, lane = tid & 31;
+    // byte offsets inside a stage (chunk quad 0; quad 1 = offset ^ 16)
+    const uint32_t nb_off = Cfg::P_BYTES + swz32((uint32_t)((ti * NCOL + tc) * Cfg::PXB));
+    uint32_t a_off[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) a_off[k] = swz32((uint32_t)((ti * PCOL + tc + 2 * D - k) * Cfg::PXB));
+    const float inv_c = 1.f / (float)C;
+    const int gi = ti % NG;
+    const bool first = ti < NG;
+    const int gt = (ti / NG) * NCOL + tc;  // thread index inside the 128-thread epilogue group
+    float* slot = reinterpret_cast<float*>(smem + Cfg::OFF_STAGING + gi * Cfg::SLOT_BYTES);
+
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int tx = tile % tiles_x;
+      const int ty = (tile / tiles_x) % tiles_y;
+      const int b = tile / (tiles_x * tiles_y);
+      const int i0 = ty * TH, j0 = tx * TW;
+
+      float acc[Q][Q];
+#pragma unroll
+      for (int m = 0; m < Q; ++m)
+#pragma unroll
+        for (int k = 0; k < Q; ++k) acc[m][k] = 0.f;
+
+      for (int c = 0; c < nchunks; ++c, ++g) {
+        const int stage = g % NST;
+        mbar_wait(&full[stage], (g / NST) & 1u);
+        const unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+        for (int qd = 0; qd < 2; ++qd) {
+          const unsigned char* nbp = sb + (nb_off ^ (uint32_t)(qd << 4));
+          float4 bv[Q];
+#pragma unroll
+          for (int m = 0; m < Q; ++m) bv[m] = *reinterpret_cast<const float4*>(nbp + m * (NCOL * Cfg::PXB));
+#pragma unroll
+          for (int k = 0; k < Q; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
+#pragma unroll
+            for (int m = 0; m < Q; ++m) {
+              acc[m][k] = fmaf(a.x, bv[m].x, acc[m][k]);
+              acc[m][k] = fmaf(a.y, bv[m].y, acc[m][k]);
+              acc[m][k] = fmaf(a.z, bv[m].z, acc[m][k]);
+              acc[m][k] = fmaf(a.w, bv[m].w, acc[m][k]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+      }
+
+      // -------------------------------------------------------------------------- epilogue
+      const int twv = min(TW, W - j0);  // valid pixel columns of this tile
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        named_bar_sync(1 + gi, 2 * NCOL);  // slot free / previous half copied out
+        if ((half == 0) == first) {
+#pragma unroll
+          for (int k = 0; k < Q; ++k) {
+            const int lp = tc - k;  // local pixel column of acc[.][k]
+            if (lp >= 0 && lp < twv) {
+#pragma unroll
+              for (int m = 0; m < Q; ++m) slot[lp * NDISP + m * Q + k] = lrelu(acc[m][k] * inv_c, slope);
+            }
+          }
+        }
+        named_bar_sync(1 + gi, 2 * NCOL);  // slot complete
+        const int i = i0 + gi + half * NG;
+        if (i < H) {
+          float* dst = out + ((size_t)((size_t)b * H + i) * W + j0) * (size_t)ops;
+          const int n = twv * NDISP;
+          if (ops == NDISP && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(slot);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int e = gt; e < (n >> 2); e += 2 * NCOL) d4[e] = s4[e];
+          } else if (ops == NDISP) {
+            for (int e = gt; e < n; e += 2 * NCOL) dst[e] = slot[e];
+          } else {
+            for (int e = gt; e < n; e += 2 * NCOL) dst[(size_t)(e / NDISP) * ops + (e % NDISP)] = slot[e];
+          }
+        }
+      }
+    }
+  }
 }
+
+// -------------------------------------------------------------------------------------- host
+#ifndef QPWC_EMU
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C, int boxC, int boxW, int boxH) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available"); return false; }
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return false; }
+  return true;
+}
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+#else
+static int sm_count() { return 3; }  // small persistent grid: exercises the multi-tile loop
+#endif
+
+template <class Cfg>
+static int run_tiled(const float* prv, const float* nxt, const float* flow, float* out, int B, int H,
+                     int W, int C, float slope, long long ops, cudaStream_t stream) {
+  TensorMap tmP, tmN;
+  if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::KC, Cfg::PCOL, Cfg::TH)) return QPWC_ERR_CUDA;
+  if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, Cfg::KC, Cfg::NCOL, Cfg::NROW)) return QPWC_ERR_CUDA;
+  const int tiles_x = cdiv(W, Cfg::TW), tiles_y = cdiv(H, Cfg::TH);
+  const long long nt = (long long)tiles_x * tiles_y * B;
+  if (nt >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
+  const int ntiles = (int)nt;
+  const int grid = ntiles < sm_count() ? ntiles : sm_count();
+  auto k = corr_fwd_tiled_kernel<Cfg>;
+#ifndef QPWC_EMU
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_fwd_tiled: smem attribute (%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+    attr_done = true;
+  }
+#endif
+  QPWC_LAUNCH(k, grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream, tmP, tmN, nxt, flow, out, B, H, W, C, slope, ops,
+              tiles_x, tiles_y, ntiles);
+  return check_launch("corr_fwd_tiled");
+}
+
+int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow, int mode, float* out,
+                          int B, int H, int W, int C, int d, float slope, long long ops,
+                          cudaStream_t stream) {
+  // domain: d == 4, C a multiple of 4, 16-byte aligned inputs (TMA), maps at least one tile wide
+  if (d != 4 || (C & 3) || C < 4) return QPWC_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15)) return QPWC_ERR_UNSUPPORTED;
+  if ((long long)H * W < 64) return QPWC_ERR_UNSUPPORTED;
+  if (!flow) return run_tiled<TiledCfg<6, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<6, 1, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  return run_tiled<TiledCfg<6, 1, QPWC_MODE_TFA>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+}
+
 int launch_corr_bwd_tiled(const float*, const float*, const float*, const float*, float*, float*,
                           int, int, int, int, int, float, long long, cudaStream_t) {
   return QPWC_ERR_UNSUPPORTED;

@@ -11,6 +11,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
@@ -58,13 +59,17 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 
 namespace qpwc_emu {
 
+[[noreturn]] inline void watchdog_abort(const char* what, int a, int b);
+inline void mark(const char* what, int id);
+
 class Barrier {
  public:
-  void arrive_and_wait(int n) {
+  void arrive_and_wait(int n, const char* what = "barrier", int id = -1) {
+    mark(what, id);
     std::unique_lock<std::mutex> lk(mu_);
     const unsigned gen = gen_;
     if (++count_ == n) { count_ = 0; ++gen_; cv_.notify_all(); }
-    else cv_.wait(lk, [&] { return gen != gen_; });
+    else if (!cv_.wait_for(lk, std::chrono::seconds(20), [&] { return gen != gen_; })) watchdog_abort(what, id, count_);
   }
  private:
   std::mutex mu_;
@@ -76,6 +81,8 @@ class Barrier {
 struct WarpState { Barrier bar; uint32_t buf[32]; int nthreads = 32; };
 
 struct BlockState {
+  std::vector<const char*> where;   // last wait entered by each thread (debug)
+  std::vector<int> where_id;
   unsigned char* smem = nullptr;
   int nthreads = 0;
   Barrier bar;
@@ -93,6 +100,21 @@ inline unsigned char* dyn_smem() { return tl_block->smem; }
 inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 namespace qpwc_emu {
+inline void mark(const char* what, int id) {
+  if (tl_block) { tl_block->where[tl_tid] = what; tl_block->where_id[tl_tid] = id; }
+}
+// a barrier nobody completes within 20 s is a protocol bug: report who is stuck instead of hanging
+[[noreturn]] inline void watchdog_abort(const char* what, int a, int b) {
+  fprintf(stderr, "[qpwc_emu] DEADLOCK: thread %d of block %u stuck in %s (id/parity=%d, state=%d)\n",
+          tl_tid, blockIdx.x, what, a, b);
+  for (int t = 0; t < tl_block->nthreads; ++t)
+    fprintf(stderr, "  t%d: %s %d\n", t, tl_block->where[t], tl_block->where_id[t]);
+  fflush(stderr);
+  abort();
+}
+}  // namespace qpwc_emu
+
+namespace qpwc_emu {
 
 template <class F>
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
@@ -101,6 +123,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
   bs.nthreads = nt;
   bs.smem = (unsigned char*)aligned_alloc(1024, ((smem_bytes + 1023) / 1024 + 1) * 1024);
   bs.warps = std::vector<WarpState>((nt + 31) / 32);
+  bs.where.assign(nt, "running"); bs.where_id.assign(nt, 0);
   for (size_t w = 0; w < bs.warps.size(); ++w) bs.warps[w].nthreads = std::min(32, nt - (int)w * 32);
   const long long nblocks = (long long)grid.x * grid.y * grid.z;
   std::vector<std::thread> ths;
@@ -114,7 +137,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
       for (long long b = 0; b < nblocks; ++b) {
         blockIdx = dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long long)grid.x * grid.y)));
         body();
-        bs.bar.arrive_and_wait(nt);  // block boundary: shared memory is reused by the next block
+        bs.bar.arrive_and_wait(nt, "block-end");  // block boundary: shared memory is reused by the next block
       }
     });
   for (auto& th : ths) th.join();
@@ -125,13 +148,13 @@ inline uint32_t shfl_exchange(uint32_t v, int src_lane_of_me /* computed by call
 
 }  // namespace qpwc_emu
 
-inline void __syncthreads() { qpwc_emu::tl_block->bar.arrive_and_wait(qpwc_emu::tl_block->nthreads); }
+inline void __syncthreads() { qpwc_emu::tl_block->bar.arrive_and_wait(qpwc_emu::tl_block->nthreads, "__syncthreads"); }
 inline void __syncwarp(unsigned = 0xffffffffu) {
   auto& w = qpwc_emu::tl_block->warps[qpwc_emu::tl_tid / 32];
-  w.bar.arrive_and_wait(w.nthreads);
+  w.bar.arrive_and_wait(w.nthreads, "__syncwarp");
 }
 // bar.sync id, nthreads
-inline void qpwc_emu_named_barrier(int id, int nthreads) { qpwc_emu::tl_block->named[id].arrive_and_wait(nthreads); }
+inline void qpwc_emu_named_barrier(int id, int nthreads) { qpwc_emu::tl_block->named[id].arrive_and_wait(nthreads, "bar.sync(named)", id); }
 
 template <class T, class SrcFn>
 inline T qpwc_emu_shfl(T v, SrcFn src_of) {

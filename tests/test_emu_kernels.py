@@ -91,3 +91,35 @@ def test_emu_host_entry_and_errors():
         emu_lib.corr_fwd(prv, nxt, 4, ops=80)
     with pytest.raises(RuntimeError, match="2x2"):
         emu_lib.warp_fwd(np.zeros((1, 1, 4, 2), np.float32), np.zeros((1, 1, 4, 2), np.float32), "tfa")
+
+
+# ------------------------------------------------------------------ register-tiled kernels (d=4, C%4==0)
+TILED = [(1, 7, 60, 8), (2, 13, 70, 12), (1, 9, 57, 20), (1, 16, 16, 4)]
+
+
+@pytest.mark.parametrize("B,H,W,C", TILED)
+def test_emu_corr_fwd_tiled(B, H, W, C):
+    r = rng(10)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    ref = oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), 4)
+    got = emu_lib.corr_fwd(prv, nxt, 4)
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    got_s = emu_lib.corr_fwd(prv, nxt, 4, ops=81 + 3)
+    np.testing.assert_array_equal(got_s[..., :81], got)
+    assert np.isnan(got_s[..., 81:]).all()
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,H,W,C", TILED[:3])
+def test_emu_fused_fwd_tiled(mode, B, H, W, C):
+    r = rng(11)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    flo = (r.standard_normal((B, H, W, 2)) * 3).astype(np.float32)
+    ref = oracle.warp_cost_volume(*(a.astype(np.float64) for a in (prv, nxt, flo)), mode, 4)
+    got = emu_lib.warp_corr_fwd(prv, nxt, flo, mode, 4)
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    # the fused kernel warps with exactly the stand-alone warp kernel's arithmetic
+    comp = emu_lib.corr_fwd(prv, emu_lib.warp_fwd(nxt, flo, mode), 4)
+    np.testing.assert_allclose(got, comp, rtol=0, atol=1e-6 * np.abs(ref).max())
