@@ -21,8 +21,9 @@
 //     boundaries.  Plain: one thread issues the two TMA loads per chunk.  Fused: the second-frame
 //     stage is produced by the warpgroup itself -- 4 gathers + blend per halo pixel, bit-identical
 //     to the stand-alone warp kernel -- so warped features never reach HBM.
-//   * epilogue: accumulators -> (x 1/C, leaky relu) -> per-row staging in shared memory (transposes
-//     the per-thread 9x9 blocks into the NHWC 81-vector) -> coalesced 16-byte row stores.
+//   * epilogue: accumulators -> (x 1/C, leaky relu) -> a private per-row staging slot in shared
+//     memory, half a row (28 px) at a time (transposes the per-thread 9x9 blocks into the NHWC
+//     81-vector) -> coalesced 16-byte stores of the contiguous 28 x 324-byte run.
 #include "qpwc_async.cuh"
 
 namespace qpwc {
@@ -38,17 +39,17 @@ struct TiledCfg {
   static constexpr int P_BYTES = TH * PCOL * PXB, N_BYTES = NROW * NCOL * PXB;
   static constexpr int STAGE_BYTES = P_BYTES + N_BYTES;
   static constexpr int NCONS = TH * TWT, NPROD = 128, NTHREADS = NCONS + NPROD;
-  static constexpr int NG = TH / 2;                            // epilogue groups: rows g and g+NG
-  static constexpr int SLOT_BYTES = ((TW * NDISP * 4 + 127) / 128) * 128;
+  static constexpr int HALF = TW / 2;                          // epilogue: a row is staged in two halves of 28 px
+  static constexpr int SLOT_BYTES = ((HALF * NDISP * 4 + 127) / 128) * 128;
   static constexpr int TAPS_BYTES = WARP ? NROW * NCOL * 32 : 0;
   static constexpr int OFF_STAGING = NST * STAGE_BYTES;
-  static constexpr int OFF_TAPS = OFF_STAGING + NG * SLOT_BYTES;
+  static constexpr int OFF_TAPS = OFF_STAGING + TH * SLOT_BYTES;
   static constexpr int OFF_BARS = OFF_TAPS + TAPS_BYTES;
   static constexpr int SMEM_BYTES = OFF_BARS + 2 * NST * 8;
   static constexpr int FULL_COUNT = 1 + (WARP ? NPROD / 32 : 0);
   static constexpr int EMPTY_COUNT = NCONS / 32;
   static constexpr int REG_CONS = 152, REG_PROD = 56;         // 384*152 + 128*56 == 65536
-  static_assert(TH % 2 == 0 && P_BYTES % 256 == 0 && N_BYTES % 256 == 0, "tile shape");
+  static_assert(TW % 8 == 0 && P_BYTES % 256 == 0 && N_BYTES % 256 == 0 && TH <= 14, "tile shape");
   static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536 || TH != 6, "register budget");
 };
 
@@ -63,7 +64,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
                       int tiles_x, int tiles_y, int ntiles) {
   constexpr int D = Cfg::D, Q = Cfg::Q, NDISP = Cfg::NDISP, TH = Cfg::TH, TW = Cfg::TW;
   constexpr int NCOL = Cfg::NCOL, PCOL = Cfg::PCOL, NROW = Cfg::NROW, NST = Cfg::NST, KC = Cfg::KC;
-  constexpr int NCONS = Cfg::NCONS, NPROD = Cfg::NPROD, NG = Cfg::NG;
+  constexpr int NCONS = Cfg::NCONS, NPROD = Cfg::NPROD, HALF = Cfg::HALF;
 
   // dynamic shared memory starts at the CTA's window base (no static __shared__ in this kernel):
   // 1024-byte aligned, which the swizzle arithmetic relies on (checked below, once per CTA)
@@ -131,25 +132,46 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           // units: (halo pixel, 16-byte channel quad); lane pairs share a pixel => 32-byte reads
           const float* nb = nxt + (size_t)b * H * W * C + (size_t)c * KC;
           unsigned char* ns = sb + Cfg::P_BYTES;
-          for (int u = ptid; u < NROW * NCOL * 2; u += NPROD) {
-            const int pix = u >> 1, qd = u & 1;
-            const TapsEntry e = taps[pix];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e.o00 >= 0 && c * KC + qd * 4 < C) {
-              const float* base = nb + qd * 4;
-              const float4 v00 = __ldg(reinterpret_cast<const float4*>(base + (size_t)e.o00 * C));
-              const float4 v01 = __ldg(reinterpret_cast<const float4*>(base + (size_t)e.o01 * C));
-              const float4 v10 = __ldg(reinterpret_cast<const float4*>(base + (size_t)e.o10 * C));
-              const float4 v11 = __ldg(reinterpret_cast<const float4*>(base + (size_t)e.o11 * C));
-              Taps t;
-              t.o00 = t.o01 = t.o10 = t.o11 = 0;
-              t.w00 = e.w00; t.w01 = e.w01; t.w10 = e.w10; t.w11 = e.w11;
-              v.x = blend<Cfg::MODE>(t, v00.x, v01.x, v10.x, v11.x);
-              v.y = blend<Cfg::MODE>(t, v00.y, v01.y, v10.y, v11.y);
-              v.z = blend<Cfg::MODE>(t, v00.z, v01.z, v10.z, v11.z);
-              v.w = blend<Cfg::MODE>(t, v00.w, v01.w, v10.w, v11.w);
+          constexpr int NU = NROW * NCOL * 2;
+          constexpr int UB = 2;  // units in flight per thread: 8 independent 16-byte gathers
+          for (int u0 = ptid; u0 < NU; u0 += NPROD * UB) {
+            TapsEntry e[UB];
+            float4 v00[UB], v01[UB], v10[UB], v11[UB];
+            bool live[UB];
+#pragma unroll
+            for (int x = 0; x < UB; ++x) {
+              const int u = u0 + x * NPROD;
+              live[x] = false;
+              if (u < NU) {
+                const int pix = u >> 1, qd = u & 1;
+                e[x] = taps[pix];
+                live[x] = e[x].o00 >= 0 && c * KC + qd * 4 < C;
+                if (live[x]) {
+                  const float* base = nb + qd * 4;
+                  v00[x] = __ldg(reinterpret_cast<const float4*>(base + (size_t)e[x].o00 * C));
+                  v01[x] = __ldg(reinterpret_cast<const float4*>(base + (size_t)e[x].o01 * C));
+                  v10[x] = __ldg(reinterpret_cast<const float4*>(base + (size_t)e[x].o10 * C));
+                  v11[x] = __ldg(reinterpret_cast<const float4*>(base + (size_t)e[x].o11 * C));
+                }
+              }
             }
-            *reinterpret_cast<float4*>(ns + swz32((uint32_t)(pix * Cfg::PXB + qd * 16))) = v;
+#pragma unroll
+            for (int x = 0; x < UB; ++x) {
+              const int u = u0 + x * NPROD;
+              if (u < NU) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live[x]) {
+                  Taps t;
+                  t.o00 = t.o01 = t.o10 = t.o11 = 0;
+                  t.w00 = e[x].w00; t.w01 = e[x].w01; t.w10 = e[x].w10; t.w11 = e[x].w11;
+                  v.x = blend<Cfg::MODE>(t, v00[x].x, v01[x].x, v10[x].x, v11[x].x);
+                  v.y = blend<Cfg::MODE>(t, v00[x].y, v01[x].y, v10[x].y, v11[x].y);
+                  v.z = blend<Cfg::MODE>(t, v00[x].z, v01[x].z, v10[x].z, v11[x].z);
+                  v.w = blend<Cfg::MODE>(t, v00[x].w, v01[x].w, v10[x].w, v11[x].w);
+                }
+                *reinterpret_cast<float4*>(ns + swz32((uint32_t)((u >> 1) * Cfg::PXB + (u & 1) * 16))) = v;
+              }
+            }
           }
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&full[stage]);
@@ -166,10 +188,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
 #pragma unroll
     for (int k = 0; k < Q; ++k) a_off[k] = swz32((uint32_t)((ti * PCOL + tc + 2 * D - k) * Cfg::PXB));
     const float inv_c = 1.f / (float)C;
-    const int gi = ti % NG;
-    const bool first = ti < NG;
-    const int gt = (ti / NG) * NCOL + tc;  // thread index inside the 128-thread epilogue group
-    float* slot = reinterpret_cast<float*>(smem + Cfg::OFF_STAGING + gi * Cfg::SLOT_BYTES);
+    float* slot = reinterpret_cast<float*>(smem + Cfg::OFF_STAGING + ti * Cfg::SLOT_BYTES);  // private to this row
 
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -211,33 +230,37 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
       }
 
       // -------------------------------------------------------------------------- epilogue
+      // Each tile row (2 warps, named barrier 1+ti) stages its 56 px x 81 outputs through a
+      // private slot in two halves of 28 px and copies them out as one contiguous run -- rows
+      // never wait for each other.
       const int twv = min(TW, W - j0);  // valid pixel columns of this tile
+      const int i = i0 + ti;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        named_bar_sync(1 + gi, 2 * NCOL);  // slot free / previous half copied out
-        if ((half == 0) == first) {
+        const int lp0 = half * HALF;
+        const int lp1 = min(lp0 + HALF, twv);
+        named_bar_sync(1 + ti, NCOL);  // previous copy-out of this slot has finished
 #pragma unroll
-          for (int k = 0; k < Q; ++k) {
-            const int lp = tc - k;  // local pixel column of acc[.][k]
-            if (lp >= 0 && lp < twv) {
+        for (int k = 0; k < Q; ++k) {
+          const int lp = tc - k;  // local pixel column of acc[.][k]
+          if (lp >= lp0 && lp < lp1) {
+            float* dstp = slot + (lp - lp0) * NDISP + k;
 #pragma unroll
-              for (int m = 0; m < Q; ++m) slot[lp * NDISP + m * Q + k] = lrelu(acc[m][k] * inv_c, slope);
-            }
+            for (int m = 0; m < Q; ++m) dstp[m * Q] = lrelu(acc[m][k] * inv_c, slope);
           }
         }
-        named_bar_sync(1 + gi, 2 * NCOL);  // slot complete
-        const int i = i0 + gi + half * NG;
-        if (i < H) {
-          float* dst = out + ((size_t)((size_t)b * H + i) * W + j0) * (size_t)ops;
-          const int n = twv * NDISP;
+        named_bar_sync(1 + ti, NCOL);  // half-slot complete
+        if (i < H && lp1 > lp0) {
+          float* dst = out + ((size_t)((size_t)b * H + i) * W + j0 + lp0) * (size_t)ops;
+          const int n = (lp1 - lp0) * NDISP;
           if (ops == NDISP && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
             const float4* s4 = reinterpret_cast<const float4*>(slot);
             float4* d4 = reinterpret_cast<float4*>(dst);
-            for (int e = gt; e < (n >> 2); e += 2 * NCOL) d4[e] = s4[e];
+            for (int e = tc; e < (n >> 2); e += NCOL) d4[e] = s4[e];
           } else if (ops == NDISP) {
-            for (int e = gt; e < n; e += 2 * NCOL) dst[e] = slot[e];
+            for (int e = tc; e < n; e += NCOL) dst[e] = slot[e];
           } else {
-            for (int e = gt; e < n; e += 2 * NCOL) dst[(size_t)(e / NDISP) * ops + (e % NDISP)] = slot[e];
+            for (int e = tc; e < n; e += NCOL) dst[(size_t)(e / NDISP) * ops + (e % NDISP)] = slot[e];
           }
         }
       }
