@@ -128,17 +128,20 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__
         for (int k = 0; k < V; ++k) {
           if (MODE == QPWC_MODE_TF) {
             // gather_nd grad: scatter w*g into the four clipped taps
-            a00[k] = t.w00 * g[k]; a10[k] = t.w10 * g[k]; a01[k] = t.w01 * g[k]; a11[k] = t.w11 * g[k];
+            a00[k] = __fmul_rn(t.w00, g[k]); a10[k] = __fmul_rn(t.w10, g[k]);
+            a01[k] = __fmul_rn(t.w01, g[k]); a11[k] = __fmul_rn(t.w11, g[k]);
           } else {
             const float ax = t.w00, ay = t.w01;
             const float top = __fadd_rn(__fmul_rn(ax, __fsub_rn(v01[k], v00[k])), v00[k]);
             const float bot = __fadd_rn(__fmul_rn(ax, __fsub_rn(v11[k], v10[k])), v10[k]);
-            gy += g[k] * (bot - top);
-            const float g_bot = ay * g[k];
-            const float g_top = g[k] - g_bot;
-            gx += g_top * (v01[k] - v00[k]) + g_bot * (v11[k] - v10[k]);
-            const float g_tr = ax * g_top, g_br = ax * g_bot;
-            a01[k] = g_tr; a00[k] = g_top - g_tr; a11[k] = g_br; a10[k] = g_bot - g_br;
+            // every product/sum rounded on its own, like the TF gradient graph (and the oracle)
+            gy = __fadd_rn(gy, __fmul_rn(g[k], __fsub_rn(bot, top)));
+            const float g_bot = __fmul_rn(ay, g[k]);
+            const float g_top = __fsub_rn(g[k], g_bot);
+            gx = __fadd_rn(gx, __fadd_rn(__fmul_rn(g_top, __fsub_rn(v01[k], v00[k])),
+                                         __fmul_rn(g_bot, __fsub_rn(v11[k], v10[k]))));
+            const float g_tr = __fmul_rn(ax, g_top), g_br = __fmul_rn(ax, g_bot);
+            a01[k] = g_tr; a00[k] = __fsub_rn(g_top, g_tr); a11[k] = g_br; a10[k] = __fsub_rn(g_bot, g_br);
           }
         }
         if (MODE == QPWC_MODE_TF) {
@@ -150,8 +153,13 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__
           const float ay1 = __fsub_rn((float)y1, y), ay0 = __fsub_rn(y, (float)y0);
 #pragma unroll
           for (int k = 0; k < V; ++k) {
-            gx += g[k] * (((-ay1 * v00[k] + -ay0 * v10[k]) + ay1 * v01[k]) + ay0 * v11[k]);
-            gy += g[k] * (((-ax1 * v00[k] + ax1 * v10[k]) + -ax0 * v01[k]) + ax0 * v11[k]);
+            // un-contracted on purpose: clipped taps (Ia == Ic, ...) must cancel exactly as in TF
+            const float sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-ay1, v00[k]), __fmul_rn(-ay0, v10[k])),
+                                                 __fmul_rn(ay1, v01[k])), __fmul_rn(ay0, v11[k]));
+            const float sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-ax1, v00[k]), __fmul_rn(ax1, v10[k])),
+                                                 __fmul_rn(-ax0, v01[k])), __fmul_rn(ax0, v11[k]));
+            gx = __fadd_rn(gx, __fmul_rn(g[k], sx));
+            gy = __fadd_rn(gy, __fmul_rn(g[k], sy));
           }
         }
         vatomic_add<V>(g_img + boff + (size_t)t.o00 * C + co, a00);

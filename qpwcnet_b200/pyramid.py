@@ -94,9 +94,33 @@ class PyramidWorkload:
         return ops.cost_volume_into(self.outputs[k], prv, nxt, self.d)
 
     def step(self):
-        """One pass of the hot path over the batch: 1 cost volume + 4 fused warp->cost volumes."""
+        """One pass of the hot path over the batch: 1 cost volume + 4 fused warp->cost volumes
+        (five C-ABI launches on the current stream)."""
         for k in range(len(self.levels)):
             self.run_level(k)
+        return self.outputs
+
+    def capture(self):
+        """Record step() into a CUDA graph (device-resident workloads only): the five launches --
+        TMA descriptors included, they are plain kernel parameters -- replay with one
+        cudaGraphLaunch, which removes the per-call host overhead from the launch-bound coarse
+        levels.  Returns self; use replay() afterwards."""
+        if not self.outputs[0].is_cuda:
+            raise RuntimeError("CUDA graphs need device-resident buffers")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up off the capture: smem attributes, entry points
+            for _ in range(2):
+                self.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.step()
+        return self
+
+    def replay(self):
+        self._graph.replay()
         return self.outputs
 
     launches_per_step = 5
