@@ -162,10 +162,24 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__
             gy = __fadd_rn(gy, __fmul_rn(g[k], sy));
           }
         }
+        // Clipped taps coincide (mode TF, sample outside the image): fold them in registers first.
+        // Their weights are exact negatives of each other, so the fold cancels exactly -- as the
+        // reference's sequential scatter does -- instead of leaving +-|w*g| rounding residue in an
+        // order-dependent atomic sum; it also saves the redundant atomics.
+        const bool dupx = (MODE == QPWC_MODE_TF) && (t.o00 == t.o01);
+        const bool dupy = (MODE == QPWC_MODE_TF) && (t.o00 == t.o10);
+        if (dupx) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) { a00[k] = __fadd_rn(a00[k], a01[k]); a10[k] = __fadd_rn(a10[k], a11[k]); }
+        }
+        if (dupy) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) { a00[k] = __fadd_rn(a00[k], a10[k]); a01[k] = __fadd_rn(a01[k], a11[k]); }
+        }
         vatomic_add<V>(g_img + boff + (size_t)t.o00 * C + co, a00);
-        vatomic_add<V>(g_img + boff + (size_t)t.o01 * C + co, a01);
-        vatomic_add<V>(g_img + boff + (size_t)t.o10 * C + co, a10);
-        vatomic_add<V>(g_img + boff + (size_t)t.o11 * C + co, a11);
+        if (!dupx) vatomic_add<V>(g_img + boff + (size_t)t.o01 * C + co, a01);
+        if (!dupy) vatomic_add<V>(g_img + boff + (size_t)t.o10 * C + co, a10);
+        if (!dupx && !dupy) vatomic_add<V>(g_img + boff + (size_t)t.o11 * C + co, a11);
       }
     }
     // fixed-order butterfly over the G lanes of the group
