@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import struct
 from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong,
                     c_size_t, c_uint8, c_uint16, c_uint32, c_uint64, c_void_p)
 
@@ -108,45 +109,53 @@ class _DLManagedTensorVersioned(Structure):
                 ("flags", c_uint64), ("dl_tensor", _DLTensor)]
 
 
+_DLT = struct.Struct("<QiiiBBHQQQ")
+_I64 = [struct.Struct("<%dq" % n) for n in range(9)]
+_string_at = ctypes.string_at
 _capi = ctypes.pythonapi
-_capi.PyCapsule_GetName.restype = c_char_p
-_capi.PyCapsule_GetName.argtypes = [ctypes.py_object]
-_capi.PyCapsule_GetPointer.restype = c_void_p
-_capi.PyCapsule_GetPointer.argtypes = [ctypes.py_object, c_char_p]
+_PyCapsule_GetName = _capi.PyCapsule_GetName
+_PyCapsule_GetName.restype = c_char_p
+_PyCapsule_GetName.argtypes = [ctypes.py_object]
+_PyCapsule_GetPointer = _capi.PyCapsule_GetPointer
+_PyCapsule_GetPointer.restype = c_void_p
+_PyCapsule_GetPointer.argtypes = [ctypes.py_object, c_char_p]
 
 
 class DLView:
     """Pointer/shape/device of a tensor read out of its DLPack capsule.  Holds the capsule (and so
-    the producer's memory) alive for as long as the view lives."""
+    the producer's memory) alive for as long as the view lives.  Pointer, device and dtype are read
+    eagerly (one 48-byte unpack -- this sits on the launch path); shape/strides on demand."""
 
-    __slots__ = ("ptr", "shape", "strides", "device_type", "device_id", "_capsule")
+    __slots__ = ("ptr", "device_type", "device_id", "ndim", "_shape_p", "_strides_p", "_capsule")
 
-    def __init__(self, capsule):
-        name = _capi.PyCapsule_GetName(capsule)
-        if name == b"dltensor":
-            raw = _capi.PyCapsule_GetPointer(capsule, b"dltensor")
-            t = ctypes.cast(raw, POINTER(_DLManagedTensor)).contents.dl_tensor
-        elif name == b"dltensor_versioned":
-            raw = _capi.PyCapsule_GetPointer(capsule, b"dltensor_versioned")
-            t = ctypes.cast(raw, POINTER(_DLManagedTensorVersioned)).contents.dl_tensor
-        else:
-            raise TypeError(f"not an unconsumed DLPack capsule (name={name!r})")
-        if (t.dtype.code, t.dtype.bits, t.dtype.lanes) != (2, 32, 1):
-            raise TypeError("libqpwc takes float32 tensors "
-                            f"(DLPack dtype code={t.dtype.code} bits={t.dtype.bits})")
-        nd = t.ndim
-        self.shape = tuple(int(t.shape[k]) for k in range(nd))
-        self.strides = None if not t.strides else tuple(int(t.strides[k]) for k in range(nd))
-        self.ptr = (t.data or 0) + int(t.byte_offset)
-        self.device_type = int(t.device.device_type)
-        self.device_id = int(t.device.device_id)
+    def __init__(self, capsule, name=b"dltensor"):
+        raw = _PyCapsule_GetPointer(capsule, name)
+        # DLTensor = {void* data; int32 device_type, device_id; int32 ndim; uint8 code, bits;
+        # uint16 lanes; int64* shape; int64* strides; uint64 byte_offset}: 48 bytes, first member
+        # of DLManagedTensor, at offset 32 of DLManagedTensorVersioned.
+        (data, self.device_type, self.device_id, self.ndim, code, bits, lanes, self._shape_p,
+         self._strides_p, byte_offset) = _DLT.unpack(_string_at(raw if name == b"dltensor" else raw + 32, 48))
+        if code != 2 or bits != 32 or lanes != 1:
+            raise TypeError(f"libqpwc takes float32 tensors (DLPack dtype code={code} bits={bits})")
+        self.ptr = data + byte_offset
         self._capsule = capsule
 
+    @property
+    def shape(self):
+        nd = self.ndim
+        return _I64[nd].unpack(_string_at(self._shape_p, 8 * nd)) if nd else ()
+
+    @property
+    def strides(self):
+        nd = self.ndim
+        return _I64[nd].unpack(_string_at(self._strides_p, 8 * nd)) if (self._strides_p and nd) else None
+
     def is_contiguous(self) -> bool:
-        if self.strides is None:
+        strides = self.strides
+        if strides is None:
             return True
         expect = 1
-        for n, s in zip(reversed(self.shape), reversed(self.strides)):
+        for n, s in zip(reversed(self.shape), reversed(strides)):
             if n != 1 and s != expect:
                 return False
             expect *= n
@@ -161,14 +170,31 @@ class DLView:
         return self.device_type in (kDLCPU, kDLCUDAHost)
 
 
+try:  # torch is the usual producer, but any __dlpack__ object works
+    import torch as _torch
+    _to_dlpack = _torch.utils.dlpack.to_dlpack
+except ImportError:  # pragma: no cover
+    _torch = None
+
+
+def dlptr(x):
+    """Launch-path shortcut of dlview() for torch tensors the caller keeps alive: returns
+    ``(device pointer, DLPack device_type)`` read from the tensor's DLPack export."""
+    cap = _to_dlpack(x.detach() if x.requires_grad else x)
+    (data, devt, _id, _nd, code, bits, lanes, _s, _st, off) = _DLT.unpack(
+        _string_at(_PyCapsule_GetPointer(cap, b"dltensor"), 48))
+    if code != 2 or bits != 32 or lanes != 1:
+        raise TypeError(f"libqpwc takes float32 tensors (DLPack dtype code={code} bits={bits})")
+    return data + off, devt
+
+
 def dlview(x) -> DLView:
     """DLPack view of a tensor-like (torch.Tensor, or any object with ``__dlpack__``)."""
-    try:
-        import torch
-        if isinstance(x, torch.Tensor):
-            return DLView(torch.utils.dlpack.to_dlpack(x.detach()))
-    except ImportError:  # pragma: no cover
-        pass
+    if _torch is not None and isinstance(x, _torch.Tensor):
+        # torch exports the legacy (unversioned) capsule; detach(): exporting a tensor that requires
+        # grad is refused by torch, the autograd Functions own the graph anyway
+        return DLView(_to_dlpack(x.detach() if x.requires_grad else x))
     if hasattr(x, "__dlpack__"):
-        return DLView(x.__dlpack__())
+        cap = x.__dlpack__()
+        return DLView(cap, _PyCapsule_GetName(cap))
     raise TypeError(f"cannot export {type(x).__name__} through DLPack")

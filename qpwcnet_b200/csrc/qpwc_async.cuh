@@ -58,6 +58,18 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const TensorMap* tm,
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// generic-proxy writes (st.shared) -> async-proxy reads (bulk store): order them
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// asynchronous 1-D bulk store shared -> global (TMA engine); bytes % 16 == 0, both 16-byte aligned
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still have to READ their shared-memory source
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -138,6 +150,10 @@ inline void tma_load_4d(void* smem_dst, const TensorMap* tm, uint64_t* bar, int 
   EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
   b->tx -= (int32_t)bytes; emu_detail::settle(b);
 }
+inline void fence_proxy_async() {}
+inline void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) { memcpy(gdst, smem_src, bytes); }
+inline void bulk_commit() {}
+template <int N> inline void bulk_wait_read() {}
 inline void named_bar_sync(int id, int nthreads) { qpwc_emu_named_barrier(id, nthreads); }
 template <int N> inline void setmaxnreg_inc() {}
 template <int N> inline void setmaxnreg_dec() {}

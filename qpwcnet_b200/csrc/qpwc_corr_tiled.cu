@@ -21,9 +21,11 @@
 //     boundaries.  Plain: one thread issues the two TMA loads per chunk.  Fused: the second-frame
 //     stage is produced by the warpgroup itself -- 4 gathers + blend per halo pixel, bit-identical
 //     to the stand-alone warp kernel -- so warped features never reach HBM.
-//   * epilogue: accumulators -> (x 1/C, leaky relu) -> a private per-row staging slot in shared
+//   * epilogue: accumulators -> (x 1/C, leaky relu) -> private per-row staging slots in shared
 //     memory, half a row (28 px) at a time (transposes the per-thread 9x9 blocks into the NHWC
-//     81-vector) -> coalesced 16-byte stores of the contiguous 28 x 324-byte run.
+//     81-vector) -> one asynchronous TMA bulk store per contiguous 28 x 324-byte run.
+#include <stdlib.h>
+
 #include "qpwc_async.cuh"
 
 namespace qpwc {
@@ -34,18 +36,24 @@ struct TiledCfg {
   static constexpr int TH = TH_, TWT = 64, TW = TWT - 2 * D;  // 56 pixel columns per tile
   static constexpr int WARP = WARP_, MODE = MODE_;
   static constexpr int KC = 8, PXB = KC * 4;                   // 32 bytes per pixel per stage
-  static constexpr int NROW = TH + 2 * D, NCOL = TWT, PCOL = TW + 4 * D;  // 72
+  static constexpr int NROW = TH + 2 * D, NCOL = TWT, PCOL = TW;         // P tile: the 56 valid columns only
   static constexpr int NST = 3;
   static constexpr int P_BYTES = TH * PCOL * PXB, N_BYTES = NROW * NCOL * PXB;
   static constexpr int STAGE_BYTES = P_BYTES + N_BYTES;
   static constexpr int NCONS = TH * TWT, NPROD = 128, NTHREADS = NCONS + NPROD;
-  static constexpr int HALF = TW / 2;                          // epilogue: a row is staged in two halves of 28 px
-  static constexpr int SLOT_BYTES = ((HALF * NDISP * 4 + 127) / 128) * 128;
+  // Epilogue staging.  AGENT (plain variant): one full-row slot per tile row; consumer warps only
+  // deposit their accumulators and move on, a store-agent warp hands the row to the TMA engine.
+  // Fused variant: the taps table needs the room => half-row slots, stores issued by the row itself.
+  static constexpr int AGENT = WARP ? 0 : 1;
+  static constexpr int HALF = TW / 2;
+  static constexpr int SLOT_BYTES = (((AGENT ? TW : HALF) * NDISP * 4 + 127) / 128) * 128;
+  static constexpr int NSLOT = 1;
   static constexpr int TAPS_BYTES = WARP ? NROW * NCOL * 32 : 0;
   static constexpr int OFF_STAGING = NST * STAGE_BYTES;
-  static constexpr int OFF_TAPS = OFF_STAGING + TH * SLOT_BYTES;
+  static constexpr int OFF_TAPS = OFF_STAGING + TH * NSLOT * SLOT_BYTES;
   static constexpr int OFF_BARS = OFF_TAPS + TAPS_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BARS + 2 * NST * 8;
+  static constexpr int SMEM_BYTES = OFF_BARS + 2 * NST * 8 + 2 * TH * 8;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
   static constexpr int FULL_COUNT = 1 + (WARP ? NPROD / 32 : 0);
   static constexpr int EMPTY_COUNT = NCONS / 32;
   static constexpr int REG_CONS = 152, REG_PROD = 56;         // 384*152 + 128*56 == 65536
@@ -61,7 +69,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
 corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CONSTANT TensorMap tmN,
                       const float* __restrict__ nxt, const float* __restrict__ flow,
                       float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
-                      int tiles_x, int tiles_y, int ntiles) {
+                      int tiles_x, int tiles_y, int ntiles, int ablate) {
   constexpr int D = Cfg::D, Q = Cfg::Q, NDISP = Cfg::NDISP, TH = Cfg::TH, TW = Cfg::TW;
   constexpr int NCOL = Cfg::NCOL, PCOL = Cfg::PCOL, NROW = Cfg::NROW, NST = Cfg::NST, KC = Cfg::KC;
   constexpr int NCONS = Cfg::NCONS, NPROD = Cfg::NPROD, HALF = Cfg::HALF;
@@ -71,6 +79,8 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
   QPWC_DYN_SMEM(smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
   uint64_t* empty = full + NST;
+  uint64_t* sfull = empty + NST;   // per tile row: both consumer warps deposited their outputs
+  uint64_t* sfree = sfull + TH;    // per tile row: the store of the previous tile has drained the slot
 
   const int tid = threadIdx.x;
   const int nchunks = (C + KC - 1) / KC;
@@ -80,6 +90,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
     if (smem_u32(smem) & 255u) __trap();
 #endif
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], Cfg::FULL_COUNT); mbar_init(&empty[s], Cfg::EMPTY_COUNT); }
+    for (int r = 0; r < TH; ++r) { mbar_init(&sfull[r], NCOL / 32); mbar_init(&sfree[r], 1); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -93,7 +104,42 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
     // idle along on the empty barriers: nothing would gate on them, so a slow one could fall two
     // phases behind and alias the parity wait (found by the CPU emulation harness).  In the fused
     // variant every producer warp arrives on `full`, which keeps all of them within one phase.
+    if (Cfg::AGENT && ptid >= 32 && ptid < 64) {
+      // ---- store agent (plain variant): waits for each row's slot, issues its bulk store, and
+      // releases the slots once the engine has read them.  Consumers never wait for stores.
+      if (ablate & 2) return;
+      const int lane = ptid & 31;
+      uint32_t n = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+        const int tx = tile % tiles_x;
+        const int ty = (tile / tiles_x) % tiles_y;
+        const int b = tile / (tiles_x * tiles_y);
+        const int i0 = ty * TH, j0 = tx * TW;
+        const int twv = min(TW, W - j0);
+        for (int r = 0; r < TH; ++r) {
+          mbar_wait(&sfull[r], n & 1u);
+          const int i = i0 + r;
+          if (i < H) {
+            const float* slot = reinterpret_cast<const float*>(smem + Cfg::OFF_STAGING + r * Cfg::SLOT_BYTES);
+            float* dst = out + ((size_t)((size_t)b * H + i) * W + j0) * (size_t)ops;
+            const int cnt = twv * NDISP;
+            if (ops == NDISP && (cnt & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+              if (lane == 0) bulk_store(dst, slot, (uint32_t)cnt * 4u);
+            } else if (ops == NDISP) {  // unaligned row: plain coalesced copy
+              for (int e = lane; e < cnt; e += 32) dst[e] = slot[e];
+            } else {                    // strided output (concat buffer)
+              for (int e = lane; e < cnt; e += 32) dst[(size_t)(e / NDISP) * ops + (e % NDISP)] = slot[e];
+            }
+          }
+        }
+        if (lane == 0) { bulk_commit(); bulk_wait_read<0>(); }
+        __syncwarp();
+        if (lane == 0) for (int r = 0; r < TH; ++r) mbar_arrive(&sfree[r]);
+      }
+      return;
+    }
     if (!Cfg::WARP && ptid != 0) return;
+    if (ablate & 4) return;  // dev ablation: no loads at all
     TapsEntry* taps = reinterpret_cast<TapsEntry*>(smem + Cfg::OFF_TAPS);
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -125,7 +171,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
         if (ptid == 0) {
           mbar_arrive_expect_tx(&full[stage], Cfg::P_BYTES + (Cfg::WARP ? 0 : Cfg::N_BYTES));
-          tma_load_4d(sb, &tmP, &full[stage], c * KC, j0 - 2 * D, i0, b);
+          tma_load_4d(sb, &tmP, &full[stage], c * KC, j0, i0, b);
           if (!Cfg::WARP) tma_load_4d(sb + Cfg::P_BYTES, &tmN, &full[stage], c * KC, j0 - D, i0 - D, b);
         }
         if (Cfg::WARP) {
@@ -186,11 +232,17 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
     const uint32_t nb_off = Cfg::P_BYTES + swz32((uint32_t)((ti * NCOL + tc) * Cfg::PXB));
     uint32_t a_off[Q];
 #pragma unroll
-    for (int k = 0; k < Q; ++k) a_off[k] = swz32((uint32_t)((ti * PCOL + tc + 2 * D - k) * Cfg::PXB));
+    for (int k = 0; k < Q; ++k) {
+      // first-frame pixel column of acc[.][k] is lp = tc - k; columns outside the tile belong to
+      // accumulators that are never stored, so they may read any resident pixel: clamp
+      const int lp = min(max(tc - k, 0), TW - 1);
+      a_off[k] = swz32((uint32_t)((ti * PCOL + lp) * Cfg::PXB));
+    }
     const float inv_c = 1.f / (float)C;
-    float* slot = reinterpret_cast<float*>(smem + Cfg::OFF_STAGING + ti * Cfg::SLOT_BYTES);  // private to this row
+    float* slot0 = reinterpret_cast<float*>(smem + Cfg::OFF_STAGING + ti * Cfg::NSLOT * Cfg::SLOT_BYTES);  // private to this row
+    const bool leader = (tc == 0);
 
-    uint32_t g = 0;
+    uint32_t g = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int tx = tile % tiles_x;
       const int ty = (tile / tiles_x) % tiles_y;
@@ -205,8 +257,9 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
 
       for (int c = 0; c < nchunks; ++c, ++g) {
         const int stage = g % NST;
-        mbar_wait(&full[stage], (g / NST) & 1u);
+        if (!(ablate & 4)) mbar_wait(&full[stage], (g / NST) & 1u);
         const unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
+        if (!(ablate & 1))
 #pragma unroll
         for (int qd = 0; qd < 2; ++qd) {
           const unsigned char* nbp = sb + (nb_off ^ (uint32_t)(qd << 4));
@@ -226,20 +279,42 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (lane == 0 && !(ablate & 4)) mbar_arrive(&empty[stage]);
       }
+      if (ablate & 2) continue;  // dev ablation: no epilogue
 
       // -------------------------------------------------------------------------- epilogue
-      // Each tile row (2 warps, named barrier 1+ti) stages its 56 px x 81 outputs through a
-      // private slot in two halves of 28 px and copies them out as one contiguous run -- rows
-      // never wait for each other.
+      // Each tile row (2 warps, named barrier 1+ti) stages its 56 px x 81 outputs in two halves of
+      // 28 px through private slots and hands each contiguous 28 x 324-byte run to the TMA engine
+      // (cp.async.bulk shared->global): no copy loop, rows never wait for each other, and the
+      // store drains while the next tile is being computed.
       const int twv = min(TW, W - j0);  // valid pixel columns of this tile
+      if (Cfg::AGENT) {
+        // deposit the 9x9 block (transposed into the NHWC 81-vector order) and carry on
+        mbar_wait(&sfree[ti], (tcount & 1u) ^ 1u);  // previous tile's store has drained this slot
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+          const int lp = tc - k;  // local pixel column of acc[.][k]
+          if (lp >= 0 && lp < twv) {
+            float* dstp = slot0 + lp * NDISP + k;
+#pragma unroll
+            for (int m = 0; m < Q; ++m) dstp[m * Q] = lrelu(acc[m][k] * inv_c, slope);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sfull[ti]);
+        ++tcount;
+        continue;
+      }
       const int i = i0 + ti;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int lp0 = half * HALF;
+      for (int half = 0; half < 2; ++half) {        const int lp0 = half * HALF;
         const int lp1 = min(lp0 + HALF, twv);
-        named_bar_sync(1 + ti, NCOL);  // previous copy-out of this slot has finished
+        float* slot = slot0 + (Cfg::NSLOT == 2 ? half : 0) * (Cfg::SLOT_BYTES / 4);
+        // the bulk store that last read this slot (NSLOT==2: a tile ago; else the previous half)
+        if (leader) { if (Cfg::NSLOT == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+        named_bar_sync(1 + ti, NCOL);
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
           const int lp = tc - k;  // local pixel column of acc[.][k]
@@ -249,22 +324,22 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
             for (int m = 0; m < Q; ++m) dstp[m * Q] = lrelu(acc[m][k] * inv_c, slope);
           }
         }
+        fence_proxy_async();
         named_bar_sync(1 + ti, NCOL);  // half-slot complete
         if (i < H && lp1 > lp0) {
           float* dst = out + ((size_t)((size_t)b * H + i) * W + j0 + lp0) * (size_t)ops;
           const int n = (lp1 - lp0) * NDISP;
           if (ops == NDISP && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-            const float4* s4 = reinterpret_cast<const float4*>(slot);
-            float4* d4 = reinterpret_cast<float4*>(dst);
-            for (int e = tc; e < (n >> 2); e += NCOL) d4[e] = s4[e];
-          } else if (ops == NDISP) {
-            for (int e = tc; e < n; e += NCOL) dst[e] = slot[e];
-          } else {
-            for (int e = tc; e < n; e += NCOL) dst[(size_t)(e / NDISP) * ops + (e % NDISP)] = slot[e];
+            if (leader) bulk_store(dst, slot, (uint32_t)n * 4u);
+          } else {  // strided / unaligned output: plain coalesced copy by the row's 64 threads
+            if (ops == NDISP) { for (int e = tc; e < n; e += NCOL) dst[e] = slot[e]; }
+            else { for (int e = tc; e < n; e += NCOL) dst[(size_t)(e / NDISP) * ops + (e % NDISP)] = slot[e]; }
           }
         }
+        if (leader) bulk_commit();  // one group per half, also when empty: keeps wait_group counts uniform
       }
     }
+    if (!Cfg::AGENT && leader) bulk_wait_read<0>();  // shared memory must outlive the engine's reads
   }
 }
 
@@ -314,11 +389,18 @@ static int sm_count() {
 static int sm_count() { return 3; }  // small persistent grid: exercises the multi-tile loop
 #endif
 
+// QPWC_ABLATE (dev only): bit0 skip FFMA loop, bit1 skip epilogue, bit2 skip loads+pipeline
+static int ablate_flags() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("QPWC_ABLATE"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 template <class Cfg>
 static int run_tiled(const float* prv, const float* nxt, const float* flow, float* out, int B, int H,
                      int W, int C, float slope, long long ops, cudaStream_t stream) {
   TensorMap tmP, tmN;
-  if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::KC, Cfg::PCOL, Cfg::TH)) return QPWC_ERR_CUDA;
+  if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::KC, Cfg::PCOL, Cfg::TH)) return QPWC_ERR_CUDA;  // box 8 x 56 x TH
   if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, Cfg::KC, Cfg::NCOL, Cfg::NROW)) return QPWC_ERR_CUDA;
   const int tiles_x = cdiv(W, Cfg::TW), tiles_y = cdiv(H, Cfg::TH);
   const long long nt = (long long)tiles_x * tiles_y * B;
@@ -335,7 +417,7 @@ static int run_tiled(const float* prv, const float* nxt, const float* flow, floa
   }
 #endif
   QPWC_LAUNCH(k, grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream, tmP, tmN, nxt, flow, out, B, H, W, C, slope, ops,
-              tiles_x, tiles_y, ntiles);
+              tiles_x, tiles_y, ntiles, ablate_flags());
   return check_launch("corr_fwd_tiled");
 }
 

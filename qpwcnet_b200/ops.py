@@ -15,11 +15,30 @@ from __future__ import annotations
 import torch
 
 from . import _cabi
-from ._cabi import WARP_MODES, check, dlview, lib
+from ._cabi import WARP_MODES, check, dlptr, dlview, kDLCUDA, kDLCUDAManaged, lib
 
 
 def _stream_ptr(device) -> int:
-    return int(torch.cuda.current_stream(device).cuda_stream)
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on_device:
+    """`with _on_device(dev):` -- make `dev` current for the C call; a no-op (no context push) in
+    the common case where it already is."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _prep(t: torch.Tensor, name: str, last: int | None = None) -> torch.Tensor:
@@ -41,12 +60,18 @@ def _same(a: torch.Tensor, b: torch.Tensor, what: str):
         raise ValueError(f"{what}: device mismatch {a.device} vs {b.device}")
 
 
+class _V:
+    __slots__ = ("ptr", "on_cuda")
+
+    def __init__(self, t):
+        self.ptr, devt = dlptr(t)
+        self.on_cuda = devt == kDLCUDA or devt == kDLCUDAManaged
+
+
 def _views(*ts):
-    vs = [dlview(t) for t in ts]
-    for v in vs:
-        if not v.is_contiguous():
-            raise ValueError("libqpwc needs dense NHWC tensors")
-    return vs
+    # every tensor reaching this point went through _prep()/torch.empty(): dense by construction;
+    # pointer and device come out of the tensor's DLPack export
+    return [_V(t) for t in ts]
 
 
 def _mode(mode) -> int:
@@ -66,7 +91,7 @@ def _corr_fwd(prv, nxt, d, slope, out=None, out_stride=None):
         out = torch.empty((B, H, W, ops), dtype=torch.float32, device=prv.device)
     vp, vn, vo = _views(prv, nxt, out)
     if vp.on_cuda:
-        with torch.cuda.device(prv.device):
+        with _on_device(prv.device):
             check(lib().qpwc_corr_fwd(vp.ptr, vn.ptr, vo.ptr, B, H, W, C, d, slope, ops,
                                       _stream_ptr(prv.device)))
     else:
@@ -83,7 +108,7 @@ def _corr_bwd(prv, nxt, out, g_out, d, slope):
     g_prv = torch.empty_like(prv)
     g_nxt = torch.empty_like(nxt)
     vp, vn, vo, vg, vgp, vgn = _views(prv, nxt, out, g_out, g_prv, g_nxt)
-    with torch.cuda.device(prv.device):
+    with _on_device(prv.device):
         check(lib().qpwc_corr_bwd(vp.ptr, vn.ptr, vo.ptr, vg.ptr, vgp.ptr, vgn.ptr, B, H, W, C, d,
                                   slope, ops, _stream_ptr(prv.device)))
     return g_prv, g_nxt
@@ -94,7 +119,7 @@ def _warp_fwd(img, flow, mode):
     out = torch.empty_like(img)
     vi, vf, vo = _views(img, flow, out)
     if vi.on_cuda:
-        with torch.cuda.device(img.device):
+        with _on_device(img.device):
             check(lib().qpwc_warp_fwd(vi.ptr, vf.ptr, vo.ptr, B, H, W, C, mode,
                                       _stream_ptr(img.device)))
     else:
@@ -108,7 +133,7 @@ def _warp_bwd(img, flow, g_out, mode):
     g_img = torch.empty_like(img)
     g_flow = torch.empty_like(flow)
     vi, vf, vg, vgi, vgf = _views(img, flow, g_out, g_img, g_flow)
-    with torch.cuda.device(img.device):
+    with _on_device(img.device):
         check(lib().qpwc_warp_bwd(vi.ptr, vf.ptr, vg.ptr, vgi.ptr, vgf.ptr, B, H, W, C, mode,
                                   _stream_ptr(img.device)))
     return g_img, g_flow
@@ -122,7 +147,7 @@ def _warp_corr_fwd(prv, nxt, flow, mode, d, slope, out=None, out_stride=None):
         out = torch.empty((B, H, W, ops), dtype=torch.float32, device=prv.device)
     vp, vn, vf, vo = _views(prv, nxt, flow, out)
     if vp.on_cuda:
-        with torch.cuda.device(prv.device):
+        with _on_device(prv.device):
             check(lib().qpwc_warp_corr_fwd(vp.ptr, vn.ptr, vf.ptr, vo.ptr, B, H, W, C, d, slope,
                                            mode, ops, _stream_ptr(prv.device)))
     else:
@@ -140,7 +165,7 @@ def _warp_corr_bwd(prv, nxt, flow, out, g_out, mode, d, slope):
     nbytes = int(lib().qpwc_warp_corr_bwd_workspace(B, H, W, C))
     ws = torch.empty((max(nbytes, 16) + 3) // 4, dtype=torch.float32, device=prv.device)
     vp, vn, vf, vo, vg, vgp, vgn, vgf, vw = _views(prv, nxt, flow, out, g_out, g_prv, g_nxt, g_flow, ws)
-    with torch.cuda.device(prv.device):
+    with _on_device(prv.device):
         check(lib().qpwc_warp_corr_bwd(vp.ptr, vn.ptr, vf.ptr, vo.ptr, vg.ptr, vgp.ptr, vgn.ptr,
                                        vgf.ptr, vw.ptr, ws.numel() * 4, B, H, W, C, d, slope, mode,
                                        ops, _stream_ptr(prv.device)))
