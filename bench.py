@@ -290,7 +290,8 @@ def run_native(args):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": load_traffic(), "peak_source": peak_src,
-        "kernel": f"fused warp->corr level {lv.H}x{lv.W}x{lv.C} B={BATCH} d={SEARCH}",
+        "kernel": f"{wl.level_path[dom]} warp->corr level {lv.H}x{lv.W}x{lv.C} B={BATCH} d={SEARCH}"
+                  + (" (timed: warp kernel + corr kernel)" if wl.level_path[dom] == "composed" else ""),
         "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": dom_ms,
         "share_of_step": dom_ms / ms_per_step,
         "fp32": {"achieved_tflops": aflops / (dom_ms * 1e-3) / 1e12, "peak_tflops": FP32_PEAK_TFLOPS,
@@ -316,7 +317,9 @@ def run_native(args):
                        "levels": "14x32x256(corr) 28x64x256 56x128x128 112x256x64 224x512x32 (fused warp->corr)",
                        "l2": "inputs larger than L2: each step streams 853 MB of distinct tensors (126 MB L2)",
                        "parallelism": f"batch-sharded replicas x{world}, no collective on the data path",
-                       "launch": "CUDA graph of the 5 launches per step" if use_graph else "5 individual launches per step"},
+                       "launch": ("CUDA graph of the %d launches per step" if use_graph else "%d individual launches per step") % wl.launches_per_step,
+                       "upflow_path": dict(zip([f"{l.H}x{l.W}x{l.C}" for l in wl.levels], wl.level_path)),
+                       "autotune_ms": getattr(wl, "autotune_ms", None)},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": wl.launches_per_step * K, "clocks": sampler.summary(note),
         }

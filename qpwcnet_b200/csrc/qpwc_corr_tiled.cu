@@ -30,14 +30,18 @@
 
 namespace qpwc {
 
-template <int TH_, int WARP_, int MODE_>
+template <int TH_, int WARP_, int MODE_, int PACKED_ = 0>
 struct TiledCfg {
+  // PACKED: accumulate with packed fp32 FMAs (FFMA2, sm_100): even-/odd-channel partial sums kept
+  // as register pairs.  A 3-register scalar FFMA issues at ~0.55/clk/SMSP on B200 (register-file
+  // port limit, measured: tools/ubench/ffma_bench.cu); FFMA2 sustains ~1.0 FMA/clk/SMSP.
+  static constexpr int PACKED = PACKED_;
   static constexpr int D = 4, Q = 2 * D + 1, NDISP = Q * Q;
   static constexpr int TH = TH_, TWT = 64, TW = TWT - 2 * D;  // 56 pixel columns per tile
   static constexpr int WARP = WARP_, MODE = MODE_;
   static constexpr int KC = 8, PXB = KC * 4;                   // 32 bytes per pixel per stage
   static constexpr int NROW = TH + 2 * D, NCOL = TWT, PCOL = TW;         // P tile: the 56 valid columns only
-  static constexpr int NST = 3;
+  static constexpr int NST = PACKED_ ? 4 : 3;
   static constexpr int P_BYTES = TH * PCOL * PXB, N_BYTES = NROW * NCOL * PXB;
   static constexpr int STAGE_BYTES = P_BYTES + N_BYTES;
   static constexpr int NCONS = TH * TWT, NPROD = 128, NTHREADS = NCONS + NPROD;
@@ -56,9 +60,10 @@ struct TiledCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
   static constexpr int FULL_COUNT = 1 + (WARP ? NPROD / 32 : 0);
   static constexpr int EMPTY_COUNT = NCONS / 32;
-  static constexpr int REG_CONS = 152, REG_PROD = 56;         // 384*152 + 128*56 == 65536
+  static constexpr int REG_CONS = PACKED_ ? (WARP_ ? 224 : 232) : 152;   // scalar: 384*152 + 128*56 == 65536
+  static constexpr int REG_PROD = PACKED_ ? (WARP_ ? 56 : 32) : 56;      // packed: 256*232 + 128*32 <= 65536
   static_assert(TW % 8 == 0 && P_BYTES % 256 == 0 && N_BYTES % 256 == 0 && TH <= 14, "tile shape");
-  static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536 || TH != 6, "register budget");
+  static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536, "register budget");
 };
 
 struct TapsEntry { int o00, o01, o10, o11; float w00, w01, w10, w11; };  // 32 bytes
@@ -230,7 +235,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
     const int ti = tid / NCOL, tc = tid % NCOL, lane = tid & 31;
     // byte offsets inside a stage (chunk quad 0; quad 1 = offset ^ 16)
     const uint32_t nb_off = Cfg::P_BYTES + swz32((uint32_t)((ti * NCOL + tc) * Cfg::PXB));
-    uint32_t a_off[Q];
+    uint32_t a_off[Q];  // scalar path only (the packed path recomputes them)
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
       // first-frame pixel column of acc[.][k] is lp = tc - k; columns outside the tile belong to
@@ -249,11 +254,12 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
       const int b = tile / (tiles_x * tiles_y);
       const int i0 = ty * TH, j0 = tx * TW;
 
-      float acc[Q][Q];
+      float acc[Q][Q];              // scalar path
+      float2 acc2[Q][Q];            // packed path: (even-channel sum, odd-channel sum) per output
 #pragma unroll
       for (int m = 0; m < Q; ++m)
 #pragma unroll
-        for (int k = 0; k < Q; ++k) acc[m][k] = 0.f;
+        for (int k = 0; k < Q; ++k) { acc[m][k] = 0.f; acc2[m][k] = make_float2(0.f, 0.f); }
 
       for (int c = 0; c < nchunks; ++c, ++g) {
         const int stage = g % NST;
@@ -263,18 +269,36 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
 #pragma unroll
         for (int qd = 0; qd < 2; ++qd) {
           const unsigned char* nbp = sb + (nb_off ^ (uint32_t)(qd << 4));
-          float4 bv[Q];
+          if (Cfg::PACKED) {
+            // packed fp32 FMAs on the natural channel pairs (c0,c1) / (c2,c3) of the 16-byte
+            // operands; scheduling is left to ptxas (pinning the order with asm volatile was
+            // measured 30 % slower: it can no longer interleave the operand loads)
+            float4 bq[Q];
 #pragma unroll
-          for (int m = 0; m < Q; ++m) bv[m] = *reinterpret_cast<const float4*>(nbp + m * (NCOL * Cfg::PXB));
+            for (int m = 0; m < Q; ++m) bq[m] = *reinterpret_cast<const float4*>(nbp + m * (NCOL * Cfg::PXB));
 #pragma unroll
-          for (int k = 0; k < Q; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
+            for (int k = 0; k < Q; ++k) {
+              const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
+              const float2 alo = make_float2(a.x, a.y), ahi = make_float2(a.z, a.w);
 #pragma unroll
-            for (int m = 0; m < Q; ++m) {
-              acc[m][k] = fmaf(a.x, bv[m].x, acc[m][k]);
-              acc[m][k] = fmaf(a.y, bv[m].y, acc[m][k]);
-              acc[m][k] = fmaf(a.z, bv[m].z, acc[m][k]);
-              acc[m][k] = fmaf(a.w, bv[m].w, acc[m][k]);
+              for (int m = 0; m < Q; ++m) acc2[m][k] = __ffma2_rn(alo, make_float2(bq[m].x, bq[m].y), acc2[m][k]);
+#pragma unroll
+              for (int m = 0; m < Q; ++m) acc2[m][k] = __ffma2_rn(ahi, make_float2(bq[m].z, bq[m].w), acc2[m][k]);
+            }
+          } else {
+            float4 bv[Q];
+#pragma unroll
+            for (int m = 0; m < Q; ++m) bv[m] = *reinterpret_cast<const float4*>(nbp + m * (NCOL * Cfg::PXB));
+#pragma unroll
+            for (int k = 0; k < Q; ++k) {
+              const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
+#pragma unroll
+              for (int m = 0; m < Q; ++m) {
+                acc[m][k] = fmaf(a.x, bv[m].x, acc[m][k]);
+                acc[m][k] = fmaf(a.y, bv[m].y, acc[m][k]);
+                acc[m][k] = fmaf(a.z, bv[m].z, acc[m][k]);
+                acc[m][k] = fmaf(a.w, bv[m].w, acc[m][k]);
+              }
             }
           }
         }
@@ -288,6 +312,9 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
       // 28 px through private slots and hands each contiguous 28 x 324-byte run to the TMA engine
       // (cp.async.bulk shared->global): no copy loop, rows never wait for each other, and the
       // store drains while the next tile is being computed.
+      // packed path: fold the odd-channel partial sum into the even one in place (no second
+      // live copy of the 81 results: register pressure)
+#define QPWC_ACC(m, k) (Cfg::PACKED ? (acc2[m][k].x + acc2[m][k].y) : acc[m][k])
       const int twv = min(TW, W - j0);  // valid pixel columns of this tile
       if (Cfg::AGENT) {
         // deposit the 9x9 block (transposed into the NHWC 81-vector order) and carry on
@@ -298,7 +325,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           if (lp >= 0 && lp < twv) {
             float* dstp = slot0 + lp * NDISP + k;
 #pragma unroll
-            for (int m = 0; m < Q; ++m) dstp[m * Q] = lrelu(acc[m][k] * inv_c, slope);
+            for (int m = 0; m < Q; ++m) dstp[m * Q] = lrelu(QPWC_ACC(m, k) * inv_c, slope);
           }
         }
         fence_proxy_async();
@@ -321,7 +348,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           if (lp >= lp0 && lp < lp1) {
             float* dstp = slot + (lp - lp0) * NDISP + k;
 #pragma unroll
-            for (int m = 0; m < Q; ++m) dstp[m * Q] = lrelu(acc[m][k] * inv_c, slope);
+            for (int m = 0; m < Q; ++m) dstp[m * Q] = lrelu(QPWC_ACC(m, k) * inv_c, slope);
           }
         }
         fence_proxy_async();
@@ -428,9 +455,17 @@ int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow,
   if (d != 4 || (C & 3) || C < 4) return QPWC_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15)) return QPWC_ERR_UNSUPPORTED;
   if ((long long)H * W < 64) return QPWC_ERR_UNSUPPORTED;
-  if (!flow) return run_tiled<TiledCfg<6, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
-  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<6, 1, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
-  return run_tiled<TiledCfg<6, 1, QPWC_MODE_TFA>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  // QPWC_TILED_SCALAR=1 (dev): the scalar-FFMA 6-row variant instead of the packed-FFMA2 4-row one
+  static int scalar = -1;
+  if (scalar < 0) { const char* e = getenv("QPWC_TILED_SCALAR"); scalar = (e && atoi(e)) ? 1 : 0; }
+  if (scalar) {
+    if (!flow) return run_tiled<TiledCfg<6, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+    if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<6, 1, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+    return run_tiled<TiledCfg<6, 1, QPWC_MODE_TFA>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  }
+  if (!flow) return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
 }
 
 int launch_corr_bwd_tiled(const float*, const float*, const float*, const float*, float*, float*,

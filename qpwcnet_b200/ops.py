@@ -114,9 +114,10 @@ def _corr_bwd(prv, nxt, out, g_out, d, slope):
     return g_prv, g_nxt
 
 
-def _warp_fwd(img, flow, mode):
+def _warp_fwd(img, flow, mode, out=None):
     B, H, W, C = img.shape
-    out = torch.empty_like(img)
+    if out is None:
+        out = torch.empty_like(img)
     vi, vf, vo = _views(img, flow, out)
     if vi.on_cuda:
         with _on_device(img.device):
@@ -290,6 +291,15 @@ def warp_cost_volume_into(out, prv, nxt, flow, mode="tfa", search_range: int = 4
     _check_out(out, prv)
     return _warp_corr_fwd(prv, nxt, flow, _mode(mode), int(search_range), float(leaky_slope),
                           out=out, out_stride=out.shape[-1])
+
+
+def warp_into(out, img, flow, mode="tfa"):
+    """Inference-only ``warp`` into a caller-owned ``out`` (same shape as ``img``)."""
+    img = _prep(img, "img")
+    flow = _prep(flow, "flow", last=2)
+    if out.shape != img.shape or out.dtype != torch.float32 or out.device != img.device or not out.is_contiguous():
+        raise ValueError("out must be a dense float32 tensor shaped like img on the same device")
+    return _warp_fwd(img, flow, _mode(mode), out=out)
 
 
 def _check_out(out, prv):

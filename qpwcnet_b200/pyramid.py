@@ -50,14 +50,19 @@ class PyramidWorkload:
     in pinned host memory (``device='cpu'``), and the 5-call hot path over them."""
 
     def __init__(self, height=436, width=1024, batch=8, search_range=4, device="cuda", seed=0,
-                 flow_sigma=None, warp_mode="tfa"):
+                 flow_sigma=None, warp_mode="tfa", path="auto"):
+        """path: how an UpFlow level (warp -> cost volume) is executed --
+        'fused'    one kernel, warped features stay in shared memory (least HBM traffic);
+        'composed' the stand-alone warp kernel followed by the cost-volume kernel;
+        'auto'     time both once per level on the device and keep the faster (device workloads)."""
         self.levels = levels_for(height, width)
         self.B, self.d, self.mode = batch, search_range, warp_mode
         self.D = (2 * search_range + 1) ** 2
         sigma = search_range / 2.0 if flow_sigma is None else flow_sigma
         g = torch.Generator(device="cpu").manual_seed(seed)
         on_host = torch.device(device).type == "cpu"
-        self.inputs, self.outputs = [], []
+        self.inputs, self.outputs, self.scratch = [], [], []
+        self.path = path
         for lv in self.levels:
             shp = (batch, lv.H, lv.W, lv.C)
             prv = torch.randn(shp, generator=g)
@@ -72,6 +77,15 @@ class PyramidWorkload:
                 out = out.to(device)
             self.inputs.append(tuple(ts))
             self.outputs.append(out)
+            self.scratch.append(None)
+        self.level_path = ["fused" if lv.fused else "plain" for lv in self.levels]
+        if not on_host and path in ("composed", "auto"):
+            for k, lv in enumerate(self.levels):
+                if lv.fused:
+                    self.scratch[k] = torch.empty_like(self.inputs[k][1])
+                    self.level_path[k] = "composed"
+            if path == "auto":
+                self._autotune()
 
     # bytes per step
     def h2d_bytes(self):
@@ -86,12 +100,42 @@ class PyramidWorkload:
     def algorithmic_flops(self):
         return sum(algorithmic_flops(lv, self.B, self.d) for lv in self.levels)
 
-    def run_level(self, k):
-        lv = self.levels[k]
+    def run_level(self, k, how=None):
         prv, nxt, flo = self.inputs[k]
-        if lv.fused:
+        how = how or self.level_path[k]
+        if how == "fused":
             return ops.warp_cost_volume_into(self.outputs[k], prv, nxt, flo, self.mode, self.d)
+        if how == "composed":
+            ops.warp_into(self.scratch[k], nxt, flo, self.mode)
+            return ops.cost_volume_into(self.outputs[k], prv, self.scratch[k], self.d)
         return ops.cost_volume_into(self.outputs[k], prv, nxt, self.d)
+
+    def _autotune(self, reps=5):
+        """Per UpFlow level: median device time of the fused kernel vs warp + cost volume."""
+        self.autotune_ms = {}
+        for k, lv in enumerate(self.levels):
+            if not lv.fused:
+                continue
+            best = {}
+            for how in ("fused", "composed"):
+                for _ in range(2):
+                    self.run_level(k, how)
+                ts = []
+                for _ in range(reps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(4):                      # several launches per sample: hides host latency
+                        self.run_level(k, how)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1) / 4)
+                best[how] = sorted(ts)[len(ts) // 2]
+            self.autotune_ms[f"{lv.H}x{lv.W}x{lv.C}"] = best
+            self.level_path[k] = min(best, key=best.get)
+
+    @property
+    def launches_per_step(self):
+        return sum(2 if p == "composed" else 1 for p in self.level_path)
 
     def step(self):
         """One pass of the hot path over the batch: 1 cost volume + 4 fused warp->cost volumes
@@ -123,4 +167,3 @@ class PyramidWorkload:
         self._graph.replay()
         return self.outputs
 
-    launches_per_step = 5
