@@ -213,7 +213,7 @@ def run_native(args):
 
     assert ops.library_version() >= 100
     K, Wm = args.steps, max(args.warmup, 3)
-    wl = PyramidWorkload(HEIGHT, WIDTH, BATCH, SEARCH, device=dev, seed=rank)
+    wl = PyramidWorkload(HEIGHT, WIDTH, BATCH, SEARCH, device=dev, seed=rank, path=args.path)
     dom = max(range(len(wl.levels)), key=lambda k: algorithmic_bytes(wl.levels[k], BATCH, SEARCH))
 
     # The step (5 launches) is recorded once into a CUDA graph and replayed: same kernels, same
@@ -337,6 +337,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the 5 kernels per step individually")
+    ap.add_argument("--path", default="auto", choices=["auto", "fused", "composed"],
+                    help="UpFlow levels: fused kernel, warp + cost volume, or time both and keep the faster")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
