@@ -1,0 +1,72 @@
+"""Multi-process (gloo, world_size 2, CPU) test of the N>1 plumbing used by bench.py: frame pairs are
+sharded by rank with no data-path collective; only the step time is reduced (MAX) across ranks and the
+whole-job value is computed from it.  The compute itself is exercised on the GPU tests; here each rank
+stands in with the CPU oracle on its own shard and the shards are checked against the unsharded result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # global batch of 4 frame pairs, contiguous batch slices per rank (bench.py: one batch per rank)
+    r = np.random.default_rng(0)
+    prv = r.standard_normal((4, 6, 7, 4)).astype(np.float32)
+    nxt = r.standard_normal((4, 6, 7, 4)).astype(np.float32)
+    flo = r.standard_normal((4, 6, 7, 2)).astype(np.float32)
+    per = 4 // world
+    sl = slice(rank * per, (rank + 1) * per)
+    out = oracle.warp_cost_volume(prv[sl], nxt[sl], flo[sl], "tfa", 4)
+    # timing reduction exactly as bench.py does it: MAX over ranks, value = units / max time
+    t = torch.tensor([0.010 * (rank + 1)], dtype=torch.float64)
+    dist.barrier()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gathered = [torch.zeros_like(torch.from_numpy(out)) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(out))          # test-only: to compare with unsharded
+    if rank == 0:
+        full = oracle.warp_cost_volume(prv, nxt, flo, "tfa", 4)
+        q.put((float(t.item()), np.array_equal(torch.cat(gathered).numpy(), full)))
+    dist.destroy_process_group()
+
+
+def test_batch_sharding_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    t_max, same = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert abs(t_max - 0.020) < 1e-12          # slowest rank defines the step time
+    assert same                                  # shards == unsharded result: no cross-pair term
+
+
+def test_bench_reference_arm_runs_on_rank0_only(tmp_path):
+    import json
+    import subprocess
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "1"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == ""        # non-zero ranks exit 0 without work
