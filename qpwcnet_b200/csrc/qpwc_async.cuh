@@ -15,6 +15,14 @@ namespace qpwc {
 __host__ __device__ __forceinline__ uint32_t swz32(uint32_t byte_off) {
   return byte_off ^ (((byte_off >> 7) & 1u) << 4);
 }
+// TMA SWIZZLE_64B: bits [4:5] ^= bits [7:8] (period 512 B)
+__host__ __device__ __forceinline__ uint32_t swz64(uint32_t byte_off) {
+  return byte_off ^ (((byte_off >> 7) & 3u) << 4);
+}
+// swizzle matching a pixel stride of PXB bytes (32 -> SWIZZLE_32B, 64 -> SWIZZLE_64B)
+template <int PXB> __host__ __device__ __forceinline__ uint32_t swz(uint32_t byte_off) {
+  return PXB == 32 ? swz32(byte_off) : swz64(byte_off);
+}
 
 #ifndef QPWC_EMU
 // =============================================================================== real hardware
@@ -79,7 +87,7 @@ template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile
 // Host: encode a 4-D tiled tensor map over a dense NHWC fp32 tensor, dims (C, W, H, B), box
 // (boxC, boxW, boxH, 1), SWIZZLE_32B, zero fill out of bounds, 128-B L2 promotion.
 // Returns false (and sets the error) on failure.
-bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C, int boxC, int boxW, int boxH);
+bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C, int boxC, int boxW, int boxH);  // swizzle = boxC*4 bytes
 
 #else
 // ============================================================================ CPU emulation
@@ -143,7 +151,7 @@ inline void tma_load_4d(void* smem_dst, const TensorMap* tm, uint64_t* bar, int 
           if (in) v = tm->base[x[0] * tm->stride[0] + x[1] * tm->stride[1] + x[2] * tm->stride[2] + x[3] * tm->stride[3]];
           // hardware swizzles on absolute shared-memory address bits
           const uintptr_t abs = reinterpret_cast<uintptr_t>(dst) + lin;
-          const uintptr_t phys = abs ^ (((abs >> 7) & 1u) << 4);
+          const uintptr_t phys = abs ^ (((abs >> 7) & (tm->box[0] * 4 == 32 ? 1u : 3u)) << 4);
           *reinterpret_cast<float*>(phys) = v;
         }
   std::lock_guard<std::mutex> lk(emu_detail::mu());

@@ -39,12 +39,17 @@ struct TiledCfg {
   static constexpr int D = 4, Q = 2 * D + 1, NDISP = Q * Q;
   static constexpr int TH = TH_, TWT = 64, TW = TWT - 2 * D;  // 56 pixel columns per tile
   static constexpr int WARP = WARP_, MODE = MODE_;
-  static constexpr int KC = 8, PXB = KC * 4;                   // 32 bytes per pixel per stage
+  // channels per pipeline stage: 8 (32 B/pixel, SWIZZLE_32B); the fused variant uses 16 (64 B,
+  // SWIZZLE_64B) -- its gathers cost one L1 wavefront per distinct 128-byte line *per instruction*
+  // (measured ~2 clk each), so wider per-pixel reads halve the producer's L1 time
+  static constexpr int KC = WARP_ ? 16 : 8, PXB = KC * 4, NQ = KC / 4;
   static constexpr int NROW = TH + 2 * D, NCOL = TWT, PCOL = TW;         // P tile: the 56 valid columns only
-  static constexpr int NST = PACKED_ ? 4 : 3;
+  static constexpr int NST = WARP_ ? 2 : ((PACKED_ || TH_ <= 4) ? 4 : 3);
   static constexpr int P_BYTES = TH * PCOL * PXB, N_BYTES = NROW * NCOL * PXB;
   static constexpr int STAGE_BYTES = P_BYTES + N_BYTES;
-  static constexpr int NCONS = TH * TWT, NPROD = 128, NTHREADS = NCONS + NPROD;
+  // producers: plain = 1 TMA thread + 1 store-agent warp (of a 128-thread warpgroup, the unit of
+  // setmaxnreg); fused = 8 gather warps -- the gathers are latency-bound, they need the parallelism
+  static constexpr int NCONS = TH * TWT, NPROD = WARP_ ? 256 : 128, NTHREADS = NCONS + NPROD;
   // Epilogue staging.  AGENT (plain variant): one full-row slot per tile row; consumer warps only
   // deposit their accumulators and move on, a store-agent warp hands the row to the TMA engine.
   // Fused variant: the taps table needs the room => half-row slots, stores issued by the row itself.
@@ -60,9 +65,12 @@ struct TiledCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
   static constexpr int FULL_COUNT = 1 + (WARP ? NPROD / 32 : 0);
   static constexpr int EMPTY_COUNT = NCONS / 32;
-  static constexpr int REG_CONS = PACKED_ ? (WARP_ ? 224 : 232) : 152;   // scalar: 384*152 + 128*56 == 65536
-  static constexpr int REG_PROD = PACKED_ ? (WARP_ ? 56 : 32) : 56;      // packed: 256*232 + 128*32 <= 65536
-  static_assert(TW % 8 == 0 && P_BYTES % 256 == 0 && N_BYTES % 256 == 0 && TH <= 14, "tile shape");
+  // register split (setmaxnreg), sum <= 65536:  scalar TH=6: 384*152 + 128*56;  packed TH=4 plain:
+  // 256*232 + 128*32;  fused (scalar consumers, TH=4): 256*152 + 256*104
+  static constexpr int REG_CONS = PACKED_ ? 232 : 152;
+  static constexpr int REG_PROD = WARP_ ? 104 : (PACKED_ ? 32 : 56);
+  static_assert(!(WARP_ && (PACKED_ || TH_ > 4)), "fused variant: scalar consumers, TH <= 4");
+  static_assert(TW % 8 == 0 && P_BYTES % 512 == 0 && N_BYTES % 512 == 0 && TH <= 14, "tile shape");
   static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536, "register budget");
 };
 
@@ -92,7 +100,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
 
   if (tid == 0) {
 #ifndef QPWC_EMU
-    if (smem_u32(smem) & 255u) __trap();
+    if (smem_u32(smem) & 511u) __trap();
 #endif
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], Cfg::FULL_COUNT); mbar_init(&empty[s], Cfg::EMPTY_COUNT); }
     for (int r = 0; r < TH; ++r) { mbar_init(&sfull[r], NCOL / 32); mbar_init(&sfree[r], 1); }
@@ -180,11 +188,11 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           if (!Cfg::WARP) tma_load_4d(sb + Cfg::P_BYTES, &tmN, &full[stage], c * KC, j0 - D, i0 - D, b);
         }
         if (Cfg::WARP) {
-          // units: (halo pixel, 16-byte channel quad); lane pairs share a pixel => 32-byte reads
+          // units: (halo pixel, 16-byte channel quad); NQ adjacent lanes share a pixel => 32/64-byte reads
           const float* nb = nxt + (size_t)b * H * W * C + (size_t)c * KC;
           unsigned char* ns = sb + Cfg::P_BYTES;
-          constexpr int NU = NROW * NCOL * 2;
-          constexpr int UB = 2;  // units in flight per thread: 8 independent 16-byte gathers
+          constexpr int NU = NROW * NCOL * Cfg::NQ;
+          constexpr int UB = 4;  // units in flight per thread: 16 independent 16-byte gathers
           for (int u0 = ptid; u0 < NU; u0 += NPROD * UB) {
             TapsEntry e[UB];
             float4 v00[UB], v01[UB], v10[UB], v11[UB];
@@ -194,7 +202,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
               const int u = u0 + x * NPROD;
               live[x] = false;
               if (u < NU) {
-                const int pix = u >> 1, qd = u & 1;
+                const int pix = u / Cfg::NQ, qd = u % Cfg::NQ;
                 e[x] = taps[pix];
                 live[x] = e[x].o00 >= 0 && c * KC + qd * 4 < C;
                 if (live[x]) {
@@ -220,7 +228,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
                   v.z = blend<Cfg::MODE>(t, v00[x].z, v01[x].z, v10[x].z, v11[x].z);
                   v.w = blend<Cfg::MODE>(t, v00[x].w, v01[x].w, v10[x].w, v11[x].w);
                 }
-                *reinterpret_cast<float4*>(ns + swz32((uint32_t)((u >> 1) * Cfg::PXB + (u & 1) * 16))) = v;
+                *reinterpret_cast<float4*>(ns + swz<Cfg::PXB>((uint32_t)((u / Cfg::NQ) * Cfg::PXB + (u % Cfg::NQ) * 16))) = v;
               }
             }
           }
@@ -233,15 +241,15 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
     // ========================================================================== consumers
     setmaxnreg_inc<Cfg::REG_CONS>();
     const int ti = tid / NCOL, tc = tid % NCOL, lane = tid & 31;
-    // byte offsets inside a stage (chunk quad 0; quad 1 = offset ^ 16)
-    const uint32_t nb_off = Cfg::P_BYTES + swz32((uint32_t)((ti * NCOL + tc) * Cfg::PXB));
+    // byte offsets inside a stage (channel quad 0; quad q = offset ^ (q << 4), see swz<>)
+    const uint32_t nb_off = Cfg::P_BYTES + swz<Cfg::PXB>((uint32_t)((ti * NCOL + tc) * Cfg::PXB));
     uint32_t a_off[Q];  // scalar path only (the packed path recomputes them)
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
       // first-frame pixel column of acc[.][k] is lp = tc - k; columns outside the tile belong to
       // accumulators that are never stored, so they may read any resident pixel: clamp
       const int lp = min(max(tc - k, 0), TW - 1);
-      a_off[k] = swz32((uint32_t)((ti * PCOL + lp) * Cfg::PXB));
+      a_off[k] = swz<Cfg::PXB>((uint32_t)((ti * PCOL + lp) * Cfg::PXB));
     }
     const float inv_c = 1.f / (float)C;
     float* slot0 = reinterpret_cast<float*>(smem + Cfg::OFF_STAGING + ti * Cfg::NSLOT * Cfg::SLOT_BYTES);  // private to this row
@@ -267,7 +275,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         const unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
         if (!(ablate & 1))
 #pragma unroll
-        for (int qd = 0; qd < 2; ++qd) {
+        for (int qd = 0; qd < Cfg::NQ; ++qd) {
           const unsigned char* nbp = sb + (nb_off ^ (uint32_t)(qd << 4));
           if (Cfg::PACKED) {
             // packed fp32 FMAs on the natural channel pairs (c0,c1) / (c2,c3) of the 16-byte
@@ -398,7 +406,7 @@ bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C
   const cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, boxC * 4 == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return false; }
   return true;
@@ -458,14 +466,10 @@ int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow,
   // QPWC_TILED_SCALAR=1 (dev): the scalar-FFMA 6-row variant instead of the packed-FFMA2 4-row one
   static int scalar = -1;
   if (scalar < 0) { const char* e = getenv("QPWC_TILED_SCALAR"); scalar = (e && atoi(e)) ? 1 : 0; }
-  if (scalar) {
-    if (!flow) return run_tiled<TiledCfg<6, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
-    if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<6, 1, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
-    return run_tiled<TiledCfg<6, 1, QPWC_MODE_TFA>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
-  }
+  if (scalar && !flow) return run_tiled<TiledCfg<6, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
   if (!flow) return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
-  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
-  return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
 }
 
 int launch_corr_bwd_tiled(const float*, const float*, const float*, const float*, float*, float*,
