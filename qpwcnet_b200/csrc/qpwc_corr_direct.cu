@@ -98,6 +98,52 @@ __global__ void __launch_bounds__(256) corr_bwd_direct_kernel(
   }
 }
 
+// Vectorised variant for C % 4 == 0 and 16-byte aligned tensors: one thread per (pixel, channel
+// quad); grid = (ceil(W*C4/256), H, B) so all index arithmetic is 32-bit.  The 8..64 quad-lanes of
+// a pixel share the g_out/out loads (warp broadcast), the neighbour vectors are 16-byte loads.
+__global__ void __launch_bounds__(256) corr_bwd_quad_kernel(
+    const float* __restrict__ prv, const float* __restrict__ nxt, const float* __restrict__ out,
+    const float* __restrict__ g_out, float* __restrict__ g_prv, float* __restrict__ g_nxt, int H,
+    int W, int C, int d, float slope, long long ops) {
+  const int C4 = C >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // j * C4 + c4
+  if (idx >= W * C4) return;
+  const int j = idx / C4, c4 = idx - j * C4;
+  const int i = blockIdx.y;
+  const size_t bpix = (size_t)blockIdx.z * H * W;
+  const size_t pix = bpix + (size_t)i * W + j;
+  const int q = 2 * d + 1;
+  const float inv_c = 1.f / (float)C;
+  const float4* prv4 = reinterpret_cast<const float4*>(prv);
+  const float4* nxt4 = reinterpret_cast<const float4*>(nxt);
+  const float* go_own = g_out + pix * (size_t)ops;
+  const float* o_own = out + pix * (size_t)ops;
+  float4 ap = make_float4(0.f, 0.f, 0.f, 0.f), an = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i0 = 0; i0 < q; ++i0) {
+    const int r = i + i0 - d, rn = i - (i0 - d);
+    const bool r_ok = r >= 0 && r < H, rn_ok = rn >= 0 && rn < H;
+    for (int j0 = 0; j0 < q; ++j0) {
+      const int k = i0 * q + j0;
+      const int s = j + j0 - d, sn = j - (j0 - d);
+      if (r_ok && s >= 0 && s < W) {  // g_prv: own gradient row against the displaced second frame
+        float g = __ldg(go_own + k);
+        g = (__ldg(o_own + k) > 0.f ? g : slope * g) * inv_c;
+        const float4 x = __ldg(nxt4 + (bpix + (size_t)r * W + s) * C4 + c4);
+        ap.x = fmaf(g, x.x, ap.x); ap.y = fmaf(g, x.y, ap.y); ap.z = fmaf(g, x.z, ap.z); ap.w = fmaf(g, x.w, ap.w);
+      }
+      if (rn_ok && sn >= 0 && sn < W) {  // g_nxt: first-frame pixels that looked at this pixel
+        const size_t pp = bpix + (size_t)rn * W + sn;
+        float g = __ldg(g_out + pp * (size_t)ops + k);
+        g = (__ldg(out + pp * (size_t)ops + k) > 0.f ? g : slope * g) * inv_c;
+        const float4 x = __ldg(prv4 + pp * C4 + c4);
+        an.x = fmaf(g, x.x, an.x); an.y = fmaf(g, x.y, an.y); an.z = fmaf(g, x.z, an.z); an.w = fmaf(g, x.w, an.w);
+      }
+    }
+  }
+  reinterpret_cast<float4*>(g_prv)[pix * C4 + c4] = ap;
+  reinterpret_cast<float4*>(g_nxt)[pix * C4 + c4] = an;
+}
+
 static int grid_for(long long total, int block, int waves) {
   const long long want = cdivll(total, block);
   const long long cap = 148LL * waves;
@@ -129,6 +175,19 @@ int launch_corr_bwd_direct(const float* prv, const float* nxt, const float* out,
                            float slope, long long ops, cudaStream_t stream) {
   const long long total = (long long)B * H * W * C;
   if (total == 0) return QPWC_OK;
+  const bool al16 = !((reinterpret_cast<uintptr_t>(prv) | reinterpret_cast<uintptr_t>(nxt) |
+                       reinterpret_cast<uintptr_t>(g_prv) | reinterpret_cast<uintptr_t>(g_nxt)) & 15);
+  if ((C & 3) == 0 && al16 && H <= 65535 && (long long)W * (C >> 2) < (1LL << 31)) {
+    auto k = corr_bwd_quad_kernel;
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+      const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
+      const dim3 grid((unsigned)cdiv(W * (C >> 2), 256), (unsigned)H, (unsigned)nb);
+      const size_t off = (size_t)b0 * H * W;
+      QPWC_LAUNCH(k, grid, 256, 0, stream, prv + off * C, nxt + off * C, out + off * ops, g_out + off * ops,
+                  g_prv + off * C, g_nxt + off * C, H, W, C, d, slope, ops);
+    }
+    return check_launch("corr_bwd_quad");
+  }
   const int block = 256, grid = grid_for(total, block, 64);
   auto k = corr_bwd_direct_kernel;
   QPWC_LAUNCH(k, grid, block, 0, stream, prv, nxt, out, g_out, g_prv, g_nxt, H, W, C, d, slope, ops, total);

@@ -56,32 +56,31 @@ template <> __device__ __forceinline__ void vatomic_add<2>(float* p, const float
 template <> __device__ __forceinline__ void vatomic_add<1>(float* p, const float (&v)[1]) { atomicAdd(p, v[0]); }
 
 // ------------------------------------------------------------------------------------------ fwd
+// grid = (ceil(W*CV / 256), H, B): row and batch come from the block index, so the only index
+// arithmetic per thread is one 32-bit divide by CV (the first version decoded a 64-bit linear index
+// with three 64-bit divisions per thread and was instruction-bound: ncu 207 instr/thread).
 template <int MODE, int V>
 __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__ img,
                                                        const float* __restrict__ flow,
-                                                       float* __restrict__ out, int H, int W, int C,
-                                                       long long total /* B*H*W*(C/V) */) {
+                                                       float* __restrict__ out, int H, int W, int C) {
   const int CV = C / V;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int cv = (int)(idx % CV);
-    const long long pix = idx / CV;  // b*H*W + i*W + j
-    const int j = (int)(pix % W);
-    const long long bi = pix / W;
-    const int i = (int)(bi % H);
-    const long long b = bi / H;
-    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);  // ch0 = x, ch1 = y
-    const Taps t = make_taps<MODE>(i, j, f.x, f.y, H, W);
-    const float* base = img + (size_t)b * H * W * C + (size_t)cv * V;
-    float v00[V], v01[V], v10[V], v11[V], o[V];
-    vload<V>(base + (size_t)t.o00 * C, v00);
-    vload<V>(base + (size_t)t.o01 * C, v01);
-    vload<V>(base + (size_t)t.o10 * C, v10);
-    vload<V>(base + (size_t)t.o11 * C, v11);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // j * CV + cv
+  if (idx >= W * CV) return;
+  const int j = idx / CV, cv = idx - j * CV;
+  const int i = blockIdx.y;
+  const size_t row = (size_t)blockIdx.z * H + i;           // b*H + i
+  const size_t pix = row * W + j;
+  const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);  // ch0 = x, ch1 = y
+  const Taps t = make_taps<MODE>(i, j, f.x, f.y, H, W);
+  const float* base = img + (size_t)blockIdx.z * H * W * C + (size_t)cv * V;
+  float v00[V], v01[V], v10[V], v11[V], o[V];
+  vload<V>(base + (size_t)t.o00 * C, v00);
+  vload<V>(base + (size_t)t.o01 * C, v01);
+  vload<V>(base + (size_t)t.o10 * C, v10);
+  vload<V>(base + (size_t)t.o11 * C, v11);
 #pragma unroll
-    for (int k = 0; k < V; ++k) o[k] = blend<MODE>(t, v00[k], v01[k], v10[k], v11[k]);
-    vstore<V>(out + (size_t)pix * C + (size_t)cv * V, o);
-  }
+  for (int k = 0; k < V; ++k) o[k] = blend<MODE>(t, v00[k], v01[k], v10[k], v11[k]);
+  vstore<V>(out + pix * C + (size_t)cv * V, o);
 }
 
 // ------------------------------------------------------------------------------------------ bwd
@@ -205,28 +204,33 @@ static int pick_vec(int C, const void* a, const void* b, const void* c = nullptr
 }
 
 template <int MODE, int V>
-static void run_warp_fwd(const float* img, const float* flow, float* out, int H, int W, int C,
-                         long long total, cudaStream_t stream) {
+static void run_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                         cudaStream_t stream) {
   const int block = 256;
-  const long long want = cdivll(total, block);
-  const int grid = (int)(want < 148LL * 32 ? want : 148LL * 32);
+  const int CV = C / V;
   auto k = warp_fwd_kernel<MODE, V>;
-  QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, out, H, W, C, total);
+  // gridDim.y/z are limited to 65535: chunk the batch (and refuse absurd heights upstream)
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
+    const dim3 grid((unsigned)cdiv(W * CV, block), (unsigned)H, (unsigned)nb);
+    const size_t off = (size_t)b0 * H * W;
+    QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + off * 2, out + off * C, H, W, C);
+  }
 }
 
 int launch_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
                     int mode, cudaStream_t stream) {
   const int V = pick_vec(C, img, out);
-  const long long total = (long long)B * H * W * (C / V);
-  if (total == 0) return QPWC_OK;
+  if ((long long)B * H * W * C == 0) return QPWC_OK;
+  if (H > 65535 || (long long)W * (C / V) >= (1LL << 31)) return set_error(QPWC_ERR_UNSUPPORTED, "warp_fwd: H > 65535 or W*C too large");
   if (mode == QPWC_MODE_TF) {
-    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, out, H, W, C, total, stream);
-    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, out, H, W, C, total, stream);
-    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, out, H, W, C, total, stream);
+    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, out, B, H, W, C, stream);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, out, B, H, W, C, stream);
+    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, out, B, H, W, C, stream);
   } else {
-    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, out, H, W, C, total, stream);
-    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, out, H, W, C, total, stream);
-    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, out, H, W, C, total, stream);
+    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, out, B, H, W, C, stream);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, out, B, H, W, C, stream);
+    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, out, B, H, W, C, stream);
   }
   return check_launch("warp_fwd");
 }

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--bwd", action="store_true")
     a = ap.parse_args()
     dev = "cuda"
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
@@ -54,7 +55,14 @@ def main():
         px = B * H * W
         t_corr = timeit(lambda: ops.cost_volume_into(out, prv, nxt, 4), a.iters, flush)
         t_fused = timeit(lambda: ops.warp_cost_volume_into(out, prv, nxt, flo, "tfa", 4), a.iters, flush)
-        t_warp = timeit(lambda: ops.warp(nxt, flo, "tfa"), a.iters, flush)
+        t_warp = timeit(lambda: ops.warp_into(wout, nxt, flo, "tfa"), a.iters, flush)
+        if a.bwd:
+            g81 = torch.randn((B, H, W, 81), device=dev, generator=g)
+            gC = torch.randn((B, H, W, C), device=dev, generator=g)
+            cvout = ops.cost_volume(prv, nxt, 4)
+            t_cb = timeit(lambda: ops._corr_bwd(prv, nxt, cvout, g81, 4, 0.1), max(3, a.iters // 4), flush)
+            t_wb = timeit(lambda: ops._warp_bwd(nxt, flo, gC, 1), max(3, a.iters // 4), flush)
+            print(f"{'':>14}  corr_bwd {t_cb*1e6:9.1f} us ({4*81*C*px/t_cb/1e12:5.1f} TF)   warp_bwd {t_wb*1e6:8.1f} us ({4*(3*C+4)*px/t_wb/1e9:6.0f} GB/s)")
         flops = 2 * 81 * C * px
         by_corr, by_fused, by_warp = 4 * (2 * C + 81) * px, 4 * (2 * C + 2 + 81) * px, 4 * (2 * C + 2) * px
         lb = lambda by: max(by / HBM, flops / FP32)
