@@ -284,14 +284,24 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
             float4 bq[Q];
 #pragma unroll
             for (int m = 0; m < Q; ++m) bq[m] = *reinterpret_cast<const float4*>(nbp + m * (NCOL * Cfg::PXB));
+            // software-skewed: the (c2,c3) update of column k-1 is issued together with the (c0,c1)
+            // update of column k, so the two FFMA2s on one accumulator pair are >= 9 instructions
+            // apart whatever ptxas does locally (back-to-back they stall on the FMA latency)
+            float2 ahi_prev = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < Q; ++k) {
-              const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
-              const float2 alo = make_float2(a.x, a.y), ahi = make_float2(a.z, a.w);
+            for (int k = 0; k <= Q; ++k) {
+              float2 alo = make_float2(0.f, 0.f), ahi = make_float2(0.f, 0.f);
+              if (k < Q) {
+                const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
+                alo = make_float2(a.x, a.y); ahi = make_float2(a.z, a.w);
 #pragma unroll
-              for (int m = 0; m < Q; ++m) acc2[m][k] = __ffma2_rn(alo, make_float2(bq[m].x, bq[m].y), acc2[m][k]);
+                for (int m = 0; m < Q; ++m) acc2[m][k] = __ffma2_rn(alo, make_float2(bq[m].x, bq[m].y), acc2[m][k]);
+              }
+              if (k > 0) {
 #pragma unroll
-              for (int m = 0; m < Q; ++m) acc2[m][k] = __ffma2_rn(ahi, make_float2(bq[m].z, bq[m].w), acc2[m][k]);
+                for (int m = 0; m < Q; ++m) acc2[m][k - 1] = __ffma2_rn(ahi_prev, make_float2(bq[m].z, bq[m].w), acc2[m][k - 1]);
+              }
+              ahi_prev = ahi;
             }
           } else {
             float4 bv[Q];
@@ -467,7 +477,13 @@ int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow,
   static int scalar = -1;
   if (scalar < 0) { const char* e = getenv("QPWC_TILED_SCALAR"); scalar = (e && atoi(e)) ? 1 : 0; }
   if (scalar && !flow) return run_tiled<TiledCfg<6, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
-  if (!flow) return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  if (!flow) {
+    // few tiles (coarse pyramid levels): 2-row tiles double the number of busy SMs
+    const long long tiles4 = (long long)cdiv(W, 56) * cdiv(H, 4) * B;
+    if (tiles4 * 2 <= sm_count())
+      return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+    return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  }
   if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
   return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
 }

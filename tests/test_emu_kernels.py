@@ -94,7 +94,8 @@ def test_emu_host_entry_and_errors():
 
 
 # ------------------------------------------------------------------ register-tiled kernels (d=4, C%4==0)
-TILED = [(1, 7, 60, 8), (2, 13, 70, 12), (1, 9, 57, 20), (1, 16, 16, 4)]
+TILED = [(1, 7, 60, 8), (2, 13, 70, 12), (1, 9, 57, 20), (1, 16, 16, 4),
+         (1, 4, 16, 8), (1, 3, 40, 4)]      # last two: single 4-row tile => the 2-row-tile variant
 
 
 @pytest.mark.parametrize("B,H,W,C", TILED)
