@@ -96,6 +96,14 @@ int qpwc_warp_corr_fwd_host(const float* prv, const float* nxt, const float* flo
                             int B, int H, int W, int C, int search_range, float leaky_slope,
                             int mode, int device);
 
+/* Deferred completion for the _host entry points: after qpwc_host_set_deferred(1) a _host call
+ * returns as soon as its copies and kernels are enqueued (on the library's internal streams), so
+ * that consecutive calls -- e.g. the five levels of one pyramid pass -- overlap their H2D, compute
+ * and D2H phases; qpwc_host_sync(device) then waits for everything enqueued so far.  The caller must
+ * keep input and output host buffers alive and unmodified until the sync.  Process-wide setting. */
+int qpwc_host_set_deferred(int on);
+int qpwc_host_sync(int device);
+
 #ifdef __cplusplus
 }
 #endif

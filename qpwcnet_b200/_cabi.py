@@ -59,6 +59,8 @@ def lib() -> ctypes.CDLL:
         "qpwc_corr_fwd_host": ([fp, fp, fp, i, i, i, i, i, f, i], c_int),
         "qpwc_warp_fwd_host": ([fp, fp, fp, i, i, i, i, i, i], c_int),
         "qpwc_warp_corr_fwd_host": ([fp, fp, fp, fp, i, i, i, i, i, f, i, i], c_int),
+        "qpwc_host_set_deferred": ([i], c_int),
+        "qpwc_host_sync": ([i], c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(L, name)          # AttributeError here = header/library mismatch: be loud
@@ -72,6 +74,7 @@ EXPORTED_SYMBOLS = (
     "qpwc_version", "qpwc_last_error", "qpwc_corr_fwd", "qpwc_corr_bwd", "qpwc_warp_fwd",
     "qpwc_warp_bwd", "qpwc_warp_corr_fwd", "qpwc_warp_corr_bwd_workspace", "qpwc_warp_corr_bwd",
     "qpwc_corr_fwd_host", "qpwc_warp_fwd_host", "qpwc_warp_corr_fwd_host",
+    "qpwc_host_set_deferred", "qpwc_host_sync",
 )
 
 

@@ -89,6 +89,7 @@ struct HostStage {
   std::mutex mu;
 };
 static HostStage g_stage[16];
+static bool g_host_deferred = false;  // qpwc_host_set_deferred(): _host calls return after enqueueing
 
 static int stage_reserve(HostStage& hs, int slot, size_t bytes) {
   if (!hs.stream[slot]) {
@@ -122,7 +123,8 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
   if (per > B) per = B;
   HostStage& hs = g_stage[device];
   std::lock_guard<std::mutex> lock(hs.mu);
-  int rc = QPWC_OK, slot = 0;
+  static int next_slot = 0;  // keeps rotating across calls: consecutive deferred calls overlap
+  int rc = QPWC_OK, slot = next_slot;
   for (int b0 = 0; b0 < B && rc == QPWC_OK; b0 += per, slot = (slot + 1) % HostStage::NSLOT) {
     const int nb = (B - b0 < per) ? (B - b0) : per;
     rc = stage_reserve(hs, slot, item * per);
@@ -142,11 +144,26 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
     if (rc != QPWC_OK) break;
     e = cudaMemcpyAsync(out + n_o * b0, dout, n_o * nb * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) { rc = set_error(QPWC_ERR_CUDA, "host call: D2H: %s", cudaGetErrorString(e)); break; }
+    next_slot = (slot + 1) % HostStage::NSLOT;
   }
+  if (g_host_deferred && rc == QPWC_OK) return rc;  // completion is collected by qpwc_host_sync()
   for (int s = 0; s < HostStage::NSLOT; ++s)
     if (hs.stream[s]) {
       e = cudaStreamSynchronize(hs.stream[s]);
       if (e != cudaSuccess && rc == QPWC_OK) rc = set_error(QPWC_ERR_CUDA, "host call: sync: %s", cudaGetErrorString(e));
+    }
+  return rc;
+}
+
+static int host_sync(int device) {
+  if (device < 0 || device >= 16) return set_error(QPWC_ERR_INVALID, "qpwc_host_sync: device ordinal %d outside [0,16)", device);
+  HostStage& hs = g_stage[device];
+  std::lock_guard<std::mutex> lock(hs.mu);
+  int rc = QPWC_OK;
+  for (int s = 0; s < HostStage::NSLOT; ++s)
+    if (hs.stream[s]) {
+      const cudaError_t e = cudaStreamSynchronize(hs.stream[s]);
+      if (e != cudaSuccess && rc == QPWC_OK) rc = set_error(QPWC_ERR_CUDA, "qpwc_host_sync: %s", cudaGetErrorString(e));
     }
   return rc;
 }
@@ -158,6 +175,8 @@ using namespace qpwc;
 extern "C" {
 
 int qpwc_version(void) { return 100; /* 0.1.0 */ }
+int qpwc_host_set_deferred(int on) { g_host_deferred = on != 0; return QPWC_OK; }
+int qpwc_host_sync(int device) { return host_sync(device); }
 const char* qpwc_last_error(void) { return g_err; }
 
 int qpwc_corr_fwd(const float* prv, const float* nxt, float* out, int B, int H, int W, int C,

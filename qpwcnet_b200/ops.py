@@ -309,5 +309,20 @@ def _check_out(out, prv):
                          f"got {tuple(out.shape)} {out.dtype} @ {out.device}")
 
 
+class host_batch:
+    """``with ops.host_batch():`` -- host-buffer (CPU tensor) calls inside the block only enqueue
+    their H2D / kernels / D2H on the library's streams and overlap with each other; the block exit
+    waits for all of them.  Inputs and outputs must stay alive and untouched until then."""
+
+    def __enter__(self):
+        check(lib().qpwc_host_set_deferred(1))
+        return self
+
+    def __exit__(self, *exc):
+        check(lib().qpwc_host_set_deferred(0))
+        check(lib().qpwc_host_sync(torch.cuda.current_device()))
+        return False
+
+
 def library_version() -> int:
     return int(lib().qpwc_version())

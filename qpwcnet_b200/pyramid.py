@@ -140,6 +140,11 @@ class PyramidWorkload:
     def step(self):
         """One pass of the hot path over the batch: 1 cost volume + 4 fused warp->cost volumes
         (five C-ABI launches on the current stream)."""
+        if not self.outputs[0].is_cuda:
+            with ops.host_batch():      # host buffers: let the five levels' copies/kernels overlap
+                for k in range(len(self.levels)):
+                    self.run_level(k)
+            return self.outputs
         for k in range(len(self.levels)):
             self.run_level(k)
         return self.outputs
