@@ -454,11 +454,13 @@ static int run_tiled(const float* prv, const float* nxt, const float* flow, floa
   const int grid = ntiles < sm_count() ? ntiles : sm_count();
   auto k = corr_fwd_tiled_kernel<Cfg>;
 #ifndef QPWC_EMU
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static unsigned attr_done = 0;  // per instantiation, one bit per device (the attribute is per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_done >> (dev & 31) & 1u)) {
     const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_fwd_tiled: smem attribute (%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-    attr_done = true;
+    attr_done |= 1u << (dev & 31);
   }
 #endif
   QPWC_LAUNCH(k, grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream, tmP, tmN, nxt, flow, out, B, H, W, C, slope, ops,
