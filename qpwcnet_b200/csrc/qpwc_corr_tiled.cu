@@ -82,7 +82,11 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
 corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CONSTANT TensorMap tmN,
                       const float* __restrict__ nxt, const float* __restrict__ flow,
                       float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
-                      int tiles_x, int tiles_y, int ntiles, int ablate) {
+                      int tiles_x, int tiles_y, int ntiles, int ablate, int nwin, int dsearch) {
+  // nwin = 1: the 9x9 displacement window is the whole search range (d = 4).  nwin = 4 (d = 8): the
+  // 17x17 range is covered by four 9x9 windows centred at (+-4, +-4); a tile index then also
+  // selects the window, whose offset (oi, oj) shifts the second-frame tile and the output channels
+  // (the shared lines di = 0 / dj = 0 are produced twice, bit-identically).
   constexpr int D = Cfg::D, Q = Cfg::Q, NDISP = Cfg::NDISP, TH = Cfg::TH, TW = Cfg::TW;
   constexpr int NCOL = Cfg::NCOL, PCOL = Cfg::PCOL, NROW = Cfg::NROW, NST = Cfg::NST, KC = Cfg::KC;
   constexpr int NCONS = Cfg::NCONS, NPROD = Cfg::NPROD, HALF = Cfg::HALF;
@@ -117,37 +121,45 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
     // idle along on the empty barriers: nothing would gate on them, so a slow one could fall two
     // phases behind and alias the parity wait (found by the CPU emulation harness).  In the fused
     // variant every producer warp arrives on `full`, which keeps all of them within one phase.
-    if (Cfg::AGENT && ptid >= 32 && ptid < 64) {
+    if (Cfg::AGENT && ptid >= 32) {
       // ---- store agent (plain variant): waits for each row's slot, issues its bulk store, and
       // releases the slots once the engine has read them.  Consumers never wait for stores.
       if (ablate & 2) return;
       const int lane = ptid & 31;
+      const int aw = (ptid >> 5) - 1;  // agent warp 0..2: rows r with r % 3 == aw
       uint32_t n = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
         const int tx = tile % tiles_x;
         const int ty = (tile / tiles_x) % tiles_y;
-        const int b = tile / (tiles_x * tiles_y);
+        const int bw = tile / (tiles_x * tiles_y);
+        const int b = bw / nwin, win = bw - b * nwin;
+        const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4);
         const int i0 = ty * TH, j0 = tx * TW;
         const int twv = min(TW, W - j0);
-        for (int r = 0; r < TH; ++r) {
+        for (int r = aw; r < TH; r += 3) {
           mbar_wait(&sfull[r], n & 1u);
           const int i = i0 + r;
           if (i < H) {
             const float* slot = reinterpret_cast<const float*>(smem + Cfg::OFF_STAGING + r * Cfg::SLOT_BYTES);
             float* dst = out + ((size_t)((size_t)b * H + i) * W + j0) * (size_t)ops;
             const int cnt = twv * NDISP;
-            if (ops == NDISP && (cnt & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            if (nwin == 1 && ops == NDISP && (cnt & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
               if (lane == 0) bulk_store(dst, slot, (uint32_t)cnt * 4u);
-            } else if (ops == NDISP) {  // unaligned row: plain coalesced copy
+            } else if (nwin == 1 && ops == NDISP) {  // unaligned row: plain coalesced copy
               for (int e = lane; e < cnt; e += 32) dst[e] = slot[e];
-            } else {                    // strided output (concat buffer)
-              for (int e = lane; e < cnt; e += 32) dst[(size_t)(e / NDISP) * ops + (e % NDISP)] = slot[e];
+            } else {  // strided output (concat buffer) and/or a window of a wider search range
+              const int qo = 2 * dsearch + 1;
+              const int chb = (oi - D + dsearch) * qo + (oj - D + dsearch);
+              for (int e = lane; e < cnt; e += 32) {
+                const int px = e / NDISP, mk = e - px * NDISP, m = mk / Q, k = mk - m * Q;
+                dst[(size_t)px * ops + chb + m * qo + k] = slot[e];
+              }
             }
           }
         }
         if (lane == 0) { bulk_commit(); bulk_wait_read<0>(); }
         __syncwarp();
-        if (lane == 0) for (int r = 0; r < TH; ++r) mbar_arrive(&sfree[r]);
+        if (lane == 0) for (int r = aw; r < TH; r += 3) mbar_arrive(&sfree[r]);
       }
       return;
     }
@@ -158,13 +170,15 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int tx = tile % tiles_x;
       const int ty = (tile / tiles_x) % tiles_y;
-      const int b = tile / (tiles_x * tiles_y);
+      const int bw = tile / (tiles_x * tiles_y);
+      const int b = bw / nwin, win = bw - b * nwin;
+      const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4);
       const int i0 = ty * TH, j0 = tx * TW;
       if (Cfg::WARP) {
         // per-tile table of sampling taps for every halo pixel of the warped second frame
         named_bar_sync(15, NPROD);  // previous tile's last chunk no longer reads the table
         for (int p = ptid; p < NROW * NCOL; p += NPROD) {
-          const int r = i0 - D + p / NCOL, s = j0 - D + p % NCOL;
+          const int r = i0 - D + oi + p / NCOL, s = j0 - D + oj + p % NCOL;
           TapsEntry e;
           e.o00 = -1; e.o01 = e.o10 = e.o11 = 0; e.w00 = e.w01 = e.w10 = e.w11 = 0.f;
           if (r >= 0 && r < H && s >= 0 && s < W) {  // outside: zero padding of the warped frame
@@ -185,7 +199,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         if (ptid == 0) {
           mbar_arrive_expect_tx(&full[stage], Cfg::P_BYTES + (Cfg::WARP ? 0 : Cfg::N_BYTES));
           tma_load_4d(sb, &tmP, &full[stage], c * KC, j0, i0, b);
-          if (!Cfg::WARP) tma_load_4d(sb + Cfg::P_BYTES, &tmN, &full[stage], c * KC, j0 - D, i0 - D, b);
+          if (!Cfg::WARP) tma_load_4d(sb + Cfg::P_BYTES, &tmN, &full[stage], c * KC, j0 - D + oj, i0 - D + oi, b);
         }
         if (Cfg::WARP) {
           // units: (halo pixel, 16-byte channel quad); NQ adjacent lanes share a pixel => 32/64-byte reads
@@ -259,7 +273,9 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int tx = tile % tiles_x;
       const int ty = (tile / tiles_x) % tiles_y;
-      const int b = tile / (tiles_x * tiles_y);
+      const int bw = tile / (tiles_x * tiles_y);
+      const int b = bw / nwin, win = bw - b * nwin;
+      const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4);
       const int i0 = ty * TH, j0 = tx * TW;
 
       float acc[Q][Q];              // scalar path
@@ -374,11 +390,17 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         if (i < H && lp1 > lp0) {
           float* dst = out + ((size_t)((size_t)b * H + i) * W + j0 + lp0) * (size_t)ops;
           const int n = (lp1 - lp0) * NDISP;
-          if (ops == NDISP && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          if (nwin == 1 && ops == NDISP && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
             if (leader) bulk_store(dst, slot, (uint32_t)n * 4u);
-          } else {  // strided / unaligned output: plain coalesced copy by the row's 64 threads
-            if (ops == NDISP) { for (int e = tc; e < n; e += NCOL) dst[e] = slot[e]; }
-            else { for (int e = tc; e < n; e += NCOL) dst[(size_t)(e / NDISP) * ops + (e % NDISP)] = slot[e]; }
+          } else if (nwin == 1 && ops == NDISP) {  // unaligned: plain coalesced copy by the row's 64 threads
+            for (int e = tc; e < n; e += NCOL) dst[e] = slot[e];
+          } else {  // strided output and/or a window of a wider search range
+            const int qo = 2 * dsearch + 1;
+            const int chb = (oi - D + dsearch) * qo + (oj - D + dsearch);
+            for (int e = tc; e < n; e += NCOL) {
+              const int px = e / NDISP, mk = e - px * NDISP, m = mk / Q, k = mk - m * Q;
+              dst[(size_t)px * ops + chb + m * qo + k] = slot[e];
+            }
           }
         }
         if (leader) bulk_commit();  // one group per half, also when empty: keeps wait_group counts uniform
@@ -443,12 +465,13 @@ static int ablate_flags() {
 
 template <class Cfg>
 static int run_tiled(const float* prv, const float* nxt, const float* flow, float* out, int B, int H,
-                     int W, int C, float slope, long long ops, cudaStream_t stream) {
+                     int W, int C, float slope, long long ops, cudaStream_t stream, int dsearch = 4) {
+  const int nwin = dsearch == 8 ? 4 : 1;
   TensorMap tmP, tmN;
   if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::KC, Cfg::PCOL, Cfg::TH)) return QPWC_ERR_CUDA;  // box 8 x 56 x TH
   if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, Cfg::KC, Cfg::NCOL, Cfg::NROW)) return QPWC_ERR_CUDA;
   const int tiles_x = cdiv(W, Cfg::TW), tiles_y = cdiv(H, Cfg::TH);
-  const long long nt = (long long)tiles_x * tiles_y * B;
+  const long long nt = (long long)tiles_x * tiles_y * B * nwin;
   if (nt >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
   const int ntiles = (int)nt;
   const int grid = ntiles < sm_count() ? ntiles : sm_count();
@@ -464,30 +487,31 @@ static int run_tiled(const float* prv, const float* nxt, const float* flow, floa
   }
 #endif
   QPWC_LAUNCH(k, grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream, tmP, tmN, nxt, flow, out, B, H, W, C, slope, ops,
-              tiles_x, tiles_y, ntiles, ablate_flags());
+              tiles_x, tiles_y, ntiles, ablate_flags(), nwin, dsearch);
   return check_launch("corr_fwd_tiled");
 }
 
 int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow, int mode, float* out,
                           int B, int H, int W, int C, int d, float slope, long long ops,
                           cudaStream_t stream) {
-  // domain: d == 4, C a multiple of 4, 16-byte aligned inputs (TMA), maps at least one tile wide
-  if (d != 4 || (C & 3) || C < 4) return QPWC_ERR_UNSUPPORTED;
+  // domain: d == 4 (one 9x9 window) or d == 8 (four windows), C a multiple of 4, 16-byte aligned
+  // inputs (TMA), maps at least one tile wide
+  if ((d != 4 && d != 8) || (C & 3) || C < 4) return QPWC_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15)) return QPWC_ERR_UNSUPPORTED;
   if ((long long)H * W < 64) return QPWC_ERR_UNSUPPORTED;
   // QPWC_TILED_SCALAR=1 (dev): the scalar-FFMA 6-row variant instead of the packed-FFMA2 4-row one
   static int scalar = -1;
   if (scalar < 0) { const char* e = getenv("QPWC_TILED_SCALAR"); scalar = (e && atoi(e)) ? 1 : 0; }
-  if (scalar && !flow) return run_tiled<TiledCfg<6, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  if (scalar && !flow && d == 4) return run_tiled<TiledCfg<6, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
   if (!flow) {
     // few tiles (coarse pyramid levels): 2-row tiles double the number of busy SMs
-    const long long tiles4 = (long long)cdiv(W, 56) * cdiv(H, 4) * B;
+    const long long tiles4 = (long long)cdiv(W, 56) * cdiv(H, 4) * B * (d == 8 ? 4 : 1);
     if (tiles4 * 2 <= sm_count())
-      return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
-    return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+      return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+    return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
   }
-  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
-  return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
+  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+  return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
 }
 
 int launch_corr_bwd_tiled(const float*, const float*, const float*, const float*, float*, float*,

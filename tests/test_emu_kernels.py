@@ -124,3 +124,24 @@ def test_emu_fused_fwd_tiled(mode, B, H, W, C):
     # the fused kernel warps with exactly the stand-alone warp kernel's arithmetic
     comp = emu_lib.corr_fwd(prv, emu_lib.warp_fwd(nxt, flo, mode), 4)
     np.testing.assert_allclose(got, comp, rtol=0, atol=1e-6 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("B,H,W,C", [(1, 10, 60, 8), (2, 7, 21, 4)])
+def test_emu_tiled_search_range_8(B, H, W, C):
+    """d = 8 runs the tiled kernel as four 9x9 windows of the 17x17 range."""
+    r = rng(31)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    flo = (r.standard_normal((B, H, W, 2)) * 3).astype(np.float32)
+    a64 = [a.astype(np.float64) for a in (prv, nxt, flo)]
+    ref = oracle.cost_volume(a64[0], a64[1], 8)
+    got = emu_lib.corr_fwd(prv, nxt, 8)
+    assert got.shape[-1] == 289 and not np.isnan(got).any()
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    got_s = emu_lib.corr_fwd(prv, nxt, 8, ops=289 + 7)
+    np.testing.assert_array_equal(got_s[..., :289], got)
+    assert np.isnan(got_s[..., 289:]).all()
+    for mode in ("tf", "tfa"):
+        reff = oracle.warp_cost_volume(*a64, mode, 8)
+        gotf = emu_lib.warp_corr_fwd(prv, nxt, flo, mode, 8)
+        assert np.abs(gotf - reff).max() <= 1e-5 * np.abs(reff).max()
