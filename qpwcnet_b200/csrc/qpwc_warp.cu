@@ -85,111 +85,100 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
 
 // ------------------------------------------------------------------------------------------ bwd
 // G lanes per pixel (power of two, <= 32).  Lane l of a group handles channel vectors l, l+G, ...
+// grid = (ceil(W / groups_per_block), H, B): row and batch come from the block index (32-bit maths).
 template <int MODE, int V>
 __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__ img,
                                                        const float* __restrict__ flow,
                                                        const float* __restrict__ g_out,
                                                        float* __restrict__ g_img,
                                                        float* __restrict__ g_flow, int H, int W, int C,
-                                                       int G, long long npix) {
+                                                       int G) {
   const int CV = C / V;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);           // lane inside the group
   const int groups_per_block = blockDim.x / G;
-  const int gid = threadIdx.x / G;
-  const long long gstride = (long long)gridDim.x * groups_per_block;
-  // every lane of a warp runs the same number of iterations (shuffles below need the full warp)
-  const long long iters = cdivll(npix, gstride);
-  for (long long it = 0; it < iters; ++it) {
-    const long long pix = (long long)blockIdx.x * groups_per_block + gid + it * gstride;
-    const bool live = pix < npix;
-    float gx = 0.f, gy = 0.f;
-    bool px = true, py = true;
-    if (live) {
-      const int j = (int)(pix % W);
-      const long long bi = pix / W;
-      const int i = (int)(bi % H);
-      const long long b = bi / H;
-      const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);
-      Taps t;
-      if (MODE == QPWC_MODE_TF) t = taps_tf(i, j, f.x, f.y, H, W);
-      else t = taps_tfa(i, j, f.x, f.y, H, W, &px, &py);
-      const size_t boff = (size_t)b * H * W * C;
-      for (int cv = gl; cv < CV; cv += G) {
-        const size_t co = (size_t)cv * V;
-        float v00[V], v01[V], v10[V], v11[V], g[V], a00[V], a01[V], a10[V], a11[V];
-        vload<V>(img + boff + (size_t)t.o00 * C + co, v00);
-        vload<V>(img + boff + (size_t)t.o01 * C + co, v01);
-        vload<V>(img + boff + (size_t)t.o10 * C + co, v10);
-        vload<V>(img + boff + (size_t)t.o11 * C + co, v11);
-        vload<V>(g_out + (size_t)pix * C + co, g);
+  const int j = blockIdx.x * groups_per_block + threadIdx.x / G;
+  const int i = blockIdx.y;
+  const bool live = j < W;                 // whole groups are live or not; shuffles below need the full warp
+  const size_t boff = (size_t)blockIdx.z * H * W * C;
+  const size_t pix = ((size_t)blockIdx.z * H + i) * W + (live ? j : 0);
+  float gx = 0.f, gy = 0.f;
+  bool px = true, py = true;
+  if (live) {
+    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);
+    Taps t;
+    if (MODE == QPWC_MODE_TF) t = taps_tf(i, j, f.x, f.y, H, W);
+    else t = taps_tfa(i, j, f.x, f.y, H, W, &px, &py);
+    // mode TF: the 1-D factors of the weights, recomputed exactly as taps_tf does
+    float ax1 = 0.f, ax0 = 0.f, ay1 = 0.f, ay0 = 0.f;
+    if (MODE == QPWC_MODE_TF) {
+      const float x = __fadd_rn((float)j, f.x), y = __fadd_rn((float)i, f.y);
+      const int y0 = t.o00 / W, x0 = t.o00 - y0 * W, y1 = t.o11 / W, x1 = t.o11 - y1 * W;
+      ax1 = __fsub_rn((float)x1, x); ax0 = __fsub_rn(x, (float)x0);
+      ay1 = __fsub_rn((float)y1, y); ay0 = __fsub_rn(y, (float)y0);
+    }
+    const bool dupx = (MODE == QPWC_MODE_TF) && (t.o00 == t.o01);
+    const bool dupy = (MODE == QPWC_MODE_TF) && (t.o00 == t.o10);
+    for (int cv = gl; cv < CV; cv += G) {
+      const size_t co = (size_t)cv * V;
+      float v00[V], v01[V], v10[V], v11[V], g[V], a00[V], a01[V], a10[V], a11[V];
+      vload<V>(img + boff + (size_t)t.o00 * C + co, v00);
+      vload<V>(img + boff + (size_t)t.o01 * C + co, v01);
+      vload<V>(img + boff + (size_t)t.o10 * C + co, v10);
+      vload<V>(img + boff + (size_t)t.o11 * C + co, v11);
+      vload<V>(g_out + pix * C + co, g);
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          if (MODE == QPWC_MODE_TF) {
-            // gather_nd grad: scatter w*g into the four clipped taps
-            a00[k] = __fmul_rn(t.w00, g[k]); a10[k] = __fmul_rn(t.w10, g[k]);
-            a01[k] = __fmul_rn(t.w01, g[k]); a11[k] = __fmul_rn(t.w11, g[k]);
-          } else {
-            const float ax = t.w00, ay = t.w01;
-            const float top = __fadd_rn(__fmul_rn(ax, __fsub_rn(v01[k], v00[k])), v00[k]);
-            const float bot = __fadd_rn(__fmul_rn(ax, __fsub_rn(v11[k], v10[k])), v10[k]);
-            // every product/sum rounded on its own, like the TF gradient graph (and the oracle)
-            gy = __fadd_rn(gy, __fmul_rn(g[k], __fsub_rn(bot, top)));
-            const float g_bot = __fmul_rn(ay, g[k]);
-            const float g_top = __fsub_rn(g[k], g_bot);
-            gx = __fadd_rn(gx, __fadd_rn(__fmul_rn(g_top, __fsub_rn(v01[k], v00[k])),
-                                         __fmul_rn(g_bot, __fsub_rn(v11[k], v10[k]))));
-            const float g_tr = __fmul_rn(ax, g_top), g_br = __fmul_rn(ax, g_bot);
-            a01[k] = g_tr; a00[k] = __fsub_rn(g_top, g_tr); a11[k] = g_br; a10[k] = __fsub_rn(g_bot, g_br);
-          }
-        }
+      for (int k = 0; k < V; ++k) {
         if (MODE == QPWC_MODE_TF) {
-          // d/dx = g*[-(y1-y)Ia - (y-y0)Ib + (y1-y)Ic + (y-y0)Id], d/dy analogous (Ia=v00 Ib=v10
-          // Ic=v01 Id=v11); the 1-D factors are recomputed exactly as taps_tf does.
-          const float x = __fadd_rn((float)j, f.x), y = __fadd_rn((float)i, f.y);
-          const int x0 = t.o00 % W, y0 = t.o00 / W, x1 = t.o11 % W, y1 = t.o11 / W;
-          const float ax1 = __fsub_rn((float)x1, x), ax0 = __fsub_rn(x, (float)x0);
-          const float ay1 = __fsub_rn((float)y1, y), ay0 = __fsub_rn(y, (float)y0);
-#pragma unroll
-          for (int k = 0; k < V; ++k) {
-            // un-contracted on purpose: clipped taps (Ia == Ic, ...) must cancel exactly as in TF
-            const float sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-ay1, v00[k]), __fmul_rn(-ay0, v10[k])),
-                                                 __fmul_rn(ay1, v01[k])), __fmul_rn(ay0, v11[k]));
-            const float sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-ax1, v00[k]), __fmul_rn(ax1, v10[k])),
-                                                 __fmul_rn(-ax0, v01[k])), __fmul_rn(ax0, v11[k]));
-            gx = __fadd_rn(gx, __fmul_rn(g[k], sx));
-            gy = __fadd_rn(gy, __fmul_rn(g[k], sy));
-          }
+          // gather_nd grad: scatter w*g into the four clipped taps; d/dx = g*[-(y1-y)Ia - (y-y0)Ib +
+          // (y1-y)Ic + (y-y0)Id], d/dy analogous (Ia=v00 Ib=v10 Ic=v01 Id=v11).  Un-contracted on
+          // purpose: clipped taps (Ia == Ic, ...) must cancel exactly as in TF.
+          a00[k] = __fmul_rn(t.w00, g[k]); a10[k] = __fmul_rn(t.w10, g[k]);
+          a01[k] = __fmul_rn(t.w01, g[k]); a11[k] = __fmul_rn(t.w11, g[k]);
+          const float sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-ay1, v00[k]), __fmul_rn(-ay0, v10[k])),
+                                               __fmul_rn(ay1, v01[k])), __fmul_rn(ay0, v11[k]));
+          const float sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-ax1, v00[k]), __fmul_rn(ax1, v10[k])),
+                                               __fmul_rn(-ax0, v01[k])), __fmul_rn(ax0, v11[k]));
+          gx = __fadd_rn(gx, __fmul_rn(g[k], sx));
+          gy = __fadd_rn(gy, __fmul_rn(g[k], sy));
+        } else {
+          // every product/sum rounded on its own, like the TF gradient graph (and the oracle)
+          const float ax = t.w00, ay = t.w01;
+          const float top = __fadd_rn(__fmul_rn(ax, __fsub_rn(v01[k], v00[k])), v00[k]);
+          const float bot = __fadd_rn(__fmul_rn(ax, __fsub_rn(v11[k], v10[k])), v10[k]);
+          gy = __fadd_rn(gy, __fmul_rn(g[k], __fsub_rn(bot, top)));
+          const float g_bot = __fmul_rn(ay, g[k]);
+          const float g_top = __fsub_rn(g[k], g_bot);
+          gx = __fadd_rn(gx, __fadd_rn(__fmul_rn(g_top, __fsub_rn(v01[k], v00[k])),
+                                       __fmul_rn(g_bot, __fsub_rn(v11[k], v10[k]))));
+          const float g_tr = __fmul_rn(ax, g_top), g_br = __fmul_rn(ax, g_bot);
+          a01[k] = g_tr; a00[k] = __fsub_rn(g_top, g_tr); a11[k] = g_br; a10[k] = __fsub_rn(g_bot, g_br);
         }
-        // Clipped taps coincide (mode TF, sample outside the image): fold them in registers first.
-        // Their weights are exact negatives of each other, so the fold cancels exactly -- as the
-        // reference's sequential scatter does -- instead of leaving +-|w*g| rounding residue in an
-        // order-dependent atomic sum; it also saves the redundant atomics.
-        const bool dupx = (MODE == QPWC_MODE_TF) && (t.o00 == t.o01);
-        const bool dupy = (MODE == QPWC_MODE_TF) && (t.o00 == t.o10);
-        if (dupx) {
-#pragma unroll
-          for (int k = 0; k < V; ++k) { a00[k] = __fadd_rn(a00[k], a01[k]); a10[k] = __fadd_rn(a10[k], a11[k]); }
-        }
-        if (dupy) {
-#pragma unroll
-          for (int k = 0; k < V; ++k) { a00[k] = __fadd_rn(a00[k], a10[k]); a01[k] = __fadd_rn(a01[k], a11[k]); }
-        }
-        vatomic_add<V>(g_img + boff + (size_t)t.o00 * C + co, a00);
-        if (!dupx) vatomic_add<V>(g_img + boff + (size_t)t.o01 * C + co, a01);
-        if (!dupy) vatomic_add<V>(g_img + boff + (size_t)t.o10 * C + co, a10);
-        if (!dupx && !dupy) vatomic_add<V>(g_img + boff + (size_t)t.o11 * C + co, a11);
       }
-    }
-    // fixed-order butterfly over the G lanes of the group
-    for (int o = G >> 1; o > 0; o >>= 1) {
-      gx += __shfl_xor_sync(0xffffffffu, gx, o);
-      gy += __shfl_xor_sync(0xffffffffu, gy, o);
-    }
-    if (live && gl == 0) {
-      reinterpret_cast<float2*>(g_flow)[pix] = make_float2(px ? gx : 0.f, py ? gy : 0.f);
+      // Clipped taps coincide (mode TF, sample outside the image): fold them in registers first.
+      // Their weights are exact negatives of each other, so the fold cancels exactly -- as the
+      // reference's sequential scatter does -- instead of leaving +-|w*g| rounding residue in an
+      // order-dependent atomic sum; it also saves the redundant atomics.
+      if (dupx) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { a00[k] = __fadd_rn(a00[k], a01[k]); a10[k] = __fadd_rn(a10[k], a11[k]); }
+      }
+      if (dupy) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { a00[k] = __fadd_rn(a00[k], a10[k]); a01[k] = __fadd_rn(a01[k], a11[k]); }
+      }
+      vatomic_add<V>(g_img + boff + (size_t)t.o00 * C + co, a00);
+      if (!dupx) vatomic_add<V>(g_img + boff + (size_t)t.o01 * C + co, a01);
+      if (!dupy) vatomic_add<V>(g_img + boff + (size_t)t.o10 * C + co, a10);
+      if (!dupx && !dupy) vatomic_add<V>(g_img + boff + (size_t)t.o11 * C + co, a11);
     }
   }
+  // fixed-order butterfly over the G lanes of the group
+  for (int o = G >> 1; o > 0; o >>= 1) {
+    gx += __shfl_xor_sync(0xffffffffu, gx, o);
+    gy += __shfl_xor_sync(0xffffffffu, gy, o);
+  }
+  if (live && gl == 0) reinterpret_cast<float2*>(g_flow)[pix] = make_float2(px ? gx : 0.f, py ? gy : 0.f);
 }
 
 // ------------------------------------------------------------------------------------ launchers
@@ -237,16 +226,20 @@ int launch_warp_fwd(const float* img, const float* flow, float* out, int B, int 
 
 template <int MODE, int V>
 static void run_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
-                         float* g_flow, int H, int W, int C, long long npix, cudaStream_t stream) {
+                         float* g_flow, int B, int H, int W, int C, cudaStream_t stream) {
   const int CV = C / V;
   int G = 1;
   while (G < CV && G < 32) G <<= 1;
   const int block = 256;
   const int groups_per_block = block / G;
-  const long long want = cdivll(npix, groups_per_block);
-  const int grid = (int)(want < 148LL * 16 ? want : 148LL * 16);
   auto k = warp_bwd_kernel<MODE, V>;
-  QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, g_out, g_img, g_flow, H, W, C, G, npix);
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
+    const dim3 grid((unsigned)cdiv(W, groups_per_block), (unsigned)H, (unsigned)nb);
+    const size_t off = (size_t)b0 * H * W;
+    QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + off * 2, g_out + off * C, g_img + off * C,
+                g_flow + off * 2, H, W, C, G);
+  }
 }
 
 int launch_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
@@ -256,14 +249,15 @@ int launch_warp_bwd(const float* img, const float* flow, const float* g_out, flo
   cudaError_t e = cudaMemsetAsync(g_img, 0, sizeof(float) * (size_t)npix * C, stream);
   if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "warp_bwd: memset g_img: %s", cudaGetErrorString(e));
   const int V = pick_vec(C, img, g_out, g_img);
+  if (H > 65535) return set_error(QPWC_ERR_UNSUPPORTED, "warp_bwd: H > 65535");
   if (mode == QPWC_MODE_TF) {
-    if (V == 4) run_warp_bwd<QPWC_MODE_TF, 4>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
-    else if (V == 2) run_warp_bwd<QPWC_MODE_TF, 2>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
-    else run_warp_bwd<QPWC_MODE_TF, 1>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
+    if (V == 4) run_warp_bwd<QPWC_MODE_TF, 4>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
+    else if (V == 2) run_warp_bwd<QPWC_MODE_TF, 2>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
+    else run_warp_bwd<QPWC_MODE_TF, 1>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
   } else {
-    if (V == 4) run_warp_bwd<QPWC_MODE_TFA, 4>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
-    else if (V == 2) run_warp_bwd<QPWC_MODE_TFA, 2>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
-    else run_warp_bwd<QPWC_MODE_TFA, 1>(img, flow, g_out, g_img, g_flow, H, W, C, npix, stream);
+    if (V == 4) run_warp_bwd<QPWC_MODE_TFA, 4>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
+    else if (V == 2) run_warp_bwd<QPWC_MODE_TFA, 2>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
+    else run_warp_bwd<QPWC_MODE_TFA, 1>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
   }
   return check_launch("warp_bwd");
 }
