@@ -47,8 +47,9 @@ struct TiledCfg {
   static constexpr int NST = WARP_ ? 2 : ((PACKED_ || TH_ <= 4) ? 4 : 3);
   static constexpr int P_BYTES = TH * PCOL * PXB, N_BYTES = NROW * NCOL * PXB;
   static constexpr int STAGE_BYTES = P_BYTES + N_BYTES;
-  // producers: plain = 1 TMA thread + 1 store-agent warp (of a 128-thread warpgroup, the unit of
-  // setmaxnreg); fused = 8 gather warps -- the gathers are latency-bound, they need the parallelism
+  // producers (128-thread warpgroups, the unit of setmaxnreg): plain = 1 TMA thread + 3 store-agent
+  // warps; fused = 8 gather warps -- the gathers are latency-bound, they need the parallelism
+  // (measured: 4 gather warps with 200-register consumers are slower at every level)
   static constexpr int NCONS = TH * TWT, NPROD = WARP_ ? 256 : 128, NTHREADS = NCONS + NPROD;
   // Epilogue staging.  AGENT (plain variant): one full-row slot per tile row; consumer warps only
   // deposit their accumulators and move on, a store-agent warp hands the row to the TMA engine.
@@ -76,13 +77,34 @@ struct TiledCfg {
 
 struct TapsEntry { int o00, o01, o10, o11; float w00, w01, w10, w11; };  // 32 bytes
 
+// Work enumeration shared by the three roles (producer, consumers, store agent): a CTA takes
+// segments segi = blockIdx.x, blockIdx.x + gridDim.x, ...; a segment is `seg` vertically consecutive
+// tiles of one (batch, window, tile column) strip.  seg == 1 is the plain tile list.  seg > 1 is
+// used by the fused variant when all channels fit in the pipeline stages (C <= KC*NST): consecutive
+// tiles then share TH+2D-TH = 2D halo rows, which stay in shared memory ("rolling" rows) -- only TH
+// new warped rows are produced per tile instead of TH+2D.
+#define QPWC_FOR_TILES_BEGIN                                                                     \
+  for (int segi = blockIdx.x; segi < nsegs; segi += gridDim.x) {                                 \
+    const int tx = segi % tiles_x, rest_ = segi / tiles_x; /* tile column fastest: concurrent   */ \
+    const int sy = rest_ % segs_per_strip, bw = rest_ / segs_per_strip; /* CTAs share image rows */ \
+    const int b = bw / nwin, win = bw - b * nwin;                                                \
+    const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4); \
+    const int seg_ = Cfg::WARP ? seg : 1; /* plain variants: compile-time single-tile segments */ \
+    for (int tseg = 0; tseg < seg_; ++tseg) {                                                    \
+      const int ty = sy * seg_ + tseg;                                                           \
+      if (ty >= tiles_y) break;                                                                  \
+      const int i0 = ty * TH, j0 = tx * TW;                                                      \
+      (void)oi; (void)oj; (void)b;
+#define QPWC_FOR_TILES_END }}
+
 // ---------------------------------------------------------------------------------------------
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
 corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CONSTANT TensorMap tmN,
                       const float* __restrict__ nxt, const float* __restrict__ flow,
                       float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
-                      int tiles_x, int tiles_y, int ntiles, int ablate, int nwin, int dsearch) {
+                      int tiles_x, int tiles_y, int nsegs, int segs_per_strip, int seg, int ablate, int nwin,
+                      int dsearch) {
   // nwin = 1: the 9x9 displacement window is the whole search range (d = 4).  nwin = 4 (d = 8): the
   // 17x17 range is covered by four 9x9 windows centred at (+-4, +-4); a tile index then also
   // selects the window, whose offset (oi, oj) shifts the second-frame tile and the output channels
@@ -101,6 +123,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
 
   const int tid = threadIdx.x;
   const int nchunks = (C + KC - 1) / KC;
+  const bool fixed_stage = Cfg::WARP && nchunks <= NST;  // fused variant with all channels resident
 
   if (tid == 0) {
 #ifndef QPWC_EMU
@@ -128,13 +151,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
       const int lane = ptid & 31;
       const int aw = (ptid >> 5) - 1;  // agent warp 0..2: rows r with r % 3 == aw
       uint32_t n = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
-        const int tx = tile % tiles_x;
-        const int ty = (tile / tiles_x) % tiles_y;
-        const int bw = tile / (tiles_x * tiles_y);
-        const int b = bw / nwin, win = bw - b * nwin;
-        const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4);
-        const int i0 = ty * TH, j0 = tx * TW;
+      QPWC_FOR_TILES_BEGIN
         const int twv = min(TW, W - j0);
         for (int r = aw; r < TH; r += 3) {
           mbar_wait(&sfull[r], n & 1u);
@@ -160,25 +177,25 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         if (lane == 0) { bulk_commit(); bulk_wait_read<0>(); }
         __syncwarp();
         if (lane == 0) for (int r = aw; r < TH; r += 3) mbar_arrive(&sfree[r]);
-      }
+        ++n;
+      QPWC_FOR_TILES_END
       return;
     }
     if (!Cfg::WARP && ptid != 0) return;
     if (ablate & 4) return;  // dev ablation: no loads at all
     TapsEntry* taps = reinterpret_cast<TapsEntry*>(smem + Cfg::OFF_TAPS);
-    uint32_t g = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int tx = tile % tiles_x;
-      const int ty = (tile / tiles_x) % tiles_y;
-      const int bw = tile / (tiles_x * tiles_y);
-      const int b = bw / nwin, win = bw - b * nwin;
-      const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4);
-      const int i0 = ty * TH, j0 = tx * TW;
+    uint32_t g = 0, ptile = 0;
+    QPWC_FOR_TILES_BEGIN
+      // rolling rows: the first tile of a segment produces the whole (TH+2D)-row halo window, the
+      // following ones only its last TH rows; row rr of the window lives in ring slot (rot+rr)%NROW
+      const int rr0 = (tseg == 0) ? 0 : (NROW - TH);
+      const int rot = (tseg * TH) % NROW;
+      const int nprod_px = (NROW - rr0) * NCOL;
       if (Cfg::WARP) {
         // per-tile table of sampling taps for every halo pixel of the warped second frame
         named_bar_sync(15, NPROD);  // previous tile's last chunk no longer reads the table
-        for (int p = ptid; p < NROW * NCOL; p += NPROD) {
-          const int r = i0 - D + oi + p / NCOL, s = j0 - D + oj + p % NCOL;
+        for (int p = ptid; p < nprod_px; p += NPROD) {
+          const int r = i0 - D + oi + rr0 + p / NCOL, s = j0 - D + oj + p % NCOL;
           TapsEntry e;
           e.o00 = -1; e.o01 = e.o10 = e.o11 = 0; e.w00 = e.w01 = e.w10 = e.w11 = 0.f;
           if (r >= 0 && r < H && s >= 0 && s < W) {  // outside: zero padding of the warped frame
@@ -192,8 +209,9 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         named_bar_sync(15, NPROD);
       }
       for (int c = 0; c < nchunks; ++c, ++g) {
-        const int stage = g % NST;
-        const uint32_t ph = (g / NST) & 1u;
+        // rolling rows need chunk c of every tile in the same stage: stage = c, one use per tile
+        const int stage = fixed_stage ? c : (int)(g % NST);
+        const uint32_t ph = fixed_stage ? (ptile & 1u) : ((g / NST) & 1u);
         mbar_wait(&empty[stage], ph ^ 1u);  // consumers released this stage
         unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
         if (ptid == 0) {
@@ -205,7 +223,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           // units: (halo pixel, 16-byte channel quad); NQ adjacent lanes share a pixel => 32/64-byte reads
           const float* nb = nxt + (size_t)b * H * W * C + (size_t)c * KC;
           unsigned char* ns = sb + Cfg::P_BYTES;
-          constexpr int NU = NROW * NCOL * Cfg::NQ;
+          const int NU = nprod_px * Cfg::NQ;
           constexpr int UB = 4;  // units in flight per thread: 16 independent 16-byte gathers
           for (int u0 = ptid; u0 < NU; u0 += NPROD * UB) {
             TapsEntry e[UB];
@@ -242,7 +260,9 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
                   v.z = blend<Cfg::MODE>(t, v00[x].z, v01[x].z, v10[x].z, v11[x].z);
                   v.w = blend<Cfg::MODE>(t, v00[x].w, v01[x].w, v10[x].w, v11[x].w);
                 }
-                *reinterpret_cast<float4*>(ns + swz<Cfg::PXB>((uint32_t)((u / Cfg::NQ) * Cfg::PXB + (u % Cfg::NQ) * 16))) = v;
+                const int pp = u / Cfg::NQ;                                   // produced pixel (taps index)
+                const int srow = (rot + rr0 + pp / NCOL) % NROW;               // its ring slot row
+                *reinterpret_cast<float4*>(ns + swz<Cfg::PXB>((uint32_t)((srow * NCOL + pp % NCOL) * Cfg::PXB + (u % Cfg::NQ) * 16))) = v;
               }
             }
           }
@@ -250,13 +270,16 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           if ((tid & 31) == 0) mbar_arrive(&full[stage]);
         }
       }
-    }
+      ++ptile;
+    QPWC_FOR_TILES_END
   } else {
     // ========================================================================== consumers
     setmaxnreg_inc<Cfg::REG_CONS>();
     const int ti = tid / NCOL, tc = tid % NCOL, lane = tid & 31;
     // byte offsets inside a stage (channel quad 0; quad q = offset ^ (q << 4), see swz<>)
-    const uint32_t nb_off = Cfg::P_BYTES + swz<Cfg::PXB>((uint32_t)((ti * NCOL + tc) * Cfg::PXB));
+    // column part of the second-frame operand offset (the swizzle depends on the column only: the
+    // row pitch is a multiple of the swizzle period); the row part is brow[m], per tile
+    const uint32_t nb_off = Cfg::P_BYTES + swz<Cfg::PXB>((uint32_t)(((Cfg::WARP ? 0 : ti) * NCOL + tc) * Cfg::PXB));
     uint32_t a_off[Q];  // scalar path only (the packed path recomputes them)
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
@@ -269,14 +292,15 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
     float* slot0 = reinterpret_cast<float*>(smem + Cfg::OFF_STAGING + ti * Cfg::NSLOT * Cfg::SLOT_BYTES);  // private to this row
     const bool leader = (tc == 0);
 
-    uint32_t g = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int tx = tile % tiles_x;
-      const int ty = (tile / tiles_x) % tiles_y;
-      const int bw = tile / (tiles_x * tiles_y);
-      const int b = bw / nwin, win = bw - b * nwin;
-      const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4);
-      const int i0 = ty * TH, j0 = tx * TW;
+    uint32_t g = 0, tcount = 0, ctile = 0;
+    QPWC_FOR_TILES_BEGIN
+      // second-frame rows of this thread, as byte offsets inside the stage's N area (fused variant:
+      // ring slots, see the producer; plain variant: compile-time multiples of the row pitch)
+      uint32_t brow[Q];
+#pragma unroll
+      for (int m = 0; m < Q; ++m)
+        brow[m] = Cfg::WARP ? (uint32_t)(((tseg * TH) % NROW + ti + m) % NROW) * (NCOL * Cfg::PXB)
+                            : (uint32_t)(m * (NCOL * Cfg::PXB));   // compile-time: folds into the load
 
       float acc[Q][Q];              // scalar path
       float2 acc2[Q][Q];            // packed path: (even-channel sum, odd-channel sum) per output
@@ -286,8 +310,8 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         for (int k = 0; k < Q; ++k) { acc[m][k] = 0.f; acc2[m][k] = make_float2(0.f, 0.f); }
 
       for (int c = 0; c < nchunks; ++c, ++g) {
-        const int stage = g % NST;
-        if (!(ablate & 4)) mbar_wait(&full[stage], (g / NST) & 1u);
+        const int stage = fixed_stage ? c : (int)(g % NST);
+        if (!(ablate & 4)) mbar_wait(&full[stage], fixed_stage ? (ctile & 1u) : ((g / NST) & 1u));
         const unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
         if (!(ablate & 1))
 #pragma unroll
@@ -299,7 +323,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
             // measured 30 % slower: it can no longer interleave the operand loads)
             float4 bq[Q];
 #pragma unroll
-            for (int m = 0; m < Q; ++m) bq[m] = *reinterpret_cast<const float4*>(nbp + m * (NCOL * Cfg::PXB));
+            for (int m = 0; m < Q; ++m) bq[m] = *reinterpret_cast<const float4*>(nbp + brow[m]);
             // software-skewed: the (c2,c3) update of column k-1 is issued together with the (c0,c1)
             // update of column k, so the two FFMA2s on one accumulator pair are >= 9 instructions
             // apart whatever ptxas does locally (back-to-back they stall on the FMA latency)
@@ -322,7 +346,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           } else {
             float4 bv[Q];
 #pragma unroll
-            for (int m = 0; m < Q; ++m) bv[m] = *reinterpret_cast<const float4*>(nbp + m * (NCOL * Cfg::PXB));
+            for (int m = 0; m < Q; ++m) bv[m] = *reinterpret_cast<const float4*>(nbp + brow[m]);
 #pragma unroll
             for (int k = 0; k < Q; ++k) {
               const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
@@ -339,6 +363,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         __syncwarp();
         if (lane == 0 && !(ablate & 4)) mbar_arrive(&empty[stage]);
       }
+      ++ctile;
       if (ablate & 2) continue;  // dev ablation: no epilogue
 
       // -------------------------------------------------------------------------- epilogue
@@ -405,7 +430,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         }
         if (leader) bulk_commit();  // one group per half, also when empty: keeps wait_group counts uniform
       }
-    }
+    QPWC_FOR_TILES_END
     if (!Cfg::AGENT && leader) bulk_wait_read<0>();  // shared memory must outlive the engine's reads
   }
 }
@@ -471,10 +496,21 @@ static int run_tiled(const float* prv, const float* nxt, const float* flow, floa
   if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::KC, Cfg::PCOL, Cfg::TH)) return QPWC_ERR_CUDA;  // box 8 x 56 x TH
   if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, Cfg::KC, Cfg::NCOL, Cfg::NROW)) return QPWC_ERR_CUDA;
   const int tiles_x = cdiv(W, Cfg::TW), tiles_y = cdiv(H, Cfg::TH);
-  const long long nt = (long long)tiles_x * tiles_y * B * nwin;
-  if (nt >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
-  const int ntiles = (int)nt;
-  const int grid = ntiles < sm_count() ? ntiles : sm_count();
+  // rolling rows (fused variant, all channels resident in the stages, single window): segments of
+  // vertically consecutive tiles; short enough that there are several segments per SM
+  int seg = 1;
+  if (Cfg::WARP && nwin == 1 && cdiv(C, Cfg::KC) <= Cfg::NST) {
+    seg = 8;
+    while (seg > 2 && (long long)tiles_x * B * cdiv(tiles_y, seg) < 3LL * sm_count()) seg >>= 1;
+    static int forced = -1;  // QPWC_SEG (dev/tests): force the segment length
+    if (forced < 0) { const char* e = getenv("QPWC_SEG"); forced = e ? atoi(e) : 0; }
+    if (forced > 0) seg = forced;
+  }
+  const int segs_per_strip = cdiv(tiles_y, seg);
+  const long long ns = (long long)tiles_x * B * nwin * segs_per_strip;
+  if (ns >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
+  const int nsegs = (int)ns;
+  const int grid = nsegs < sm_count() ? nsegs : sm_count();
   auto k = corr_fwd_tiled_kernel<Cfg>;
 #ifndef QPWC_EMU
   static unsigned attr_done = 0;  // per instantiation, one bit per device (the attribute is per device)
@@ -487,7 +523,7 @@ static int run_tiled(const float* prv, const float* nxt, const float* flow, floa
   }
 #endif
   QPWC_LAUNCH(k, grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream, tmP, tmN, nxt, flow, out, B, H, W, C, slope, ops,
-              tiles_x, tiles_y, ntiles, ablate_flags(), nwin, dsearch);
+              tiles_x, tiles_y, nsegs, segs_per_strip, seg, ablate_flags(), nwin, dsearch);
   return check_launch("corr_fwd_tiled");
 }
 

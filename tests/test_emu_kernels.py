@@ -145,3 +145,30 @@ def test_emu_tiled_search_range_8(B, H, W, C):
         reff = oracle.warp_cost_volume(*a64, mode, 8)
         gotf = emu_lib.warp_corr_fwd(prv, nxt, flo, mode, 8)
         assert np.abs(gotf - reff).max() <= 1e-5 * np.abs(reff).max()
+
+
+@pytest.mark.parametrize("C", [16, 32])
+def test_emu_fused_rolling_rows_long_segments(C, monkeypatch):
+    """Fused variant with all channels resident (C <= 32): vertically consecutive tiles keep their
+    shared halo rows in shared memory; run in a subprocess with a forced segment length of 8 tiles so
+    that the ring rotation cycles through all its phases."""
+    import subprocess
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests/emu")
+import oracle, emu_lib
+r = np.random.default_rng(41)
+B, H, W, C = 1, 30, 70, int(sys.argv[1])
+prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+flo = (r.standard_normal((B, H, W, 2)) * 3).astype(np.float32)
+for mode in ("tf", "tfa"):
+    ref = oracle.warp_cost_volume(*(a.astype(np.float64) for a in (prv, nxt, flo)), mode, 4)
+    got = emu_lib.warp_corr_fwd(prv, nxt, flo, mode, 4)
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max(), mode
+print("ok")
+'''
+    env = dict(os.environ, QPWC_SEG="8")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code, str(C)], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
