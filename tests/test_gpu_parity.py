@@ -349,3 +349,46 @@ def test_non_default_stream_and_noncontiguous_inputs():
     nc = prv.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)     # NHWC view of NCHW storage
     assert not nc.is_contiguous()
     assert torch.equal(ops.cost_volume(nc, nxt, 4), ref)
+
+
+@pytest.mark.parametrize("d", [4, 8])
+def test_strided_output_concat_buffer(d):
+    """out_pixel_stride > (2d+1)^2: the cost volume lands in channels [0, D) of a wider buffer
+    (the OptFlow concat input, qpwcnet/core/non_layers.py:381-382); the other channels are untouched."""
+    r = rng(31 + d)
+    B, H, W, C = 2, 19, 61, 32
+    D = (2 * d + 1) ** 2
+    prv, nxt = dev(r.standard_normal((B, H, W, C))), dev(r.standard_normal((B, H, W, C)))
+    flo = dev(r.standard_normal((B, H, W, 2)) * 2)
+    for fused in (False, True):
+        buf = torch.full((B, H, W, D + C + 2), -7.0, device=DEV)
+        if fused:
+            ops.warp_cost_volume_into(buf, prv, nxt, flo, "tfa", d)
+            ref = ops.warp_cost_volume(prv, nxt, flo, "tfa", d)
+        else:
+            ops.cost_volume_into(buf, prv, nxt, d)
+            ref = ops.cost_volume(prv, nxt, d)
+        assert torch.equal(buf[..., :D], ref)
+        assert bool((buf[..., D:] == -7.0).all())
+
+
+def test_unaligned_and_odd_width_inputs():
+    """Views whose data pointer is only 4-byte aligned (no TMA) and widths that break the 16-byte
+    row alignment of the bulk store take the generic kernels / copy paths -- same numbers."""
+    r = rng(37)
+    B, H, W, C = 1, 13, 27, 8
+    prv_h, nxt_h = r.standard_normal((B, H, W, C)), r.standard_normal((B, H, W, C))
+    ref = oracle.cost_volume(prv_h.astype(np.float64), nxt_h.astype(np.float64), 4)
+    # odd width, aligned base
+    assert_rel(host(ops.cost_volume(dev(prv_h), dev(nxt_h), 4)), ref)
+    # misaligned base: carve the tensors out of a flat buffer at a 4-byte offset
+    n = B * H * W * C
+    flat_p = torch.empty(n + 1, device=DEV); flat_n = torch.empty(n + 1, device=DEV)
+    p_un = flat_p[1:].view(B, H, W, C); n_un = flat_n[1:].view(B, H, W, C)
+    p_un.copy_(dev(prv_h)); n_un.copy_(dev(nxt_h))
+    assert p_un.data_ptr() % 16 != 0 and p_un.is_contiguous()
+    assert_rel(host(ops.cost_volume(p_un, n_un, 4)), ref)
+    img = dev(r.random((B, H, W, C)))
+    flo = dev(r.standard_normal((B, H, W, 2)))
+    i_un = flat_p[1:].view(B, H, W, C); i_un.copy_(img)
+    np.testing.assert_array_equal(host(ops.warp(i_un, flo, "tf")), oracle.warp(host(img), host(flo), "tf"))
