@@ -121,8 +121,13 @@ def cpu_reference_step(sample_batch=1, threads=None, repeats=1):
 
     import oracle
     from qpwcnet_b200.pyramid import levels_for
-    if threads:
-        oracle.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1 per rank; the CPU arm is meant to use every host core
+    if not threads:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:  # pragma: no cover
+            threads = os.cpu_count() or 1
+    oracle.set_num_threads(threads)
     r = np.random.default_rng(0)
     data = []
     for lv in levels_for(HEIGHT, WIDTH):
