@@ -81,6 +81,13 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// opaque 8-byte shared-memory load (address in the shared window): ptxas may not merge or sink it
+__device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+  return v;
+}
+#define QPWC_SMEM_ADDR(p) smem_u32(p)
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -163,6 +170,9 @@ inline void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) { memcp
 inline void bulk_commit() {}
 template <int N> inline void bulk_wait_read() {}
 inline void named_bar_sync(int id, int nthreads) { qpwc_emu_named_barrier(id, nthreads); }
+// emulation: "shared window addresses" are offsets from the CTA's dynamic shared memory base
+inline float2 lds_f2(uint32_t saddr) { return *reinterpret_cast<const float2*>(qpwc_emu::dyn_smem() + saddr); }
+#define QPWC_SMEM_ADDR(p) ((uint32_t)(reinterpret_cast<const unsigned char*>(p) - qpwc_emu::dyn_smem()))
 template <int N> inline void setmaxnreg_inc() {}
 template <int N> inline void setmaxnreg_dec() {}
 

@@ -481,6 +481,8 @@ static int sm_count() {
 static int sm_count() { return 3; }  // small persistent grid: exercises the multi-tile loop
 #endif
 
+int sm_count_cached() { return sm_count(); }
+
 // QPWC_ABLATE (dev only): bit0 skip FFMA loop, bit1 skip epilogue, bit2 skip loads+pipeline
 static int ablate_flags() {
   static int v = -1;
@@ -527,6 +529,9 @@ static int run_tiled(const float* prv, const float* nxt, const float* flow, floa
   return check_launch("corr_fwd_tiled");
 }
 
+int launch_corr_fwd_rowpair(const float*, const float*, float*, int, int, int, int, int, float, long long,
+                            cudaStream_t);  // qpwc_corr_rowpair.cu
+
 int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow, int mode, float* out,
                           int B, int H, int W, int C, int d, float slope, long long ops,
                           cudaStream_t stream) {
@@ -540,6 +545,13 @@ int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow,
   if (scalar < 0) { const char* e = getenv("QPWC_TILED_SCALAR"); scalar = (e && atoi(e)) ? 1 : 0; }
   if (scalar && !flow && d == 4) return run_tiled<TiledCfg<6, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
   if (!flow) {
+    // QPWC_CORR_VARIANT=rowpair selects the row-pair kernel (qpwc_corr_rowpair.cu).  Its inner loop
+    // is faster (scalar-broadcast FFMA2, 0.73 vs 0.60 FMA/lane/clk in isolation) but with two
+    // pipeline stages and a 4-slot epilogue it only ties the 4-row kernel end to end on B200
+    // (195 vs 193 us at 224x512x32, B=8; ablations in profiles/README.md), so it is opt-in.
+    const char* var = getenv("QPWC_CORR_VARIANT");
+    if (var && var[0] == 'r')
+      return launch_corr_fwd_rowpair(prv, nxt, out, B, H, W, C, d, slope, ops, stream);
     // few tiles (coarse pyramid levels): 2-row tiles double the number of busy SMs
     const long long tiles4 = (long long)cdiv(W, 56) * cdiv(H, 4) * B * (d == 8 ? 4 : 1);
     if (tiles4 * 2 <= sm_count())

@@ -111,6 +111,37 @@ def test_emu_corr_fwd_tiled(B, H, W, C):
     assert np.isnan(got_s[..., 81:]).all()
 
 
+@pytest.mark.parametrize("B,H,W,C", [(1, 7, 60, 8), (2, 13, 70, 12), (1, 9, 57, 20), (1, 16, 16, 4), (1, 3, 40, 4)])
+def test_emu_corr_fwd_rowpair(B, H, W, C, monkeypatch):
+    """Row-pair FFMA2 kernel (qpwc_corr_rowpair.cu): TMA -> repack warp -> consumers -> staged bulk
+    stores; odd heights (half-filled row pairs), ragged widths, channel tails, strided output."""
+    monkeypatch.setenv("QPWC_CORR_VARIANT", "rowpair")
+    r = rng(12)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    ref = oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), 4)
+    got = emu_lib.corr_fwd(prv, nxt, 4)
+    assert not np.isnan(got).any()
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    got_s = emu_lib.corr_fwd(prv, nxt, 4, ops=81 + 3)
+    np.testing.assert_array_equal(got_s[..., :81], got)
+    assert np.isnan(got_s[..., 81:]).all()
+    monkeypatch.setenv("QPWC_CORR_VARIANT", "tiled")
+    old = emu_lib.corr_fwd(prv, nxt, 4)
+    np.testing.assert_allclose(got, old, rtol=0, atol=2e-6 * np.abs(ref).max())
+
+
+def test_emu_corr_fwd_rowpair_search_range_8(monkeypatch):
+    monkeypatch.setenv("QPWC_CORR_VARIANT", "rowpair")
+    r = rng(13)
+    prv = r.standard_normal((1, 10, 60, 8)).astype(np.float32)
+    nxt = r.standard_normal((1, 10, 60, 8)).astype(np.float32)
+    ref = oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), 8)
+    got = emu_lib.corr_fwd(prv, nxt, 8)
+    assert not np.isnan(got).any()
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("mode", ["tf", "tfa"])
 @pytest.mark.parametrize("B,H,W,C", TILED[:3])
 def test_emu_fused_fwd_tiled(mode, B, H, W, C):
