@@ -562,9 +562,13 @@ int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow,
   return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
 }
 
+#ifdef QPWC_EMU
+// the tiled backward kernel (qpwc_corr_bwd_tiled.cu) uses a 3-D grid and is not part of the CPU
+// emulation build; the emulated library always takes the direct backward kernels
 int launch_corr_bwd_tiled(const float*, const float*, const float*, const float*, float*, float*,
                           int, int, int, int, int, float, long long, cudaStream_t) {
   return QPWC_ERR_UNSUPPORTED;
 }
+#endif
 
 }  // namespace qpwc

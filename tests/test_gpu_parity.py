@@ -71,6 +71,25 @@ def test_cost_volume_forward(B, H, W, C, d):
     assert_rel(got, ref)
 
 
+@pytest.mark.parametrize("B,H,W,C,d", [(2, 14, 32, 256, 4), (1, 56, 128, 128, 4), (1, 33, 70, 64, 4), (1, 40, 72, 32, 4),
+                                       (1, 17, 19, 16, 4), (1, 20, 30, 32, 8), (2, 11, 61, 96, 4), (3, 61, 190, 36, 4)])
+def test_cost_volume_forward_rowpair_variant(B, H, W, C, d, monkeypatch):
+    """The opt-in row-pair FFMA2 kernel (qpwc_corr_rowpair.cu, QPWC_CORR_VARIANT=rowpair): odd
+    heights (half-filled row pairs), ragged widths, channel tails, d = 8 windows, strided output."""
+    monkeypatch.setenv("QPWC_CORR_VARIANT", "rowpair")
+    r = rng(B * 977 + C)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    ref = oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), d)
+    got = host(ops.cost_volume(dev(prv), dev(nxt), d))
+    assert_rel(got, ref)
+    D = (2 * d + 1) ** 2
+    buf = torch.full((B, H, W, D + 6), float("nan"), device=DEV)
+    ops.cost_volume_into(buf, dev(prv), dev(nxt), d)
+    np.testing.assert_array_equal(host(buf[..., :D]), got)
+    assert torch.isnan(buf[..., D:]).all()
+
+
 @pytest.mark.parametrize("B,H,W,C,d", [(4, 32, 64, 3, 4), (1, 28, 64, 256, 4), (1, 40, 72, 32, 4),
                                        (1, 17, 19, 16, 4), (1, 9, 9, 5, 4), (1, 12, 13, 6, 2),
                                        (1, 20, 30, 32, 8)])
