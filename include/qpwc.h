@@ -70,6 +70,22 @@ int qpwc_warp_fwd(const float* img, const float* flow, float* out, int B, int H,
 int qpwc_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
                   float* g_flow, int B, int H, int W, int C, int mode, void* stream);
 
+/* FrameInterpolate's two half-flow warps -- qpwcnet/core/non_layers.py:303-311 (layers.py:384-385):
+ *   nxt_w = warp((nxt, 0.5 * flo_01));  prv_w = warp((prv, 0.5 * flo_10));  concat([prv_w, nxt_w, ...])
+ * `_ex`: the flow is multiplied by flow_scale inside the kernel (one rounded multiply, the
+ * reference's own op) and the output may be a channel slice of a wider buffer (pixel stride >= C).
+ * `_pair_fwd`: both warps in ONE launch; out[..., 0:C] = warp(img_a, s*flow_a),
+ * out[..., C:2C] = warp(img_b, s*flow_b), pixel stride >= 2C.  `_bwd_ex`: g_out may be such a
+ * slice; g_flow is the gradient with respect to the UNSCALED flow. */
+int qpwc_warp_fwd_ex(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                     int mode, float flow_scale, long long out_pixel_stride, void* stream);
+int qpwc_warp_pair_fwd(const float* img_a, const float* flow_a, const float* img_b,
+                       const float* flow_b, float* out, int B, int H, int W, int C, int mode,
+                       float flow_scale, long long out_pixel_stride, void* stream);
+int qpwc_warp_bwd_ex(const float* img, const float* flow, const float* g_out, float* g_img,
+                     float* g_flow, int B, int H, int W, int C, int mode, float flow_scale,
+                     long long g_out_pixel_stride, void* stream);
+
 /* UpFlow's  CostVolumeV2((prv, WarpV2((nxt, flo))))  -- qpwcnet/core/non_layers.py:377-380
  * (layers.py:478-481) as ONE kernel: the warped second frame never reaches HBM. */
 int qpwc_warp_corr_fwd(const float* prv, const float* nxt, const float* flow, float* out, int B,

@@ -41,3 +41,10 @@ def warp_cost_volume(inputs, mode, search_range, fmt, leaky_slope=0.1):
     out = ops.warp_cost_volume(to_nhwc(prv, fmt), to_nhwc(nxt, fmt), to_nhwc(flo, fmt), mode,
                                search_range, leaky_slope)
     return from_nhwc(out, fmt)
+
+
+def half_flow_warps(inputs, mode, fmt, flow_scale=0.5):
+    prv, nxt, flo_01, flo_10 = inputs
+    out = ops.half_flow_warps(to_nhwc(prv, fmt), to_nhwc(nxt, fmt), to_nhwc(flo_01, fmt),
+                              to_nhwc(flo_10, fmt), mode, flow_scale)
+    return from_nhwc(out, fmt)

@@ -54,3 +54,18 @@ class WarpCostVolume(_Functor):
 
     def __call__(self, inputs):
         return _impl.warp_cost_volume(inputs, self.warp_mode, self.search_range, self.data_format)
+
+
+class HalfFlowWarps(_Functor):
+    """The two half-flow warps at the head of ``FrameInterpolate.__call__``
+    (qpwcnet/core/non_layers.py:303-311): call with ``(prv, nxt, flo_01, flo_10)``; returns
+    ``concat([warp((prv, 0.5*flo_10)), warp((nxt, 0.5*flo_01))], channel axis)`` -- the reference's
+    ``[prv_w, nxt_w]`` -- from one kernel launch, with the 0.5 scaling fused."""
+
+    def __init__(self, warp_mode="tfa", flow_scale=0.5, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.warp_mode = warp_mode
+        self.flow_scale = float(flow_scale)
+
+    def __call__(self, inputs):
+        return _impl.half_flow_warps(inputs, self.warp_mode, self.data_format, self.flow_scale)

@@ -14,6 +14,8 @@ namespace qpwc {
 // kernels (qpwc_warp.cu, qpwc_corr_direct.cu, qpwc_corr_tiled.cu)
 int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+int launch_warp_fwd_ex(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
+int launch_warp_bwd_ex(const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
 int launch_corr_fwd_direct(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t);
 int launch_corr_bwd_direct(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
 // returns QPWC_ERR_UNSUPPORTED (without setting an error) when the shape is outside its domain
@@ -228,6 +230,57 @@ int qpwc_warp_bwd(const float* img, const float* flow, const float* g_out, float
   }
   QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "g_out", g_out)); QPWC_TRY(check_ptr(fn, "g_img", g_img));
   return launch_warp_bwd(img, flow, g_out, g_img, g_flow, B, H, W, C, mode, (cudaStream_t)stream);
+}
+
+static int check_warp_stride(const char* fn, const char* what, long long stride, long long need) {
+  if (stride < need) return set_error(QPWC_ERR_INVALID, "%s: %s %lld < %lld", fn, what, stride, need);
+  return QPWC_OK;
+}
+
+int qpwc_warp_fwd_ex(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                     int mode, float flow_scale, long long out_pixel_stride, void* stream) {
+  const char* fn = "qpwc_warp_fwd_ex";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_warp_stride(fn, "out_pixel_stride", out_pixel_stride, C));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
+  if (reinterpret_cast<uintptr_t>(flow) % 8) return set_error(QPWC_ERR_INVALID, "%s: flow must be 8-byte aligned", fn);
+  return launch_warp_fwd_ex(img, flow, nullptr, nullptr, out, B, H, W, C, mode, flow_scale, out_pixel_stride, (cudaStream_t)stream);
+}
+
+int qpwc_warp_pair_fwd(const float* img_a, const float* flow_a, const float* img_b, const float* flow_b,
+                       float* out, int B, int H, int W, int C, int mode, float flow_scale,
+                       long long out_pixel_stride, void* stream) {
+  const char* fn = "qpwc_warp_pair_fwd";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_warp_stride(fn, "out_pixel_stride", out_pixel_stride, 2LL * C));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "img_a", img_a)); QPWC_TRY(check_ptr(fn, "flow_a", flow_a));
+  QPWC_TRY(check_ptr(fn, "img_b", img_b)); QPWC_TRY(check_ptr(fn, "flow_b", flow_b)); QPWC_TRY(check_ptr(fn, "out", out));
+  if (reinterpret_cast<uintptr_t>(flow_a) % 8 || reinterpret_cast<uintptr_t>(flow_b) % 8)
+    return set_error(QPWC_ERR_INVALID, "%s: flows must be 8-byte aligned", fn);
+  return launch_warp_fwd_ex(img_a, flow_a, img_b, flow_b, out, B, H, W, C, mode, flow_scale, out_pixel_stride, (cudaStream_t)stream);
+}
+
+int qpwc_warp_bwd_ex(const float* img, const float* flow, const float* g_out, float* g_img,
+                     float* g_flow, int B, int H, int W, int C, int mode, float flow_scale,
+                     long long g_out_pixel_stride, void* stream) {
+  const char* fn = "qpwc_warp_bwd_ex";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_warp_stride(fn, "g_out_pixel_stride", g_out_pixel_stride, C));
+  if (B == 0 || H == 0 || W == 0) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "g_flow", g_flow));
+  if (reinterpret_cast<uintptr_t>(flow) % 8 || reinterpret_cast<uintptr_t>(g_flow) % 8)
+    return set_error(QPWC_ERR_INVALID, "%s: flow and g_flow must be 8-byte aligned", fn);
+  if (C == 0) {
+    const cudaError_t e = cudaMemsetAsync(g_flow, 0, sizeof(float) * 2 * (size_t)B * H * W, (cudaStream_t)stream);
+    return e == cudaSuccess ? QPWC_OK : set_error(QPWC_ERR_CUDA, "%s: memset: %s", fn, cudaGetErrorString(e));
+  }
+  QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "g_out", g_out)); QPWC_TRY(check_ptr(fn, "g_img", g_img));
+  return launch_warp_bwd_ex(img, flow, g_out, g_img, g_flow, B, H, W, C, mode, flow_scale, g_out_pixel_stride, (cudaStream_t)stream);
 }
 
 int qpwc_warp_corr_fwd(const float* prv, const float* nxt, const float* flow, float* out, int B,

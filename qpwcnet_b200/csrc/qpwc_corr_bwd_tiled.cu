@@ -7,7 +7,7 @@
 //
 // Both are the same banded product  R[p,c] = sum_e Gs[x,e] * X[x,c],  x = p + e (per displacement
 // row), once the gradient slice is laid out per SOURCE pixel x ("skewed" for g_prv, as stored for
-// g_nxt), so one kernel serves both (blockIdx.z & 1 selects the gradient).
+// g_nxt), so one kernel template serves both (instantiated per gradient).
 //
 // Decomposition: a CTA owns 4 rows x 64 pixels x 32 channels of one gradient; thread (row, g, h)
 // owns 8 consecutive pixels x 8 channels = 32 fp32x2 accumulators.  It walks the nine displacement
@@ -67,6 +67,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+template <int WHICH>  // 0 = g_prv, 1 = g_nxt
 __global__ void __launch_bounds__(bwdcfg::NTHREADS, 2)
 corr_bwd_tiled_kernel(const float* __restrict__ prv, const float* __restrict__ nxt,
                       const float* __restrict__ out, const float* __restrict__ g_out,
@@ -77,7 +78,8 @@ corr_bwd_tiled_kernel(const float* __restrict__ prv, const float* __restrict__ n
   const int tid = threadIdx.x;
   const int h = tid % NH, g = (tid / NH) % NG, r = tid / (NH * NG);  // warp = row r, lane = (g, h)
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-  const int cb = blockIdx.y % ncb, which = blockIdx.y / ncb;          // which: 0 = g_prv, 1 = g_nxt
+  const int cb = blockIdx.y;
+  constexpr int which = WHICH;
   const int b = blockIdx.z;
   const int i0 = ty * TH, j0 = tx * TW, c0 = cb * CB;
   const float* X = which == 0 ? nxt : prv;
@@ -93,8 +95,8 @@ corr_bwd_tiled_kernel(const float* __restrict__ prv, const float* __restrict__ n
   //      .x = global element offset relative to (row0 of the step, column 0 of the slice, channel
   //      0 of the slice), .y = Gs byte offset | rr << 16 | px << 24.  Padding elements (n >= nel)
   //      re-read element 0 and store into a dummy word.
-  const int npx = which == 0 ? TW : XW;
-  const int nel = TH * npx * Q;
+  constexpr int npx = which == 0 ? TW : XW;
+  constexpr int nel = TH * npx * Q;
 #pragma unroll 1
   for (int k = 0; k < NK; ++k) {
     const int n = tid + k * NTHREADS;
@@ -174,8 +176,7 @@ corr_bwd_tiled_kernel(const float* __restrict__ prv, const float* __restrict__ n
 #pragma unroll
     for (int c = 0; c < CHT / 2; ++c) acc[p][c] = make_float2(0.f, 0.f);
 
-  // prologue: ring rows 0 .. TH-1 and the slice of step 0
-  __syncthreads();  // table complete
+  // prologue: ring rows 0 .. TH-1 and the slice of step 0 (each thread reads only its own table entries)
   for (int n = 0; n < TH; ++n) issue_xrow(n);
   cp_async_commit();
   fetch_gs(0);
@@ -258,19 +259,20 @@ int launch_corr_bwd_tiled(const float* prv, const float* nxt, const float* out, 
   const char* var = getenv("QPWC_CORR_BWD_VARIANT");  // dev/tests: "direct" forces the untiled kernels
   if (var && var[0] == 'd') return QPWC_ERR_UNSUPPORTED;
   const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH), ncb = cdiv(C, CB);
-  if ((long long)ncb * 2 > 65535 || B > 65535) return QPWC_ERR_UNSUPPORTED;
-  auto k = corr_bwd_tiled_kernel;
+  if (ncb > 65535 || B > 65535) return QPWC_ERR_UNSUPPORTED;
 #ifndef QPWC_EMU
   static unsigned attr_done = 0;  // one bit per device (the attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_done >> (dev & 31) & 1u)) {
-    const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_bwd_tiled: smem attribute (%d B): %s", SMEM_BYTES, cudaGetErrorString(e));
     attr_done |= 1u << (dev & 31);
   }
-  const dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)(ncb * 2), (unsigned)B);
-  k<<<grid, NTHREADS, SMEM_BYTES, stream>>>(prv, nxt, out, g_out, g_prv, g_nxt, H, W, C, slope, ops, tiles_x, ncb);
+  const dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)ncb, (unsigned)B);
+  corr_bwd_tiled_kernel<0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(prv, nxt, out, g_out, g_prv, g_nxt, H, W, C, slope, ops, tiles_x, ncb);
+  corr_bwd_tiled_kernel<1><<<grid, NTHREADS, SMEM_BYTES, stream>>>(prv, nxt, out, g_out, g_prv, g_nxt, H, W, C, slope, ops, tiles_x, ncb);
   return check_launch("corr_bwd_tiled");
 #else
   return QPWC_ERR_UNSUPPORTED;

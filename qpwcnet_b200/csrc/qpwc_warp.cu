@@ -59,20 +59,32 @@ template <> __device__ __forceinline__ void vatomic_add<1>(float* p, const float
 // grid = (ceil(W*CV / 256), H, B): row and batch come from the block index, so the only index
 // arithmetic per thread is one 32-bit divide by CV (the first version decoded a 64-bit linear index
 // with three 64-bit divisions per thread and was instruction-bound: ncu 207 instr/thread).
+//
+// Extended form (FrameInterpolate, qpwcnet/core/non_layers.py:303-311): the flow is multiplied by
+// `scale` first (0.5 * flo; one rounded multiply, exactly the reference's op), the output pixel
+// stride `ops` may exceed C (channel slice of a concat buffer), and batch entries z >= bsplit take
+// a second (image, flow) pair and write C channels further -- two warps in one launch.
 template <int MODE, int V>
 __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__ img,
                                                        const float* __restrict__ flow,
-                                                       float* __restrict__ out, int H, int W, int C) {
+                                                       const float* __restrict__ img2,
+                                                       const float* __restrict__ flow2,
+                                                       float* __restrict__ out, int H, int W, int C,
+                                                       int bsplit, float scale, long long ops) {
   const int CV = C / V;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // j * CV + cv
   if (idx >= W * CV) return;
   const int j = idx / CV, cv = idx - j * CV;
   const int i = blockIdx.y;
-  const size_t row = (size_t)blockIdx.z * H + i;           // b*H + i
+  const bool second = (int)blockIdx.z >= bsplit;
+  const int b = second ? (int)blockIdx.z - bsplit : (int)blockIdx.z;
+  if (second) { img = img2; flow = flow2; }
+  const size_t row = (size_t)b * H + i;                    // b*H + i
   const size_t pix = row * W + j;
-  const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);  // ch0 = x, ch1 = y
+  float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);  // ch0 = x, ch1 = y
+  f.x = __fmul_rn(scale, f.x); f.y = __fmul_rn(scale, f.y);       // exact for scale == 1
   const Taps t = make_taps<MODE>(i, j, f.x, f.y, H, W);
-  const float* base = img + (size_t)blockIdx.z * H * W * C + (size_t)cv * V;
+  const float* base = img + (size_t)b * H * W * C + (size_t)cv * V;
   float v00[V], v01[V], v10[V], v11[V], o[V];
   vload<V>(base + (size_t)t.o00 * C, v00);
   vload<V>(base + (size_t)t.o01 * C, v01);
@@ -80,7 +92,7 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
   vload<V>(base + (size_t)t.o11 * C, v11);
 #pragma unroll
   for (int k = 0; k < V; ++k) o[k] = blend<MODE>(t, v00[k], v01[k], v10[k], v11[k]);
-  vstore<V>(out + pix * C + (size_t)cv * V, o);
+  vstore<V>(out + pix * (size_t)ops + (second ? C : 0) + (size_t)cv * V, o);
 }
 
 // ------------------------------------------------------------------------------------------ bwd
@@ -92,7 +104,7 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ g_out,
                                                        float* __restrict__ g_img,
                                                        float* __restrict__ g_flow, int H, int W, int C,
-                                                       int G) {
+                                                       int G, float scale, long long gops) {
   const int CV = C / V;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);           // lane inside the group
@@ -105,7 +117,8 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__
   float gx = 0.f, gy = 0.f;
   bool px = true, py = true;
   if (live) {
-    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);
+    float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);
+    f.x = __fmul_rn(scale, f.x); f.y = __fmul_rn(scale, f.y);  // the flow the forward pass sampled with
     Taps t;
     if (MODE == QPWC_MODE_TF) t = taps_tf(i, j, f.x, f.y, H, W);
     else t = taps_tfa(i, j, f.x, f.y, H, W, &px, &py);
@@ -126,7 +139,7 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__
       vload<V>(img + boff + (size_t)t.o01 * C + co, v01);
       vload<V>(img + boff + (size_t)t.o10 * C + co, v10);
       vload<V>(img + boff + (size_t)t.o11 * C + co, v11);
-      vload<V>(g_out + pix * C + co, g);
+      vload<V>(g_out + pix * (size_t)gops + co, g);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         if (MODE == QPWC_MODE_TF) {
@@ -178,7 +191,9 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__
     gx += __shfl_xor_sync(0xffffffffu, gx, o);
     gy += __shfl_xor_sync(0xffffffffu, gy, o);
   }
-  if (live && gl == 0) reinterpret_cast<float2*>(g_flow)[pix] = make_float2(px ? gx : 0.f, py ? gy : 0.f);
+  // chain rule through scale * flow: one more rounded multiply, as TF's gradient of the Mul
+  if (live && gl == 0)
+    reinterpret_cast<float2*>(g_flow)[pix] = make_float2(px ? __fmul_rn(scale, gx) : 0.f, py ? __fmul_rn(scale, gy) : 0.f);
 }
 
 // ------------------------------------------------------------------------------------ launchers
@@ -193,40 +208,57 @@ static int pick_vec(int C, const void* a, const void* b, const void* c = nullptr
 }
 
 template <int MODE, int V>
-static void run_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+static void run_warp_fwd(const float* img, const float* flow, const float* img2, const float* flow2,
+                         float* out, int B, int H, int W, int C, float scale, long long ops,
                          cudaStream_t stream) {
   const int block = 256;
   const int CV = C / V;
   auto k = warp_fwd_kernel<MODE, V>;
+  if (img2) {  // pair: grid.z = 2B (B <= 32767 checked by the caller)
+    const dim3 grid((unsigned)cdiv(W * CV, block), (unsigned)H, (unsigned)(2 * B));
+    QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, img2, flow2, out, H, W, C, B, scale, ops);
+    return;
+  }
   // gridDim.y/z are limited to 65535: chunk the batch (and refuse absurd heights upstream)
   for (int b0 = 0; b0 < B; b0 += 65535) {
     const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
     const dim3 grid((unsigned)cdiv(W * CV, block), (unsigned)H, (unsigned)nb);
     const size_t off = (size_t)b0 * H * W;
-    QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + off * 2, out + off * C, H, W, C);
+    QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + off * 2, img2, flow2, out + off * ops, H, W, C,
+                nb, scale, ops);
   }
 }
 
-int launch_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
-                    int mode, cudaStream_t stream) {
-  const int V = pick_vec(C, img, out);
+// img2/flow2 != nullptr: two warps in one launch, the second writing channels [C, 2C) of each pixel
+int launch_warp_fwd_ex(const float* img, const float* flow, const float* img2, const float* flow2,
+                       float* out, int B, int H, int W, int C, int mode, float scale, long long ops,
+                       cudaStream_t stream) {
+  int V = pick_vec(C, img, out, img2);
+  while (V > 1 && ops % V) V >>= 1;
   if ((long long)B * H * W * C == 0) return QPWC_OK;
   if (H > 65535 || (long long)W * (C / V) >= (1LL << 31)) return set_error(QPWC_ERR_UNSUPPORTED, "warp_fwd: H > 65535 or W*C too large");
+  if (img2 && B > 32767) return set_error(QPWC_ERR_UNSUPPORTED, "warp_pair_fwd: B > 32767");
   if (mode == QPWC_MODE_TF) {
-    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, out, B, H, W, C, stream);
-    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, out, B, H, W, C, stream);
-    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, out, B, H, W, C, stream);
+    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
+    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
   } else {
-    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, out, B, H, W, C, stream);
-    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, out, B, H, W, C, stream);
-    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, out, B, H, W, C, stream);
+    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
+    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
   }
   return check_launch("warp_fwd");
 }
 
+int launch_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                    int mode, cudaStream_t stream) {
+  return launch_warp_fwd_ex(img, flow, nullptr, nullptr, out, B, H, W, C, mode, 1.f, C, stream);
+}
+
 template <int MODE, int V>
 static void run_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
-                         float* g_flow, int B, int H, int W, int C, cudaStream_t stream) {
+                         float* g_flow, int B, int H, int W, int C, float scale, long long gops,
+                         cudaStream_t stream) {
   const int CV = C / V;
   int G = 1;
   while (G < CV && G < 32) G <<= 1;
@@ -237,29 +269,36 @@ static void run_warp_bwd(const float* img, const float* flow, const float* g_out
     const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
     const dim3 grid((unsigned)cdiv(W, groups_per_block), (unsigned)H, (unsigned)nb);
     const size_t off = (size_t)b0 * H * W;
-    QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + off * 2, g_out + off * C, g_img + off * C,
-                g_flow + off * 2, H, W, C, G);
+    QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + off * 2, g_out + off * gops, g_img + off * C,
+                g_flow + off * 2, H, W, C, G, scale, gops);
   }
 }
 
-int launch_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
-                    float* g_flow, int B, int H, int W, int C, int mode, cudaStream_t stream) {
+int launch_warp_bwd_ex(const float* img, const float* flow, const float* g_out, float* g_img,
+                       float* g_flow, int B, int H, int W, int C, int mode, float scale,
+                       long long gops, cudaStream_t stream) {
   const long long npix = (long long)B * H * W;
   if (npix == 0) return QPWC_OK;
   cudaError_t e = cudaMemsetAsync(g_img, 0, sizeof(float) * (size_t)npix * C, stream);
   if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "warp_bwd: memset g_img: %s", cudaGetErrorString(e));
-  const int V = pick_vec(C, img, g_out, g_img);
+  int V = pick_vec(C, img, g_out, g_img);
+  while (V > 1 && gops % V) V >>= 1;
   if (H > 65535) return set_error(QPWC_ERR_UNSUPPORTED, "warp_bwd: H > 65535");
   if (mode == QPWC_MODE_TF) {
-    if (V == 4) run_warp_bwd<QPWC_MODE_TF, 4>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
-    else if (V == 2) run_warp_bwd<QPWC_MODE_TF, 2>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
-    else run_warp_bwd<QPWC_MODE_TF, 1>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
+    if (V == 4) run_warp_bwd<QPWC_MODE_TF, 4>(img, flow, g_out, g_img, g_flow, B, H, W, C, scale, gops, stream);
+    else if (V == 2) run_warp_bwd<QPWC_MODE_TF, 2>(img, flow, g_out, g_img, g_flow, B, H, W, C, scale, gops, stream);
+    else run_warp_bwd<QPWC_MODE_TF, 1>(img, flow, g_out, g_img, g_flow, B, H, W, C, scale, gops, stream);
   } else {
-    if (V == 4) run_warp_bwd<QPWC_MODE_TFA, 4>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
-    else if (V == 2) run_warp_bwd<QPWC_MODE_TFA, 2>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
-    else run_warp_bwd<QPWC_MODE_TFA, 1>(img, flow, g_out, g_img, g_flow, B, H, W, C, stream);
+    if (V == 4) run_warp_bwd<QPWC_MODE_TFA, 4>(img, flow, g_out, g_img, g_flow, B, H, W, C, scale, gops, stream);
+    else if (V == 2) run_warp_bwd<QPWC_MODE_TFA, 2>(img, flow, g_out, g_img, g_flow, B, H, W, C, scale, gops, stream);
+    else run_warp_bwd<QPWC_MODE_TFA, 1>(img, flow, g_out, g_img, g_flow, B, H, W, C, scale, gops, stream);
   }
   return check_launch("warp_bwd");
+}
+
+int launch_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
+                    float* g_flow, int B, int H, int W, int C, int mode, cudaStream_t stream) {
+  return launch_warp_bwd_ex(img, flow, g_out, g_img, g_flow, B, H, W, C, mode, 1.f, C, stream);
 }
 
 }  // namespace qpwc

@@ -140,6 +140,40 @@ def _warp_bwd(img, flow, g_out, mode):
     return g_img, g_flow
 
 
+def _warp_fwd_scaled(img, flow, mode, scale, out=None, out_view=None):
+    """warp(img, scale * flow) -> out (dense, or `out_view`: a channel slice [.., o:o+C] of a wider
+    contiguous NHWC buffer, written in place)."""
+    B, H, W, C = img.shape
+    if out_view is None:
+        out = torch.empty_like(img) if out is None else out
+        target, stride = out, C
+    else:
+        target, stride = out_view, out_view.stride(2)
+    vi, vf = _views(img, flow)
+    with _on_device(img.device):
+        check(lib().qpwc_warp_fwd_ex(vi.ptr, vf.ptr, target.data_ptr(), B, H, W, C, mode, float(scale),
+                                     stride, _stream_ptr(img.device)))
+    return target
+
+
+def _warp_bwd_scaled(img, flow, g_out, mode, scale):
+    """g_out may be a channel slice of a wider contiguous NHWC gradient buffer."""
+    B, H, W, C = img.shape
+    g_img = torch.empty_like(img)
+    g_flow = torch.empty_like(flow)
+    vi, vf, vgi, vgf = _views(img, flow, g_img, g_flow)
+    with _on_device(img.device):
+        check(lib().qpwc_warp_bwd_ex(vi.ptr, vf.ptr, g_out.data_ptr(), vgi.ptr, vgf.ptr, B, H, W, C, mode,
+                                     float(scale), g_out.stride(2), _stream_ptr(img.device)))
+    return g_img, g_flow
+
+
+def _slice_ok(v, C):
+    """v: (B,H,W,C) view whose pixels are C contiguous floats at a constant pixel stride."""
+    return (v.stride(3) == 1 and v.stride(1) == v.stride(2) * v.shape[2]
+            and v.stride(0) == v.stride(1) * v.shape[1] and v.stride(2) >= C)
+
+
 def _warp_corr_fwd(prv, nxt, flow, mode, d, slope, out=None, out_stride=None):
     B, H, W, C = prv.shape
     D = (2 * d + 1) ** 2
@@ -211,6 +245,56 @@ class _Warp(torch.autograd.Function):
         return g_img, g_flow, None
 
 
+class _WarpScaled(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, flow, mode, scale):
+        out = _warp_fwd_scaled(img, flow, mode, scale)
+        ctx.save_for_backward(img, flow)
+        ctx.cfg = (mode, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        img, flow = ctx.saved_tensors
+        mode, scale = ctx.cfg
+        if not _slice_ok(g_out, img.shape[3]):
+            g_out = g_out.contiguous()
+        g_img, g_flow = _warp_bwd_scaled(img, flow, g_out, mode, scale)
+        return g_img, g_flow, None, None
+
+
+class _WarpPair(torch.autograd.Function):
+    """FrameInterpolate's two half-flow warps as one forward launch into one (B,H,W,2C) buffer."""
+
+    @staticmethod
+    def forward(ctx, img_a, flow_a, img_b, flow_b, mode, scale):
+        B, H, W, C = img_a.shape
+        out = torch.empty((B, H, W, 2 * C), dtype=torch.float32, device=img_a.device)
+        _warp_pair_fwd(out, img_a, flow_a, img_b, flow_b, mode, scale)
+        ctx.save_for_backward(img_a, flow_a, img_b, flow_b)
+        ctx.cfg = (mode, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        img_a, flow_a, img_b, flow_b = ctx.saved_tensors
+        mode, scale = ctx.cfg
+        C = img_a.shape[3]
+        g_out = g_out.contiguous()
+        ga, gfa = _warp_bwd_scaled(img_a, flow_a, g_out[..., :C], mode, scale)   # slices, no copy
+        gb, gfb = _warp_bwd_scaled(img_b, flow_b, g_out[..., C:], mode, scale)
+        return ga, gfa, gb, gfb, None, None
+
+
+def _warp_pair_fwd(out, img_a, flow_a, img_b, flow_b, mode, scale):
+    B, H, W, C = img_a.shape
+    va, vfa, vb, vfb = _views(img_a, flow_a, img_b, flow_b)
+    with _on_device(img_a.device):
+        check(lib().qpwc_warp_pair_fwd(va.ptr, vfa.ptr, vb.ptr, vfb.ptr, out.data_ptr(), B, H, W, C, mode,
+                                       float(scale), out.stride(2), _stream_ptr(img_a.device)))
+    return out
+
+
 class _WarpCostVolume(torch.autograd.Function):
     @staticmethod
     def forward(ctx, prv, nxt, flow, mode, d, slope):
@@ -239,9 +323,10 @@ def cost_volume(prv, nxt, search_range: int = 4, leaky_slope: float = 0.1):
     return _CostVolume.apply(prv, nxt, int(search_range), float(leaky_slope))
 
 
-def warp(img, flow, mode="tfa"):
-    """Bilinear backward warp: ``out[b,i,j] = img[b, i+flow[...,1], j+flow[...,0]]``; ``mode`` picks
-    the reference's border rule ('tf' = Warp/tf_warp, 'tfa' = WarpV2)."""
+def warp(img, flow, mode="tfa", flow_scale: float = 1.0):
+    """Bilinear backward warp: ``out[b,i,j] = img[b, i+s*flow[...,1], j+s*flow[...,0]]``; ``mode``
+    picks the reference's border rule ('tf' = Warp/tf_warp, 'tfa' = WarpV2).  ``flow_scale`` s != 1
+    fuses the reference's ``warp((img, 0.5 * flo))`` (FrameInterpolate, non_layers.py:303-304)."""
     img = _prep(img, "img")
     flow = _prep(flow, "flow", last=2)
     if img.shape[:3] != flow.shape[:3] or img.device != flow.device:
@@ -250,9 +335,47 @@ def warp(img, flow, mode="tfa"):
     if m == 1 and (img.shape[1] < 2 or img.shape[2] < 2):
         raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
     _no_host_grad(img, flow)
+    if float(flow_scale) != 1.0:
+        if not img.is_cuda:
+            raise ValueError("warp(flow_scale != 1) needs CUDA tensors")
+        return _WarpScaled.apply(img, flow, m, float(flow_scale))
     if not img.is_cuda:
         return _warp_fwd(img, flow, m)
     return _Warp.apply(img, flow, m)
+
+
+def _pair_args(prv, nxt, flo_01, flo_10, mode):
+    prv, nxt = _prep(prv, "prv"), _prep(nxt, "nxt")
+    flo_01, flo_10 = _prep(flo_01, "flo_01", last=2), _prep(flo_10, "flo_10", last=2)
+    _same(prv, nxt, "half_flow_warps(prv, nxt)")
+    for f in (flo_01, flo_10):
+        if f.shape[:3] != prv.shape[:3] or f.device != prv.device:
+            raise ValueError(f"half_flow_warps: flow {tuple(f.shape)}@{f.device} vs features {tuple(prv.shape)}@{prv.device}")
+    if not prv.is_cuda:
+        raise ValueError("half_flow_warps needs CUDA tensors")
+    m = _mode(mode)
+    if m == 1 and (prv.shape[1] < 2 or prv.shape[2] < 2):
+        raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
+    return prv, nxt, flo_01, flo_10, m
+
+
+def half_flow_warps(prv, nxt, flo_01, flo_10, mode="tfa", flow_scale: float = 0.5):
+    """FrameInterpolate's warp pair (qpwcnet/core/non_layers.py:303-311) in one launch: returns the
+    (B,H,W,2C) tensor ``concat([warp(prv, s*flo_10), warp(nxt, s*flo_01)], -1)`` -- the reference's
+    ``[prv_w, nxt_w]`` -- without materialising ``s*flo``.  Differentiable."""
+    prv, nxt, flo_01, flo_10, m = _pair_args(prv, nxt, flo_01, flo_10, mode)
+    return _WarpPair.apply(prv, flo_10, nxt, flo_01, m, float(flow_scale))
+
+
+def half_flow_warps_into(out, prv, nxt, flo_01, flo_10, mode="tfa", flow_scale: float = 0.5):
+    """Inference-only: the pair lands in channels [0, 2C) of every pixel of a caller-owned
+    contiguous (B,H,W,S >= 2C) buffer (the concat input of FrameInterpolate's convolutions)."""
+    prv, nxt, flo_01, flo_10, m = _pair_args(prv, nxt, flo_01, flo_10, mode)
+    C = prv.shape[3]
+    if (out.dim() != 4 or out.shape[:3] != prv.shape[:3] or out.shape[3] < 2 * C or out.dtype != torch.float32
+            or out.device != prv.device or not out.is_contiguous()):
+        raise ValueError(f"half_flow_warps_into: out must be a contiguous float32 (B,H,W,S>=2C) tensor on {prv.device}")
+    return _warp_pair_fwd(out, prv, flo_10, nxt, flo_01, m, float(flow_scale))
 
 
 def warp_cost_volume(prv, nxt, flow, mode="tfa", search_range: int = 4, leaky_slope: float = 0.1):

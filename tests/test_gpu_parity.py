@@ -92,7 +92,10 @@ def test_cost_volume_forward_rowpair_variant(B, H, W, C, d, monkeypatch):
 
 @pytest.mark.parametrize("B,H,W,C,d", [(4, 32, 64, 3, 4), (1, 28, 64, 256, 4), (1, 40, 72, 32, 4),
                                        (1, 17, 19, 16, 4), (1, 9, 9, 5, 4), (1, 12, 13, 6, 2),
-                                       (1, 20, 30, 32, 8)])
+                                       (1, 20, 30, 32, 8),
+                                       # tiled backward (qpwc_corr_bwd_tiled.cu): interior tiles (no bounds
+                                       # checks), ragged 4x64 tiles, channel tails of the 32-channel blocks
+                                       (2, 24, 200, 8, 4), (1, 31, 150, 36, 4), (1, 6, 70, 68, 4), (1, 3, 5, 4, 4)])
 def test_cost_volume_backward(B, H, W, C, d):
     r = rng(7 + C)
     prv = r.standard_normal((B, H, W, C)).astype(np.float32)
@@ -108,6 +111,20 @@ def test_cost_volume_backward(B, H, W, C, d):
     assert_rel(host(gp), rp)
     assert_rel(host(gn), rn)
     assert np.array_equal(host(out) > 0, o64 > 0) or np.abs(o64[(host(out) > 0) != (o64 > 0)]).max() < 1e-6
+
+
+def test_cost_volume_backward_tiled_matches_direct(monkeypatch):
+    """The tiled and the direct backward kernels are two summation orders of the same sums."""
+    r = rng(99)
+    B, H, W, C = 2, 21, 133, 40
+    prv, nxt = dev(r.standard_normal((B, H, W, C))), dev(r.standard_normal((B, H, W, C)))
+    out = ops.cost_volume(prv, nxt, 4)
+    g = dev(r.standard_normal((B, H, W, 81)))
+    gp, gn = ops._corr_bwd(prv, nxt, out, g, 4, 0.1)
+    monkeypatch.setenv("QPWC_CORR_BWD_VARIANT", "direct")
+    gp2, gn2 = ops._corr_bwd(prv, nxt, out, g, 4, 0.1)
+    for a, b in ((gp, gp2), (gn, gn2)):
+        assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())
 
 
 WARP_SHAPES = [(4, 32, 64, 3), (2, 28, 64, 256), (1, 56, 128, 128), (1, 33, 35, 32), (1, 9, 11, 2),
@@ -175,6 +192,46 @@ def test_fused_warp_cost_volume_forward_backward(mode, B, H, W, C, d):
     assert_rel(host(gp), rp)
     assert_rel(host(gn), rn, floor=1e-3)
     assert_rel(host(gf), rf, floor=1e-3)
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 28, 256), (1, 33, 35, 32), (1, 9, 11, 3), (2, 8, 8, 6)])
+def test_half_flow_warps_frame_interpolate(mode, B, H, W, C):
+    """FrameInterpolate's pair (non_layers.py:303-311): warp((nxt, 0.5*flo_01)), warp((prv,
+    0.5*flo_10)) from one launch with the scaling fused.  0.5*flo is an exact fp32 product, so the
+    forward must be bit-identical to the oracle warp on the pre-scaled flow; gradients: the flow
+    gradient is 0.5 x the gradient of the plain warp."""
+    r = rng(400 + C)
+    prv, nxt = r.random((B, H, W, C)).astype(np.float32), r.random((B, H, W, C)).astype(np.float32)
+    f01 = (r.standard_normal((B, H, W, 2)) * 4).astype(np.float32)
+    f10 = (r.standard_normal((B, H, W, 2)) * 4).astype(np.float32)
+    tp, tn, t01, t10 = (dev(a).requires_grad_() for a in (prv, nxt, f01, f10))
+    out = ops.half_flow_warps(tp, tn, t01, t10, mode)
+    assert tuple(out.shape) == (B, H, W, 2 * C)
+    ref_p = oracle.warp(prv, np.float32(0.5) * f10, mode)
+    ref_n = oracle.warp(nxt, np.float32(0.5) * f01, mode)
+    np.testing.assert_array_equal(host(out[..., :C]), ref_p)
+    np.testing.assert_array_equal(host(out[..., C:]), ref_n)
+    # the functor and the strided `_into` form (concat buffer) agree bit for bit
+    from qpwcnet_b200.core import non_layers
+    f = non_layers.HalfFlowWarps(warp_mode=mode, data_format="channels_last")
+    np.testing.assert_array_equal(host(f((tp.detach(), tn.detach(), t01.detach(), t10.detach()))), host(out))
+    buf = torch.full((B, H, W, 2 * C + 4 + 3), float("nan"), device=DEV)
+    ops.half_flow_warps_into(buf, tp.detach(), tn.detach(), t01.detach(), t10.detach(), mode)
+    np.testing.assert_array_equal(host(buf[..., :2 * C]), host(out))
+    assert torch.isnan(buf[..., 2 * C:]).all()
+    # single scaled warp == warp on the pre-scaled flow (bit exact), incl. a scale that rounds
+    w = ops.warp(tn.detach(), t01.detach(), mode, flow_scale=0.3)
+    np.testing.assert_array_equal(host(w), oracle.warp(nxt, np.float32(0.3) * f01, mode))
+    # gradients
+    g = r.standard_normal((B, H, W, 2 * C)).astype(np.float32)
+    gp, gn, g01, g10 = torch.autograd.grad(out, (tp, tn, t01, t10), dev(g))
+    for img, flo, gs, gi_gpu, gf_gpu in ((prv, f10, g[..., :C], gp, g10), (nxt, f01, g[..., C:], gn, g01)):
+        half = (np.float32(0.5) * flo)
+        gi64, gf64 = oracle.warp_bwd(img.astype(np.float64), half.astype(np.float64), gs.astype(np.float64), mode)
+        gi32, gf32 = oracle.warp_bwd(img, half, np.ascontiguousarray(gs), mode)
+        assert_as_accurate(host(gi_gpu), gi32, gi64)
+        assert_as_accurate(host(gf_gpu), np.float32(0.5) * gf32, 0.5 * gf64, floor=1e-6 * max(1.0, C / 8))
 
 
 def test_golden_fixtures():
