@@ -66,10 +66,12 @@ struct TiledCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
   static constexpr int FULL_COUNT = 1 + (WARP ? NPROD / 32 : 0);
   static constexpr int EMPTY_COUNT = NCONS / 32;
-  // register split (setmaxnreg), sum <= 65536:  scalar TH=6: 384*152 + 128*56;  packed TH=4 plain:
-  // 256*232 + 128*32;  fused (scalar consumers, TH=4): 256*152 + 256*104
-  static constexpr int REG_CONS = PACKED_ ? 232 : 152;
-  static constexpr int REG_PROD = WARP_ ? 104 : (PACKED_ ? 32 : 56);
+  // register split (setmaxnreg), sum <= 65536:  scalar TH=4 plain: 256*200 + 128*56;  scalar TH=6:
+  // 384*152 + 128*56;  packed TH=4 plain:
+  // 256*232 + 128*32;  fused (scalar consumers, TH=4): 256*176 + 256*80
+  static constexpr int REG_CONS = PACKED_ ? 232 : (WARP_ ? 176 : (TH_ <= 4 ? 200 : 152));
+  static constexpr int REG_PROD = WARP_ ? 80 : (PACKED_ ? 32 : 56);
+  static constexpr int UB = 2;  // fused producer: units in flight per thread (8 independent 16-byte gathers)
   static_assert(!(WARP_ && (PACKED_ || TH_ > 4)), "fused variant: scalar consumers, TH <= 4");
   static_assert(TW % 8 == 0 && P_BYTES % 512 == 0 && N_BYTES % 512 == 0 && TH <= 14, "tile shape");
   static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536, "register budget");
@@ -224,7 +226,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           const float* nb = nxt + (size_t)b * H * W * C + (size_t)c * KC;
           unsigned char* ns = sb + Cfg::P_BYTES;
           const int NU = nprod_px * Cfg::NQ;
-          constexpr int UB = 4;  // units in flight per thread: 16 independent 16-byte gathers
+          constexpr int UB = Cfg::UB;
           for (int u0 = ptid; u0 < NU; u0 += NPROD * UB) {
             TapsEntry e[UB];
             float4 v00[UB], v01[UB], v10[UB], v11[UB];
@@ -556,7 +558,13 @@ int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow,
     const long long tiles4 = (long long)cdiv(W, 56) * cdiv(H, 4) * B * (d == 8 ? 4 : 1);
     if (tiles4 * 2 <= sm_count())
       return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
-    return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+    // default: scalar FFMA, 4-row tiles, 200 registers per consumer thread.  Measured on B200
+    // (tools/ab_corr.py): 178 vs 192 us at 224x512x32 B=8 against the packed channel-parity FFMA2
+    // variant (QPWC_CORR_VARIANT=packed) -- a 3-register FFMA sustains ~0.7 FMA/lane/clk with 81
+    // accumulators (tools/ubench/corr_loop_bench.cu), the packed loop 0.60 with 162.
+    if (var && var[0] == 'p')
+      return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+    return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
   }
   if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
   return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);

@@ -64,14 +64,14 @@ template <> __device__ __forceinline__ void vatomic_add<1>(float* p, const float
 // `scale` first (0.5 * flo; one rounded multiply, exactly the reference's op), the output pixel
 // stride `ops` may exceed C (channel slice of a concat buffer), and batch entries z >= bsplit take
 // a second (image, flow) pair and write C channels further -- two warps in one launch.
-template <int MODE, int V>
+template <int MODE, int V, int NV>  // NV channel vectors per thread (2: taps amortised over 32 bytes per tap)
 __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__ img,
                                                        const float* __restrict__ flow,
                                                        const float* __restrict__ img2,
                                                        const float* __restrict__ flow2,
                                                        float* __restrict__ out, int H, int W, int C,
                                                        int bsplit, float scale, long long ops) {
-  const int CV = C / V;
+  const int CV = C / (V * NV);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // j * CV + cv
   if (idx >= W * CV) return;
   const int j = idx / CV, cv = idx - j * CV;
@@ -84,15 +84,22 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
   float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);  // ch0 = x, ch1 = y
   f.x = __fmul_rn(scale, f.x); f.y = __fmul_rn(scale, f.y);       // exact for scale == 1
   const Taps t = make_taps<MODE>(i, j, f.x, f.y, H, W);
-  const float* base = img + (size_t)b * H * W * C + (size_t)cv * V;
-  float v00[V], v01[V], v10[V], v11[V], o[V];
-  vload<V>(base + (size_t)t.o00 * C, v00);
-  vload<V>(base + (size_t)t.o01 * C, v01);
-  vload<V>(base + (size_t)t.o10 * C, v10);
-  vload<V>(base + (size_t)t.o11 * C, v11);
+  const float* base = img + (size_t)b * H * W * C + (size_t)cv * (V * NV);
+  float v00[NV][V], v01[NV][V], v10[NV][V], v11[NV][V], o[NV][V];
 #pragma unroll
-  for (int k = 0; k < V; ++k) o[k] = blend<MODE>(t, v00[k], v01[k], v10[k], v11[k]);
-  vstore<V>(out + pix * (size_t)ops + (second ? C : 0) + (size_t)cv * V, o);
+  for (int n = 0; n < NV; ++n) {
+    vload<V>(base + (size_t)t.o00 * C + n * V, v00[n]);
+    vload<V>(base + (size_t)t.o01 * C + n * V, v01[n]);
+    vload<V>(base + (size_t)t.o10 * C + n * V, v10[n]);
+    vload<V>(base + (size_t)t.o11 * C + n * V, v11[n]);
+  }
+  float* dst = out + pix * (size_t)ops + (second ? C : 0) + (size_t)cv * (V * NV);
+#pragma unroll
+  for (int n = 0; n < NV; ++n) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[n][k] = blend<MODE>(t, v00[n][k], v01[n][k], v10[n][k], v11[n][k]);
+    vstore<V>(dst + n * V, o[n]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ bwd
@@ -207,13 +214,30 @@ static int pick_vec(int C, const void* a, const void* b, const void* c = nullptr
   return v;
 }
 
+template <int MODE, int V, int NV>
+static void run_warp_fwd_nv(const float* img, const float* flow, const float* img2, const float* flow2,
+                            float* out, int B, int H, int W, int C, float scale, long long ops,
+                            cudaStream_t stream);
+
 template <int MODE, int V>
 static void run_warp_fwd(const float* img, const float* flow, const float* img2, const float* flow2,
                          float* out, int B, int H, int W, int C, float scale, long long ops,
                          cudaStream_t stream) {
   const int block = 256;
-  const int CV = C / V;
-  auto k = warp_fwd_kernel<MODE, V>;
+  if (V == 4 && C % 8 == 0) {  // two 16-byte vectors per thread
+    run_warp_fwd_nv<MODE, V, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
+    return;
+  }
+  run_warp_fwd_nv<MODE, V, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
+}
+
+template <int MODE, int V, int NV>
+static void run_warp_fwd_nv(const float* img, const float* flow, const float* img2, const float* flow2,
+                            float* out, int B, int H, int W, int C, float scale, long long ops,
+                            cudaStream_t stream) {
+  const int block = 256;
+  const int CV = C / (V * NV);
+  auto k = warp_fwd_kernel<MODE, V, NV>;
   if (img2) {  // pair: grid.z = 2B (B <= 32767 checked by the caller)
     const dim3 grid((unsigned)cdiv(W * CV, block), (unsigned)H, (unsigned)(2 * B));
     QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, img2, flow2, out, H, W, C, B, scale, ops);

@@ -22,17 +22,17 @@ def main():
         prv = torch.randn((B, H, W, C), device=dev, generator=g)
         nxt = torch.randn((B, H, W, C), device=dev, generator=g)
         res = {}
-        for var in ("tiled", "rowpair"):
+        for var in ("packed", "rowpair", "default"):
             os.environ["QPWC_CORR_VARIANT"] = var
             out = torch.full((B, H, W, 81), float("nan"), device=dev)
             ops.cost_volume_into(out, prv, nxt, 4)
             torch.cuda.synchronize()
             t = timeit(lambda: ops.cost_volume_into(out, prv, nxt, 4), 15, flush)
             res[var] = (out.clone(), t)
-        a, b = res["tiled"][0], res["rowpair"][0]
+        a, b = res["default"][0], res["rowpair"][0]
         err = (a - b).abs().max().item() / a.abs().max().item()
         nan = int(torch.isnan(b).sum().item())
-        print(f"{H}x{W}x{C} B={B}: tiled {res['tiled'][1]*1e6:8.1f} us  rowpair {res['rowpair'][1]*1e6:8.1f} us  "
+        print(f"{H}x{W}x{C} B={B}: packed {res['packed'][1]*1e6:8.1f} us  rowpair {res['rowpair'][1]*1e6:8.1f} us  default(scalar) {res['default'][1]*1e6:8.1f} us  "
               f"rel diff {err:.2e}  nan {nan}", flush=True)
 
 

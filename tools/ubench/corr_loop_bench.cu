@@ -155,6 +155,66 @@ __global__ void __maxnreg__(NREG) kB(float* out, long long* cyc, int nchunks) {
   if (tid == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+
+// ---- KS: scalar FFMA, 81 accumulators, loop order (k, channel, m): the first-frame operand stays in
+//      the register-reuse cache across the 9 m's.  TH rows x 64 threads (TH = 4 or 6).
+template <int TH, int ORDER>
+__global__ void __launch_bounds__(TH * 64, 1) kS(float* out, long long* cyc, int nchunks) {
+  constexpr int NROW = TH + 8, P_BYTES = TH * PCOL * PXB, N_BYTES = NROW * NCOL * PXB, STAGE = P_BYTES + N_BYTES;
+  const int tid = threadIdx.x, ti = tid / NCOL, tc = tid % NCOL;
+  for (int e = tid; e < 2 * STAGE / 4; e += TH * 64) reinterpret_cast<float*>(smem)[e] = (float)(e % 13) * 0.01f;
+  __syncthreads();
+  uint32_t a_off[Q];
+#pragma unroll
+  for (int k = 0; k < Q; ++k) { int lp = min(max(tc - k, 0), PCOL - 1); a_off[k] = swz32((uint32_t)((ti * PCOL + lp) * PXB)); }
+  const uint32_t nb_off = P_BYTES + swz32((uint32_t)((ti * NCOL + tc) * PXB));
+  float acc[Q][Q];
+#pragma unroll
+  for (int m = 0; m < Q; ++m)
+#pragma unroll
+    for (int k = 0; k < Q; ++k) acc[m][k] = 0.f;
+  long long t0 = clock64();
+  for (int c = 0; c < nchunks; ++c) {
+    const unsigned char* sb = smem + (c & 1) * STAGE;
+#pragma unroll
+    for (int qd = 0; qd < 2; ++qd) {
+      const unsigned char* nbp = sb + (nb_off ^ (uint32_t)(qd << 4));
+      float4 bv[Q];
+#pragma unroll
+      for (int m = 0; m < Q; ++m) bv[m] = *reinterpret_cast<const float4*>(nbp + m * NCOL * PXB);
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
+        if (ORDER == 0) {
+#pragma unroll
+          for (int m = 0; m < Q; ++m) {
+            acc[m][k] = fmaf(a.x, bv[m].x, acc[m][k]); acc[m][k] = fmaf(a.y, bv[m].y, acc[m][k]);
+            acc[m][k] = fmaf(a.z, bv[m].z, acc[m][k]); acc[m][k] = fmaf(a.w, bv[m].w, acc[m][k]);
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < Q; ++m) acc[m][k] = fmaf(a.x, bv[m].x, acc[m][k]);
+#pragma unroll
+          for (int m = 0; m < Q; ++m) acc[m][k] = fmaf(a.y, bv[m].y, acc[m][k]);
+#pragma unroll
+          for (int m = 0; m < Q; ++m) acc[m][k] = fmaf(a.z, bv[m].z, acc[m][k]);
+#pragma unroll
+          for (int m = 0; m < Q; ++m) acc[m][k] = fmaf(a.w, bv[m].w, acc[m][k]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int m = 0; m < Q; ++m)
+#pragma unroll
+    for (int k = 0; k < Q; ++k) s += acc[m][k] * (1.f + m);
+  out[blockIdx.x * (TH * 64) + tid] = s;
+  if (tid == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 template <class K> static double run(K kern, int smem_bytes, float* out, long long* cyc, int nchunks, int nthr = 256) {
   long long h[148];
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -179,6 +239,16 @@ int main() {
   printf("KB 168 regs, no extra warps                      : %5.0f cycles/chunk\n", s0);
   const double b2 = run(kB<1, 232>, 2 * kb::STAGE, out, cyc, nchunks);
   printf("KB row-pair N x2ch  232: %5.0f cycles/chunk -> %.3f\n", b2, 256.0 * 162 * 8 / 128 / b2);
+  {
+    cudaFree(out); cudaMalloc(&out, sizeof(float) * 148 * 512);
+    const int st4 = 2 * (4 * PCOL * PXB + 12 * NCOL * PXB), st6 = 2 * (6 * PCOL * PXB + 14 * NCOL * PXB);
+    const double a4 = run(kS<4, 0>, st4, out, cyc, nchunks, 256), b4 = run(kS<4, 1>, st4, out, cyc, nchunks, 256);
+    const double a6 = run(kS<6, 0>, st6, out, cyc, nchunks, 384), b6 = run(kS<6, 1>, st6, out, cyc, nchunks, 384);
+    const double a8 = run(kS<8, 0>, 2 * (8 * PCOL * PXB + 16 * NCOL * PXB), out, cyc, nchunks, 512), b8 = run(kS<8, 1>, 2 * (8 * PCOL * PXB + 16 * NCOL * PXB), out, cyc, nchunks, 512);
+    printf("KS scalar TH=4 (8 warps): order m-inner/4ch %5.0f -> %.3f | order (k,c,m) %5.0f -> %.3f valid FMA/lane/clk\n", a4, 256.0 * 81 * 8 / 128 / a4, b4, 256.0 * 81 * 8 / 128 / b4);
+    printf("KS scalar TH=6 (12 warps): %5.0f -> %.3f | %5.0f -> %.3f\n", a6, 384.0 * 81 * 8 / 128 / a6, b6, 384.0 * 81 * 8 / 128 / b6);
+    printf("KS scalar TH=8 (16 warps): %5.0f -> %.3f | %5.0f -> %.3f\n", a8, 512.0 * 81 * 8 / 128 / a8, b8, 512.0 * 81 * 8 / 128 / b8);
+  }
   printf("%s %s\n", cudaGetErrorString(cudaGetLastError()), cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
 }
