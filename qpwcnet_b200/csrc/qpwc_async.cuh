@@ -55,6 +55,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Same wait for the helper warps (TMA issue, store agents, repack): with a suspend-time hint the
+// hardware parks the thread until the phase completes or ~the hint (ns) elapses, instead of
+// re-issuing try_wait every ~20 cycles.  The tiled correlation is issue-bound: the un-hinted spin
+// loops of its 4 helper warps were 26 % of all issued instructions (ncu, profiles/README.md).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const TensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -142,6 +157,7 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (!emu_detail::cv().wait_for(lk, std::chrono::seconds(20), [&] { return (uint32_t)((b->init >> 15) & 1u) != parity; }))
     qpwc_emu::watchdog_abort("mbar_wait", (int)parity, (int)b->pending * 1000000 + b->tx);
 }
+inline void mbar_wait_parked(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 inline void tma_prefetch_desc(const TensorMap*) {}
 inline void tma_load_4d(void* smem_dst, const TensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   const int co[4] = {c0, c1, c2, c3};

@@ -111,7 +111,7 @@ corr_fwd_rowpair_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_
       QPWC_RP_FOR_TILES_BEGIN
         for (int c = 0; c < nchunks; ++c, ++g) {
           const int stage = (int)(g % NST);
-          mbar_wait(&empty[stage], ((g / NST) & 1u) ^ 1u);
+          mbar_wait_parked(&empty[stage], ((g / NST) & 1u) ^ 1u);
           unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
           if (ablate & 4) { mbar_arrive(&tfull[stage]); continue; }  // dev ablation: no loads
           mbar_arrive_expect_tx(&tfull[stage], Cfg::RAW_BYTES + Cfg::N_BYTES);
@@ -137,7 +137,7 @@ corr_fwd_rowpair_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_
       QPWC_RP_FOR_TILES_BEGIN
         for (int c = 0; c < nchunks; ++c, ++g) {
           const int stage = (int)(g % NST);
-          mbar_wait(&tfull[stage], (g / NST) & 1u);  // implies the stage was released by the consumers
+          mbar_wait_parked(&tfull[stage], (g / NST) & 1u);  // implies the stage was released by the consumers
           unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
           const unsigned char* raw = sb + Cfg::OFF_RAW;
           unsigned char* pp = sb + Cfg::OFF_PP + Cfg::GUARD;
@@ -175,7 +175,7 @@ corr_fwd_rowpair_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_
         const int twv = min(TW, W - j0);
         for (int rr = 0; rr < 2; ++rr, ++n) {
           for (int rp = aw; rp < Cfg::NRP; ++rp) {
-            mbar_wait(&sfull[rp], n & 1u);
+            mbar_wait_parked(&sfull[rp], n & 1u);
             const int i = i0 + 2 * rp + rr;
             if (i < H && !(ablate & 1)) {  // (dev ablation bit 0: no stores)
               const float* slot = reinterpret_cast<const float*>(smem + Cfg::OFF_STAGING + rp * Cfg::SLOT_BYTES);

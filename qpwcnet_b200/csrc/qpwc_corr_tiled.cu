@@ -156,7 +156,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
       QPWC_FOR_TILES_BEGIN
         const int twv = min(TW, W - j0);
         for (int r = aw; r < TH; r += 3) {
-          mbar_wait(&sfull[r], n & 1u);
+          mbar_wait_parked(&sfull[r], n & 1u);
           const int i = i0 + r;
           if (i < H) {
             const float* slot = reinterpret_cast<const float*>(smem + Cfg::OFF_STAGING + r * Cfg::SLOT_BYTES);
@@ -214,7 +214,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         // rolling rows need chunk c of every tile in the same stage: stage = c, one use per tile
         const int stage = fixed_stage ? c : (int)(g % NST);
         const uint32_t ph = fixed_stage ? (ptile & 1u) : ((g / NST) & 1u);
-        mbar_wait(&empty[stage], ph ^ 1u);  // consumers released this stage
+        mbar_wait_parked(&empty[stage], ph ^ 1u);  // consumers released this stage
         unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
         if (ptid == 0) {
           mbar_arrive_expect_tx(&full[stage], Cfg::P_BYTES + (Cfg::WARP ? 0 : Cfg::N_BYTES));
@@ -556,8 +556,11 @@ int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow,
       return launch_corr_fwd_rowpair(prv, nxt, out, B, H, W, C, d, slope, ops, stream);
     // few tiles (coarse pyramid levels): 2-row tiles double the number of busy SMs
     const long long tiles4 = (long long)cdiv(W, 56) * cdiv(H, 4) * B * (d == 8 ? 4 : 1);
-    if (tiles4 * 2 <= sm_count())
-      return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+    if (tiles4 * 2 <= sm_count()) {
+      if (var && var[0] == 'p')
+        return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+      return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+    }
     // default: scalar FFMA, 4-row tiles, 200 registers per consumer thread.  Measured on B200
     // (tools/ab_corr.py): 178 vs 192 us at 224x512x32 B=8 against the packed channel-parity FFMA2
     // variant (QPWC_CORR_VARIANT=packed) -- a 3-register FFMA sustains ~0.7 FMA/lane/clk with 81

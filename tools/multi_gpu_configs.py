@@ -73,7 +73,8 @@ ten = []
 for (H, W, C) in levels:
     mk = lambda *s: torch.randn(s, device=dev).requires_grad_()
     ten.append((mk(per, H, W, C), mk(per, H, W, C), mk(per, H, W, 2)))
-img = [(torch.rand((per, H, W, c), device=dev).requires_grad_(), torch.randn((per, H, W, 2), device=dev).requires_grad_())
+img = [(torch.rand((per, H, W, c), device=dev).requires_grad_(), torch.rand((per, H, W, c), device=dev).requires_grad_(),
+        torch.randn((per, H, W, 2), device=dev).requires_grad_(), torch.randn((per, H, W, 2), device=dev).requires_grad_())
        for (H, W, _), c in zip(levels, (3, 256, 128, 64, 32))]
 grads = torch.zeros(3_100_000, device=dev)
 comm = torch.cuda.Stream()
@@ -85,8 +86,8 @@ def train_hot_path():
         for k, (p, n, f) in enumerate(ten):
             cv = ops.cost_volume(p, n, 4) if k == 0 else ops.warp_cost_volume(p, n, f, "tfa", 4)
             losses.append(cv.mean())
-    for (im, fl) in img:                                     # FrameInterpolate: two half-flow warps/level
-        losses.append(ops.warp(im, 0.5 * fl, "tfa").mean() + ops.warp(im, -0.5 * fl, "tfa").mean())
+    for (pa, nb_, f01, f10) in img:                          # FrameInterpolate: two half-flow warps/level,
+        losses.append(ops.half_flow_warps(pa, nb_, f01, f10, "tfa").mean())   # one launch, 0.5 x fused
     for k in range(1, 5):                                    # the 8 UpFlow warps are inside the fused op
         pass
     torch.stack(losses).sum().backward()
