@@ -233,11 +233,13 @@ def run_native(args):
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()   # `ncu --profile-from-start off` then lists exactly the timed steps
     ev0.record()
     for s in range(K):
         run_step()
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     t_ms = ev0.elapsed_time(ev1)
     # dominant kernel (finest fused level): its own launches, timed one by one with CUDA events on
     # the launching stream, interleaved with the rest of the step so caches see the same traffic

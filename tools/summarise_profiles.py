@@ -52,7 +52,7 @@ if os.path.exists(ll):
         agg[name][1] += float(r[vi].replace(",", ""))
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(PR, f"{tag}_launch_list_summary.txt"), "w") as fo:
-        fo.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline\n")
+        fo.write(f"# ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 5 --warmup 3 --no-graph --no-cpu-baseline --path composed  (the timed steps only; the unprofiled bench picks the composed path at every UpFlow level)\n")
         fo.write(f"# per-launch times are cold-cache and serialised: compare SHARES\n")
         for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             fo.write(f"{t/1e3:10.1f} us  {100*t/tot:5.1f}%  launches {n:4d}  avg {t/n/1e3:8.1f} us  {name}\n")
