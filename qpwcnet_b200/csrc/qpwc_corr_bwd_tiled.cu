@@ -20,7 +20,8 @@
 // of 4 rows: its elements are fetched into registers before the previous step's FMAs (element-
 // linear, so a warp touches 4-5 cache lines per load; a per-thread table in shared memory maps
 // element -> global offset / skewed destination) and masked, scaled and stored after them.
-// Two 128-thread CTAs share an SM.  No atomics: every gradient element is written once, in a fixed
+// Two 128-thread CTAs share an SM (three fit with a 4-byte table and 168 registers but run slower, 1130 vs
+// 700 us at the finest level: only ~14 KB of L1 would remain for the gradient sectors shared by consecutive steps).  No atomics: every gradient element is written once, in a fixed
 // summation order.
 #include <stdlib.h>
 
