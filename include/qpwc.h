@@ -86,6 +86,21 @@ int qpwc_warp_bwd_ex(const float* img, const float* flow, const float* g_out, fl
                      float* g_flow, int B, int H, int W, int C, int mode, float flow_scale,
                      long long g_out_pixel_stride, void* stream);
 
+/* Upsample(scale) -- qpwcnet/core/non_layers.py:183-193: scale * UpSampling2D(interpolation='bilinear')
+ * (tf.image.resize bilinear, half-pixel centres), x2.  src (B,H,W,C) -> dst (B,2H,2W,C); `_bwd` is
+ * its adjoint (g_dst (B,2H,2W,C) -> g_src (B,H,W,C)). */
+int qpwc_upsample2x_fwd(const float* src, float* dst, int B, int H, int W, int C, float scale, void* stream);
+int qpwc_upsample2x_bwd(const float* g_dst, float* g_src, int B, int H, int W, int C, float scale, void* stream);
+
+/* The flow upsampling fused into its consumers (pwcnet.py:49-56: flo = Upsample(2.0)(flo) feeds
+ * UpFlow): flow_coarse is (B,H/2,W/2,2); the kernels sample with up_scale * bilinear_x2(flow_coarse)
+ * interpolated in registers, so the upsampled flow is not read back from HBM.  H, W (output size) even. */
+int qpwc_warp_fwd_up(const float* img, const float* flow_coarse, float* out, int B, int H, int W, int C,
+                     int mode, float up_scale, void* stream);
+int qpwc_warp_corr_fwd_up(const float* prv, const float* nxt, const float* flow_coarse, float* out, int B,
+                          int H, int W, int C, int search_range, float leaky_slope, int mode,
+                          long long out_pixel_stride, float up_scale, void* stream);
+
 /* UpFlow's  CostVolumeV2((prv, WarpV2((nxt, flo))))  -- qpwcnet/core/non_layers.py:377-380
  * (layers.py:478-481) as ONE kernel: the warped second frame never reaches HBM. */
 int qpwc_warp_corr_fwd(const float* prv, const float* nxt, const float* flow, float* out, int B,

@@ -151,3 +151,53 @@ def warp_cost_volume_bwd(prv, nxt, flow, g_out, mode: str = "tfa", search_range:
     g_prv, g_nxt_w = cost_volume_bwd(prv, nxt_w, out, g_out, search_range, slope)
     g_nxt, g_flow = warp_bwd(nxt, flow, g_nxt_w, mode)
     return g_prv, g_nxt, g_flow
+
+
+# ------------------------------------------------------------------ x2 bilinear upsampling (numpy)
+def _up2_coords(n_out, n_in, dtype):
+    """tf.image.resize bilinear, half-pixel centres (ResizeBilinear kernel, restated from its
+    published algorithm; TF is not installable here => parity for this op is UNPINNED):
+    in = (o + 0.5) * (n_in / n_out) - 0.5; lo = max(floor(in), 0); hi = min(ceil(in), n_in - 1);
+    lerp = in - floor(in)."""
+    o = np.arange(n_out, dtype=dtype)
+    src = (o + dtype(0.5)) * dtype(n_in / n_out) - dtype(0.5)
+    fl = np.floor(src)
+    lo = np.maximum(fl.astype(np.int64), 0)
+    hi = np.minimum(np.ceil(src).astype(np.int64), n_in - 1)
+    return lo, hi, (src - fl).astype(dtype)
+
+
+def upsample2x(x, scale: float = 1.0):
+    """``Upsample(scale)`` -- qpwcnet/core/non_layers.py:183-193: ``scale *
+    UpSampling2D(interpolation='bilinear')(x)``; NHWC (B,H,W,C) -> (B,2H,2W,C), arithmetic in x.dtype
+    with every product/sum rounded on its own: top = tl + (tr-tl)*xl; bot = bl + (br-bl)*xl;
+    out = top + (bot-top)*yl."""
+    x = np.ascontiguousarray(x)
+    dt = x.dtype.type
+    B, H, W, C = x.shape
+    ylo, yhi, yl = _up2_coords(2 * H, H, dt)
+    xlo, xhi, xl = _up2_coords(2 * W, W, dt)
+    tl, tr = x[:, ylo][:, :, xlo], x[:, ylo][:, :, xhi]
+    bl, br = x[:, yhi][:, :, xlo], x[:, yhi][:, :, xhi]
+    xl_, yl_ = xl[None, None, :, None], yl[None, :, None, None]
+    top = tl + (tr - tl) * xl_
+    bot = bl + (br - bl) * xl_
+    return (dt(scale) * (top + (bot - top) * yl_)).astype(x.dtype)
+
+
+def upsample2x_bwd(g_out, scale: float = 1.0):
+    """Adjoint of ``upsample2x`` (what TF autodiff / ResizeBilinearGrad computes up to summation
+    order): g_in[lo/hi] += weight * g_out."""
+    g_out = np.ascontiguousarray(g_out)
+    dt = g_out.dtype.type
+    B, H2, W2, C = g_out.shape
+    H, W = H2 // 2, W2 // 2
+    ylo, yhi, yl = _up2_coords(H2, H, dt)
+    xlo, xhi, xl = _up2_coords(W2, W, dt)
+    tmp = np.zeros((B, H, W2, C), dtype=g_out.dtype)          # rows first
+    np.add.at(tmp, (slice(None), ylo), g_out * (dt(1) - yl)[None, :, None, None])
+    np.add.at(tmp, (slice(None), yhi), g_out * yl[None, :, None, None])
+    g = np.zeros((B, H, W, C), dtype=g_out.dtype)
+    np.add.at(g, (slice(None), slice(None), xlo), tmp * (dt(1) - xl)[None, None, :, None])
+    np.add.at(g, (slice(None), slice(None), xhi), tmp * xl[None, None, :, None])
+    return (dt(scale) * g).astype(g_out.dtype)

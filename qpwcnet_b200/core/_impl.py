@@ -48,3 +48,7 @@ def half_flow_warps(inputs, mode, fmt, flow_scale=0.5):
     out = ops.half_flow_warps(to_nhwc(prv, fmt), to_nhwc(nxt, fmt), to_nhwc(flo_01, fmt),
                               to_nhwc(flo_10, fmt), mode, flow_scale)
     return from_nhwc(out, fmt)
+
+
+def upsample(x, scale, fmt):
+    return from_nhwc(ops.upsample2x(to_nhwc(x, fmt), scale), fmt)

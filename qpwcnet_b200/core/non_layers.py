@@ -69,3 +69,14 @@ class HalfFlowWarps(_Functor):
 
     def __call__(self, inputs):
         return _impl.half_flow_warps(inputs, self.warp_mode, self.data_format, self.flow_scale)
+
+
+class Upsample(_Functor):
+    """qpwcnet/core/non_layers.py:183-193: ``scale * UpSampling2D(interpolation='bilinear')(x)``."""
+
+    def __init__(self, scale: float = 1.0, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.scale = float(scale)
+
+    def __call__(self, x):
+        return _impl.upsample(x, self.scale, self.data_format)

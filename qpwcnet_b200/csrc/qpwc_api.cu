@@ -14,12 +14,14 @@ namespace qpwc {
 // kernels (qpwc_warp.cu, qpwc_corr_direct.cu, qpwc_corr_tiled.cu)
 int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
-int launch_warp_fwd_ex(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
+int launch_warp_fwd_ex(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
+int launch_upsample2x_fwd(const float*, float*, int, int, int, int, float, cudaStream_t);
+int launch_upsample2x_bwd(const float*, float*, int, int, int, int, float, cudaStream_t);
 int launch_warp_bwd_ex(const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
-int launch_corr_fwd_direct(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t);
+int launch_corr_fwd_direct(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
 int launch_corr_bwd_direct(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
 // returns QPWC_ERR_UNSUPPORTED (without setting an error) when the shape is outside its domain
-int launch_corr_fwd_tiled(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t);
+int launch_corr_fwd_tiled(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
 int launch_corr_bwd_tiled(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
 
 static thread_local char g_err[512] = "";
@@ -67,10 +69,11 @@ static int check_mode(const char* fn, int mode, int H, int W) {
 }
 
 static int corr_fwd_any(const float* prv, const float* nxt, const float* flow, int mode, float* out,
-                        int B, int H, int W, int C, int d, float slope, long long ops, cudaStream_t st) {
-  const int rc = launch_corr_fwd_tiled(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st);
+                        int B, int H, int W, int C, int d, float slope, long long ops, cudaStream_t st,
+                        float up_scale = 0.f) {
+  const int rc = launch_corr_fwd_tiled(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);
   if (rc != QPWC_ERR_UNSUPPORTED) return rc;
-  return launch_corr_fwd_direct(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st);
+  return launch_corr_fwd_direct(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);
 }
 static int corr_bwd_any(const float* prv, const float* nxt, const float* out, const float* g_out,
                         float* g_prv, float* g_nxt, int B, int H, int W, int C, int d, float slope,
@@ -281,6 +284,57 @@ int qpwc_warp_bwd_ex(const float* img, const float* flow, const float* g_out, fl
   }
   QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "g_out", g_out)); QPWC_TRY(check_ptr(fn, "g_img", g_img));
   return launch_warp_bwd_ex(img, flow, g_out, g_img, g_flow, B, H, W, C, mode, flow_scale, g_out_pixel_stride, (cudaStream_t)stream);
+}
+
+static int check_up(const char* fn, int H, int W, float up_scale) {
+  if ((H & 1) || (W & 1)) return set_error(QPWC_ERR_INVALID, "%s: H and W must be even (x2 upsampled flow), got %dx%d", fn, H, W);
+  if (up_scale == 0.f) return set_error(QPWC_ERR_INVALID, "%s: up_scale must be non-zero", fn);
+  return QPWC_OK;
+}
+
+int qpwc_upsample2x_fwd(const float* src, float* dst, int B, int H, int W, int C, float scale, void* stream) {
+  const char* fn = "qpwc_upsample2x_fwd";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_ptr(fn, "src", src)); QPWC_TRY(check_ptr(fn, "dst", dst));
+  return launch_upsample2x_fwd(src, dst, B, H, W, C, scale, (cudaStream_t)stream);
+}
+
+int qpwc_upsample2x_bwd(const float* g_dst, float* g_src, int B, int H, int W, int C, float scale, void* stream) {
+  const char* fn = "qpwc_upsample2x_bwd";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_ptr(fn, "g_dst", g_dst)); QPWC_TRY(check_ptr(fn, "g_src", g_src));
+  return launch_upsample2x_bwd(g_dst, g_src, B, H, W, C, scale, (cudaStream_t)stream);
+}
+
+int qpwc_warp_fwd_up(const float* img, const float* flow_coarse, float* out, int B, int H, int W, int C,
+                     int mode, float up_scale, void* stream) {
+  const char* fn = "qpwc_warp_fwd_up";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_up(fn, H, W, up_scale));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "flow_coarse", flow_coarse)); QPWC_TRY(check_ptr(fn, "out", out));
+  if (reinterpret_cast<uintptr_t>(flow_coarse) % 8) return set_error(QPWC_ERR_INVALID, "%s: flow must be 8-byte aligned", fn);
+  return launch_warp_fwd_ex(img, flow_coarse, nullptr, nullptr, out, B, H, W, C, mode, 1.f, C, (cudaStream_t)stream, up_scale);
+}
+
+int qpwc_warp_corr_fwd_up(const float* prv, const float* nxt, const float* flow_coarse, float* out, int B,
+                          int H, int W, int C, int search_range, float leaky_slope, int mode,
+                          long long out_pixel_stride, float up_scale, void* stream) {
+  const char* fn = "qpwc_warp_corr_fwd_up";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_corr_args(fn, search_range, out_pixel_stride));
+  QPWC_TRY(check_up(fn, H, W, up_scale));
+  if (B == 0 || H == 0 || W == 0) return QPWC_OK;
+  if (C == 0) return set_error(QPWC_ERR_INVALID, "%s: C == 0", fn);
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt)); QPWC_TRY(check_ptr(fn, "flow_coarse", flow_coarse));
+  QPWC_TRY(check_ptr(fn, "out", out));
+  if (reinterpret_cast<uintptr_t>(flow_coarse) % 8) return set_error(QPWC_ERR_INVALID, "%s: flow must be 8-byte aligned", fn);
+  return corr_fwd_any(prv, nxt, flow_coarse, mode, out, B, H, W, C, search_range, leaky_slope, out_pixel_stride,
+                      (cudaStream_t)stream, up_scale);
 }
 
 int qpwc_warp_corr_fwd(const float* prv, const float* nxt, const float* flow, float* out, int B,

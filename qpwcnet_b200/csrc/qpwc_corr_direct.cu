@@ -9,7 +9,7 @@
 // register-tiled kernels in qpwc_corr_tiled.cu take over for the pyramid shapes.  Forward: one
 // thread per output element, sequential channel sum (same order as the fp32 oracle).  Backward:
 // one thread per (pixel, channel) gathering over the (2d+1)^2 displacements for both gradients.
-#include "qpwc_common.cuh"
+#include "qpwc_upsample.cuh"
 
 namespace qpwc {
 
@@ -18,7 +18,7 @@ template <int WARP, int MODE>
 __global__ void __launch_bounds__(256) corr_fwd_direct_kernel(
     const float* __restrict__ prv, const float* __restrict__ nxt, const float* __restrict__ flow,
     float* __restrict__ out, int H, int W, int C, int d, float slope, long long ops,
-    long long total /* B*H*W*D */) {
+    long long total /* B*H*W*D */, float up_scale) {
   const int q = 2 * d + 1;
   const int D = q * q;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(256) corr_fwd_direct_kernel(
       const float* p = prv + (size_t)pix * C;
       const float* nb = nxt + (size_t)b * H * W * C;
       if (WARP) {
-        const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)b * H * W + (size_t)r * W + s));
+        const float2 f = up_scale != 0.f
+            ? up2_flow(flow + (size_t)b * (H / 2) * (W / 2) * 2, r, s, H / 2, W / 2, up_scale)
+            : __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)b * H * W + (size_t)r * W + s));
         const Taps t = make_taps<MODE>(r, s, f.x, f.y, H, W);
         const float* n00 = nb + (size_t)t.o00 * C; const float* n01 = nb + (size_t)t.o01 * C;
         const float* n10 = nb + (size_t)t.o10 * C; const float* n11 = nb + (size_t)t.o11 * C;
@@ -152,20 +154,20 @@ static int grid_for(long long total, int block, int waves) {
 
 int launch_corr_fwd_direct(const float* prv, const float* nxt, const float* flow, int mode,
                            float* out, int B, int H, int W, int C, int d, float slope,
-                           long long ops, cudaStream_t stream) {
+                           long long ops, cudaStream_t stream, float up_scale) {
   const int D = (2 * d + 1) * (2 * d + 1);
   const long long total = (long long)B * H * W * D;
   if (total == 0) return QPWC_OK;
   const int block = 256, grid = grid_for(total, block, 64);
   if (!flow) {
     auto k = corr_fwd_direct_kernel<0, QPWC_MODE_TF>;
-    QPWC_LAUNCH(k, grid, block, 0, stream, prv, nxt, flow, out, H, W, C, d, slope, ops, total);
+    QPWC_LAUNCH(k, grid, block, 0, stream, prv, nxt, flow, out, H, W, C, d, slope, ops, total, up_scale);
   } else if (mode == QPWC_MODE_TF) {
     auto k = corr_fwd_direct_kernel<1, QPWC_MODE_TF>;
-    QPWC_LAUNCH(k, grid, block, 0, stream, prv, nxt, flow, out, H, W, C, d, slope, ops, total);
+    QPWC_LAUNCH(k, grid, block, 0, stream, prv, nxt, flow, out, H, W, C, d, slope, ops, total, up_scale);
   } else {
     auto k = corr_fwd_direct_kernel<1, QPWC_MODE_TFA>;
-    QPWC_LAUNCH(k, grid, block, 0, stream, prv, nxt, flow, out, H, W, C, d, slope, ops, total);
+    QPWC_LAUNCH(k, grid, block, 0, stream, prv, nxt, flow, out, H, W, C, d, slope, ops, total, up_scale);
   }
   return check_launch("corr_fwd_direct");
 }

@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include "qpwc_async.cuh"
+#include "qpwc_upsample.cuh"
 
 namespace qpwc {
 
@@ -106,7 +107,9 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
                       const float* __restrict__ nxt, const float* __restrict__ flow,
                       float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
                       int tiles_x, int tiles_y, int nsegs, int segs_per_strip, int seg, int ablate, int nwin,
-                      int dsearch) {
+                      int dsearch, float up_scale) {
+  // up_scale != 0 (fused variant): `flow` is the coarse flow (B, H/2, W/2, 2) and the taps are set up
+  // from up_scale * bilinear_x2(flow) (qpwc_upsample.cuh) -- the upsampled flow is never read back
   // nwin = 1: the 9x9 displacement window is the whole search range (d = 4).  nwin = 4 (d = 8): the
   // 17x17 range is covered by four 9x9 windows centred at (+-4, +-4); a tile index then also
   // selects the window, whose offset (oi, oj) shifts the second-frame tile and the output channels
@@ -201,7 +204,9 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           TapsEntry e;
           e.o00 = -1; e.o01 = e.o10 = e.o11 = 0; e.w00 = e.w01 = e.w10 = e.w11 = 0.f;
           if (r >= 0 && r < H && s >= 0 && s < W) {  // outside: zero padding of the warped frame
-            const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)b * H * W + (size_t)r * W + s));
+            const float2 f = up_scale != 0.f
+                ? up2_flow(flow + (size_t)b * (H / 2) * (W / 2) * 2, r, s, H / 2, W / 2, up_scale)
+                : __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)b * H * W + (size_t)r * W + s));
             const Taps t = make_taps<Cfg::MODE>(r, s, f.x, f.y, H, W);
             e.o00 = t.o00; e.o01 = t.o01; e.o10 = t.o10; e.o11 = t.o11;
             e.w00 = t.w00; e.w01 = t.w01; e.w10 = t.w10; e.w11 = t.w11;
@@ -494,7 +499,8 @@ static int ablate_flags() {
 
 template <class Cfg>
 static int run_tiled(const float* prv, const float* nxt, const float* flow, float* out, int B, int H,
-                     int W, int C, float slope, long long ops, cudaStream_t stream, int dsearch = 4) {
+                     int W, int C, float slope, long long ops, cudaStream_t stream, int dsearch = 4,
+                     float up_scale = 0.f) {
   const int nwin = dsearch == 8 ? 4 : 1;
   TensorMap tmP, tmN;
   if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::KC, Cfg::PCOL, Cfg::TH)) return QPWC_ERR_CUDA;  // box 8 x 56 x TH
@@ -527,7 +533,7 @@ static int run_tiled(const float* prv, const float* nxt, const float* flow, floa
   }
 #endif
   QPWC_LAUNCH(k, grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream, tmP, tmN, nxt, flow, out, B, H, W, C, slope, ops,
-              tiles_x, tiles_y, nsegs, segs_per_strip, seg, ablate_flags(), nwin, dsearch);
+              tiles_x, tiles_y, nsegs, segs_per_strip, seg, ablate_flags(), nwin, dsearch, up_scale);
   return check_launch("corr_fwd_tiled");
 }
 
@@ -536,7 +542,7 @@ int launch_corr_fwd_rowpair(const float*, const float*, float*, int, int, int, i
 
 int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow, int mode, float* out,
                           int B, int H, int W, int C, int d, float slope, long long ops,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, float up_scale) {
   // domain: d == 4 (one 9x9 window) or d == 8 (four windows), C a multiple of 4, 16-byte aligned
   // inputs (TMA), maps at least one tile wide
   if ((d != 4 && d != 8) || (C & 3) || C < 4) return QPWC_ERR_UNSUPPORTED;
@@ -569,8 +575,8 @@ int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow,
       return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
     return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
   }
-  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
-  return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d, up_scale);
+  return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d, up_scale);
 }
 
 #ifdef QPWC_EMU

@@ -9,7 +9,7 @@
 // Backward: sub-warp groups of G lanes own one pixel at a time (G = pow2 >= C/V, <= 32); each lane
 //           scatter-adds its channel vector into the four taps (vector red.global.add) and the
 //           flow gradient is reduced across the group with xor-shuffles in a fixed order.
-#include "qpwc_common.cuh"
+#include "qpwc_upsample.cuh"
 
 namespace qpwc {
 
@@ -70,7 +70,11 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ img2,
                                                        const float* __restrict__ flow2,
                                                        float* __restrict__ out, int H, int W, int C,
-                                                       int bsplit, float scale, long long ops) {
+                                                       int bsplit, float scale, long long ops,
+                                                       float up_scale) {
+  // up_scale != 0: `flow` is the COARSE flow (B, H/2, W/2, 2); the sampling flow is
+  // up_scale * bilinear_x2(flow), interpolated here instead of being read back from HBM
+  // (Upsample(scale=2.0) feeding UpFlow's warp, non_layers.py:183-193, pwcnet.py:49-56)
   const int CV = C / (V * NV);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // j * CV + cv
   if (idx >= W * CV) return;
@@ -81,7 +85,9 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
   if (second) { img = img2; flow = flow2; }
   const size_t row = (size_t)b * H + i;                    // b*H + i
   const size_t pix = row * W + j;
-  float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);  // ch0 = x, ch1 = y
+  float2 f;
+  if (up_scale != 0.f) f = up2_flow(flow + (size_t)b * (H / 2) * (W / 2) * 2, i, j, H / 2, W / 2, up_scale);
+  else f = __ldg(reinterpret_cast<const float2*>(flow) + pix);    // ch0 = x, ch1 = y
   f.x = __fmul_rn(scale, f.x); f.y = __fmul_rn(scale, f.y);       // exact for scale == 1
   const Taps t = make_taps<MODE>(i, j, f.x, f.y, H, W);
   const float* base = img + (size_t)b * H * W * C + (size_t)cv * (V * NV);
@@ -217,30 +223,30 @@ static int pick_vec(int C, const void* a, const void* b, const void* c = nullptr
 template <int MODE, int V, int NV>
 static void run_warp_fwd_nv(const float* img, const float* flow, const float* img2, const float* flow2,
                             float* out, int B, int H, int W, int C, float scale, long long ops,
-                            cudaStream_t stream);
+                            float up_scale, cudaStream_t stream);
 
 template <int MODE, int V>
 static void run_warp_fwd(const float* img, const float* flow, const float* img2, const float* flow2,
                          float* out, int B, int H, int W, int C, float scale, long long ops,
-                         cudaStream_t stream) {
+                         float up_scale, cudaStream_t stream) {
   const int block = 256;
   if (V == 4 && C % 8 == 0) {  // two 16-byte vectors per thread
-    run_warp_fwd_nv<MODE, V, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
+    run_warp_fwd_nv<MODE, V, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
     return;
   }
-  run_warp_fwd_nv<MODE, V, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
+  run_warp_fwd_nv<MODE, V, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
 }
 
 template <int MODE, int V, int NV>
 static void run_warp_fwd_nv(const float* img, const float* flow, const float* img2, const float* flow2,
                             float* out, int B, int H, int W, int C, float scale, long long ops,
-                            cudaStream_t stream) {
+                            float up_scale, cudaStream_t stream) {
   const int block = 256;
   const int CV = C / (V * NV);
   auto k = warp_fwd_kernel<MODE, V, NV>;
   if (img2) {  // pair: grid.z = 2B (B <= 32767 checked by the caller)
     const dim3 grid((unsigned)cdiv(W * CV, block), (unsigned)H, (unsigned)(2 * B));
-    QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, img2, flow2, out, H, W, C, B, scale, ops);
+    QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, img2, flow2, out, H, W, C, B, scale, ops, up_scale);
     return;
   }
   // gridDim.y/z are limited to 65535: chunk the batch (and refuse absurd heights upstream)
@@ -248,35 +254,36 @@ static void run_warp_fwd_nv(const float* img, const float* flow, const float* im
     const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
     const dim3 grid((unsigned)cdiv(W * CV, block), (unsigned)H, (unsigned)nb);
     const size_t off = (size_t)b0 * H * W;
-    QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + off * 2, img2, flow2, out + off * ops, H, W, C,
-                nb, scale, ops);
+    const size_t foff = up_scale != 0.f ? (size_t)b0 * (H / 2) * (W / 2) * 2 : off * 2;
+    QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + foff, img2, flow2, out + off * ops, H, W, C,
+                nb, scale, ops, up_scale);
   }
 }
 
 // img2/flow2 != nullptr: two warps in one launch, the second writing channels [C, 2C) of each pixel
 int launch_warp_fwd_ex(const float* img, const float* flow, const float* img2, const float* flow2,
                        float* out, int B, int H, int W, int C, int mode, float scale, long long ops,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, float up_scale) {
   int V = pick_vec(C, img, out, img2);
   while (V > 1 && ops % V) V >>= 1;
   if ((long long)B * H * W * C == 0) return QPWC_OK;
   if (H > 65535 || (long long)W * (C / V) >= (1LL << 31)) return set_error(QPWC_ERR_UNSUPPORTED, "warp_fwd: H > 65535 or W*C too large");
   if (img2 && B > 32767) return set_error(QPWC_ERR_UNSUPPORTED, "warp_pair_fwd: B > 32767");
   if (mode == QPWC_MODE_TF) {
-    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
-    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
-    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
+    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
+    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
   } else {
-    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
-    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
-    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, stream);
+    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
+    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
   }
   return check_launch("warp_fwd");
 }
 
 int launch_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
                     int mode, cudaStream_t stream) {
-  return launch_warp_fwd_ex(img, flow, nullptr, nullptr, out, B, H, W, C, mode, 1.f, C, stream);
+  return launch_warp_fwd_ex(img, flow, nullptr, nullptr, out, B, H, W, C, mode, 1.f, C, stream, 0.f);
 }
 
 template <int MODE, int V>

@@ -295,6 +295,85 @@ def _warp_pair_fwd(out, img_a, flow_a, img_b, flow_b, mode, scale):
     return out
 
 
+def _upsample2x_fwd(x, scale):
+    B, H, W, C = x.shape
+    out = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=x.device)
+    (vx,) = _views(x)
+    with _on_device(x.device):
+        check(lib().qpwc_upsample2x_fwd(vx.ptr, out.data_ptr(), B, H, W, C, float(scale), _stream_ptr(x.device)))
+    return out
+
+
+def _upsample2x_bwd(g_out, scale):
+    B, H2, W2, C = g_out.shape
+    g = torch.empty((B, H2 // 2, W2 // 2, C), dtype=torch.float32, device=g_out.device)
+    (vg,) = _views(g_out)
+    with _on_device(g_out.device):
+        check(lib().qpwc_upsample2x_bwd(vg.ptr, g.data_ptr(), B, H2 // 2, W2 // 2, C, float(scale),
+                                        _stream_ptr(g_out.device)))
+    return g
+
+
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return _upsample2x_fwd(x, scale)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        return _upsample2x_bwd(g_out.contiguous(), ctx.scale), None
+
+
+class _WarpUp(torch.autograd.Function):
+    """warp(img, up_scale * bilinear_x2(flow_coarse)) with the upsampling done inside the warp kernel."""
+
+    @staticmethod
+    def forward(ctx, img, flow_c, mode, up_scale):
+        B, H, W, C = img.shape
+        out = torch.empty_like(img)
+        vi, vf = _views(img, flow_c)
+        with _on_device(img.device):
+            check(lib().qpwc_warp_fwd_up(vi.ptr, vf.ptr, out.data_ptr(), B, H, W, C, mode, float(up_scale),
+                                         _stream_ptr(img.device)))
+        ctx.save_for_backward(img, flow_c)
+        ctx.cfg = (mode, up_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        img, flow_c = ctx.saved_tensors
+        mode, up_scale = ctx.cfg
+        flow = _upsample2x_fwd(flow_c, up_scale)                 # re-materialised for the backward only
+        g_img, g_flow = _warp_bwd(img, flow, g_out.contiguous(), mode)
+        return g_img, _upsample2x_bwd(g_flow, up_scale), None, None
+
+
+class _WarpCostVolumeUp(torch.autograd.Function):
+    """Fused UpFlow pair on the coarse flow: cost_volume(prv, warp(nxt, up_scale * bilinear_x2(flow_c)))."""
+
+    @staticmethod
+    def forward(ctx, prv, nxt, flow_c, mode, d, slope, up_scale):
+        B, H, W, C = prv.shape
+        D = (2 * d + 1) ** 2
+        out = torch.empty((B, H, W, D), dtype=torch.float32, device=prv.device)
+        vp, vn, vf = _views(prv, nxt, flow_c)
+        with _on_device(prv.device):
+            check(lib().qpwc_warp_corr_fwd_up(vp.ptr, vn.ptr, vf.ptr, out.data_ptr(), B, H, W, C, d, slope, mode,
+                                              D, float(up_scale), _stream_ptr(prv.device)))
+        ctx.save_for_backward(prv, nxt, flow_c, out)
+        ctx.cfg = (mode, d, slope, up_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        prv, nxt, flow_c, out = ctx.saved_tensors
+        mode, d, slope, up_scale = ctx.cfg
+        flow = _upsample2x_fwd(flow_c, up_scale)
+        g = _warp_corr_bwd(prv, nxt, flow, out, g_out.contiguous(), mode, d, slope)
+        return g[0], g[1], _upsample2x_bwd(g[2], up_scale), None, None, None, None
+
+
 class _WarpCostVolume(torch.autograd.Function):
     @staticmethod
     def forward(ctx, prv, nxt, flow, mode, d, slope):
@@ -342,6 +421,52 @@ def warp(img, flow, mode="tfa", flow_scale: float = 1.0):
     if not img.is_cuda:
         return _warp_fwd(img, flow, m)
     return _Warp.apply(img, flow, m)
+
+
+def upsample2x(x, scale: float = 1.0):
+    """``Upsample(scale)`` of the reference (non_layers.py:183-193): ``scale *
+    UpSampling2D(interpolation='bilinear')(x)`` -- tf.image.resize bilinear with half-pixel
+    centres, x2.  NHWC (B,H,W,C) -> (B,2H,2W,C).  Differentiable."""
+    x = _prep(x, "x")
+    if not x.is_cuda:
+        raise ValueError("upsample2x needs a CUDA tensor")
+    return _Upsample2x.apply(x, float(scale))
+
+
+def _check_coarse(img, flow_c, what):
+    B, H, W, _ = img.shape
+    if H % 2 or W % 2 or tuple(flow_c.shape) != (B, H // 2, W // 2, 2) or flow_c.device != img.device:
+        raise ValueError(f"{what}: features {tuple(img.shape)}@{img.device} need a coarse flow "
+                         f"({B}, {H // 2}, {W // 2}, 2) on the same device (H, W even), got {tuple(flow_c.shape)}@{flow_c.device}")
+    if not img.is_cuda:
+        raise ValueError(f"{what} needs CUDA tensors")
+
+
+def warp_up(img, flow_coarse, mode="tfa", up_scale: float = 2.0):
+    """``warp((img, Upsample(up_scale)(flow_coarse)))`` with the x2 bilinear flow upsampling
+    (pwcnet.py:49-56) interpolated inside the warp kernel: the upsampled flow is never read back
+    from HBM.  ``flow_coarse``: (B, H/2, W/2, 2).  Differentiable."""
+    img = _prep(img, "img")
+    flow_coarse = _prep(flow_coarse, "flow_coarse", last=2)
+    _check_coarse(img, flow_coarse, "warp_up")
+    m = _mode(mode)
+    if m == 1 and (img.shape[1] < 2 or img.shape[2] < 2):
+        raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
+    return _WarpUp.apply(img, flow_coarse, m, float(up_scale))
+
+
+def warp_cost_volume_up(prv, nxt, flow_coarse, mode="tfa", search_range: int = 4, leaky_slope: float = 0.1,
+                        up_scale: float = 2.0):
+    """Fused ``cost_volume(prv, warp(nxt, Upsample(up_scale)(flow_coarse)))``: UpFlow on the coarse
+    flow, one kernel; neither the upsampled flow nor the warped frame is read back from HBM."""
+    prv, nxt = _prep(prv, "prv"), _prep(nxt, "nxt")
+    flow_coarse = _prep(flow_coarse, "flow_coarse", last=2)
+    _same(prv, nxt, "warp_cost_volume_up(prv, nxt)")
+    _check_coarse(prv, flow_coarse, "warp_cost_volume_up")
+    m = _mode(mode)
+    if m == 1 and (prv.shape[1] < 2 or prv.shape[2] < 2):
+        raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
+    return _WarpCostVolumeUp.apply(prv, nxt, flow_coarse, m, int(search_range), float(leaky_slope), float(up_scale))
 
 
 def _pair_args(prv, nxt, flo_01, flo_10, mode):

@@ -234,6 +234,60 @@ def test_half_flow_warps_frame_interpolate(mode, B, H, W, C):
         assert_as_accurate(host(gf_gpu), np.float32(0.5) * gf32, 0.5 * gf64, floor=1e-6 * max(1.0, C / 8))
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 7, 9, 2), (1, 14, 32, 2), (1, 5, 3, 5)])
+def test_upsample2x_forward_backward(B, H, W, C):
+    """Upsample(scale=2.0) (non_layers.py:183-193): scale * bilinear x2, half-pixel centres."""
+    r = rng(500 + C)
+    x = r.standard_normal((B, H, W, C)).astype(np.float32)
+    tx = dev(x).requires_grad_()
+    y = ops.upsample2x(tx, 2.0)
+    ref32, ref64 = oracle.upsample2x(x, 2.0), oracle.upsample2x(x.astype(np.float64), 2.0)
+    np.testing.assert_array_equal(host(y), ref32)            # same op order as the fp32 oracle
+    assert np.abs(host(y) - ref64).max() <= 1e-6
+    g = r.standard_normal(ref32.shape).astype(np.float32)
+    (gx,) = torch.autograd.grad(y, (tx,), dev(g))
+    np.testing.assert_allclose(host(gx), oracle.upsample2x_bwd(g.astype(np.float64), 2.0), rtol=0, atol=2e-6)
+    from qpwcnet_b200.core import non_layers
+    np.testing.assert_array_equal(host(non_layers.Upsample(scale=2.0, data_format="channels_last")(tx.detach())), ref32)
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 28, 32), (1, 28, 64, 256), (1, 10, 14, 6), (1, 8, 72, 16)])
+def test_upsampled_flow_fused_into_warp_and_upflow(mode, B, H, W, C):
+    """pwcnet.py:49-56: flo = Upsample(2.0)(flo_coarse) feeds UpFlow.  The x2 upsampling is
+    interpolated inside the warp / fused warp->cost-volume kernels: results must equal the op
+    applied to the materialised upsampled flow bit for bit (same arithmetic), and the oracle."""
+    r = rng(600 + C)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    fc = (r.standard_normal((B, H // 2, W // 2, 2)) * 1.5).astype(np.float32)
+    tp, tn, tfc = (dev(a).requires_grad_() for a in (prv, nxt, fc))
+    flow_up = oracle.upsample2x(fc, 2.0)
+    w = ops.warp_up(tn, tfc, mode)
+    np.testing.assert_array_equal(host(w), oracle.warp(nxt, flow_up, mode))
+    np.testing.assert_array_equal(host(w), host(ops.warp(tn.detach(), ops.upsample2x(tfc.detach(), 2.0), mode)))
+    cv = ops.warp_cost_volume_up(tp, tn, tfc, mode, 4)
+    cv_mat = ops.warp_cost_volume(tp.detach(), tn.detach(), ops.upsample2x(tfc.detach(), 2.0), mode, 4)
+    np.testing.assert_array_equal(host(cv), host(cv_mat))
+    ref = oracle.warp_cost_volume(prv.astype(np.float64), nxt.astype(np.float64), flow_up.astype(np.float64), mode, 4)
+    assert_rel(host(cv), ref)
+    # gradients: through the fused ops == through the explicit composition
+    g = r.standard_normal((B, H, W, 81)).astype(np.float32)
+    gp, gn, gf = torch.autograd.grad(cv, (tp, tn, tfc), dev(g))
+    tp2, tn2, tfc2 = (dev(a).requires_grad_() for a in (prv, nxt, fc))
+    cv2 = ops.warp_cost_volume(tp2, tn2, ops.upsample2x(tfc2, 2.0), mode, 4)
+    gp2, gn2, gf2 = torch.autograd.grad(cv2, (tp2, tn2, tfc2), dev(g))
+    for a, b in ((gp, gp2), (gn, gn2), (gf, gf2)):
+        assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-3)
+    gw = r.standard_normal((B, H, W, C)).astype(np.float32)
+    gi, gfc = torch.autograd.grad(w, (tn, tfc), dev(gw))
+    gi64, gf64 = oracle.warp_bwd(nxt.astype(np.float64), flow_up.astype(np.float64), gw.astype(np.float64), mode)
+    gi32, gf32 = oracle.warp_bwd(nxt, flow_up, gw, mode)
+    assert_as_accurate(host(gi), gi32, gi64)
+    ref_gfc = oracle.upsample2x_bwd(gf64, 2.0)
+    assert np.abs(host(gfc) - ref_gfc).max() <= 1e-5 * max(1.0, np.abs(ref_gfc).max())
+
+
 def test_golden_fixtures():
     g = np.load(os.path.join(GOLD, "qpwc_golden.npz"))
     for name in ("cv_a", "cv_b", "cv_c", "cv_d"):

@@ -232,3 +232,29 @@ def test_golden_cfg1_reference_test_shape():
     for mode in oracle.MODES:
         w = oracle.warp(img, flo, mode)
         np.testing.assert_allclose(w[:, ::5, ::7], c[f"warp/{mode}/sample"], rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------ x2 bilinear upsampling (Upsample)
+def test_upsample2x_oracle_matches_torch_half_pixel_rule_and_adjoint():
+    """oracle.upsample2x restates tf.image.resize(bilinear, half-pixel centres) x2 (Upsample,
+    qpwcnet/core/non_layers.py:183-193).  TF is absent, so the restatement is cross-checked against
+    torch's independent implementation of the same rule (align_corners=False), hand-derived values at
+    the borders, and the adjoint identity <up(x), g> == <x, up_bwd(g)>."""
+    import torch
+    r = np.random.default_rng(5)
+    x = r.standard_normal((2, 5, 7, 3))
+    y = oracle.upsample2x(x, 2.0)
+    t = torch.nn.functional.interpolate(torch.from_numpy(x).permute(0, 3, 1, 2), scale_factor=2, mode="bilinear",
+                                        align_corners=False).permute(0, 2, 3, 1).numpy() * 2.0
+    assert y.shape == (2, 10, 14, 3)
+    np.testing.assert_allclose(y, t, rtol=0, atol=1e-13)
+    # borders replicate, interior weights are 0.25 / 0.75
+    np.testing.assert_allclose(y[:, 0, 0], 2.0 * x[:, 0, 0], atol=1e-15)
+    np.testing.assert_allclose(y[:, -1, -1], 2.0 * x[:, -1, -1], atol=1e-15)
+    np.testing.assert_allclose(y[:, 0, 1], 2.0 * (0.75 * x[:, 0, 0] + 0.25 * x[:, 0, 1]), atol=1e-14)
+    np.testing.assert_allclose(y[:, 0, 2], 2.0 * (0.25 * x[:, 0, 0] + 0.75 * x[:, 0, 1]), atol=1e-14)
+    g = r.standard_normal(y.shape)
+    gi = oracle.upsample2x_bwd(g, 2.0)
+    assert abs((y * g).sum() - (x * gi).sum()) < 1e-10
+    x32 = x.astype(np.float32)
+    assert np.abs(oracle.upsample2x(x32, 2.0) - y).max() < 2e-6

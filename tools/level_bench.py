@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--json", default=None)
     ap.add_argument("--bwd", action="store_true")
+    ap.add_argument("--up", action="store_true", help="also time the flow-upsampling fusion (SURVEY 8f rank 1)")
     a = ap.parse_args()
     dev = "cuda"
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
@@ -63,6 +64,14 @@ def main():
             t_cb = timeit(lambda: ops._corr_bwd(prv, nxt, cvout, g81, 4, 0.1), max(3, a.iters // 4), flush)
             t_wb = timeit(lambda: ops._warp_bwd(nxt, flo, gC, 1), max(3, a.iters // 4), flush)
             print(f"{'':>14}  corr_bwd {t_cb*1e6:9.1f} us ({4*81*C*px/t_cb/1e12:5.1f} TF)   warp_bwd {t_wb*1e6:8.1f} us ({4*(3*C+4)*px/t_wb/1e9:6.0f} GB/s)")
+        if a.up and H % 2 == 0 and W % 2 == 0:
+            fc = torch.randn((B, H // 2, W // 2, 2), device=dev, generator=g)
+            with torch.no_grad():
+                t_u = timeit(lambda: ops.upsample2x(fc, 2.0), a.iters, flush)
+                t_wu = timeit(lambda: ops.warp_up(nxt, fc, "tfa"), a.iters, flush)
+                t_fu = timeit(lambda: ops.warp_cost_volume_up(prv, nxt, fc, "tfa", 4), a.iters, flush)
+            print(f"{'':>14}  upsample2x {t_u*1e6:6.1f} us + warp {t_warp*1e6:6.1f} us  vs  warp_up {t_wu*1e6:6.1f} us;"
+                  f"  fused corr on coarse flow {t_fu*1e6:7.1f} us (on materialised flow {t_fused*1e6:7.1f} us)")
         flops = 2 * 81 * C * px
         by_corr, by_fused, by_warp = 4 * (2 * C + 81) * px, 4 * (2 * C + 2 + 81) * px, 4 * (2 * C + 2) * px
         lb = lambda by: max(by / HBM, flops / FP32)
