@@ -286,7 +286,7 @@ def run_native(args):
     barrier()
     e2e = {"value": BATCH * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": wl_h.h2d_bytes(),
            "d2h_bytes_per_step": wl_h.d2h_bytes(), "steps": Ke, "ms_per_step": e2e_s * 1e3,
-           "path": "ops.*_into(pinned host tensors) -> qpwc_*_host (3-slot H2D/kernel/D2H pipeline)"}
+           "path": "ops.*_into(pinned host tensors) -> qpwc_*_host (6-slot H2D/kernel/D2H pipeline)"}
 
     # ---- roofline of the dominant kernel (finest fused level)
     peak, peak_src = load_peaks()

@@ -87,10 +87,10 @@ static int corr_bwd_any(const float* prv, const float* nxt, const float* out, co
 // One workspace per device: NSLOT independent (stream, device buffer) slots.  A slot's stream runs
 // H2D -> kernel -> D2H for one batch slice; different slots overlap (both copy engines + SMs).
 struct HostStage {
-  static const int NSLOT = 3;
-  cudaStream_t stream[NSLOT] = {nullptr, nullptr, nullptr};
-  float* buf[NSLOT] = {nullptr, nullptr, nullptr};
-  size_t cap[NSLOT] = {0, 0, 0};
+  static const int NSLOT = 6;  // deep enough for the H2D engine to run ahead of the (slower, output-heavy) D2H side
+  cudaStream_t stream[NSLOT] = {};
+  float* buf[NSLOT] = {};
+  size_t cap[NSLOT] = {};
   std::mutex mu;
 };
 static HostStage g_stage[16];
