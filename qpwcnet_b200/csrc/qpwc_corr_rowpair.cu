@@ -188,9 +188,11 @@ corr_fwd_rowpair_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_
               } else {  // strided output (concat buffer) and/or one window of a wider search range
                 const int qo = 2 * dsearch + 1;
                 const int chb = (oi - D + dsearch) * qo + (oj - D + dsearch);
-                for (int e = lane; e < cnt; e += 32) {
-                  const int px = e / NDISP, mk = e - px * NDISP, m = mk / Q, k = mk - m * Q;
-                  dst[(size_t)px * ops + chb + m * qo + k] = slot[e];
+                // lanes own channels (their (m,k) -> output channel map is loop invariant), pixels are walked
+                // in order: coalesced runs per pixel, no per-element divisions
+                for (int ch = lane; ch < NDISP; ch += 32) {
+                  const int m = ch / Q, k = ch - m * Q, och = chb + m * qo + k;
+                  for (int px = 0; px < cnt / NDISP; ++px) dst[(size_t)px * ops + och] = slot[px * NDISP + ch];
                 }
               }
             }

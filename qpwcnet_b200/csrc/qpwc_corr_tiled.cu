@@ -172,9 +172,11 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
             } else {  // strided output (concat buffer) and/or a window of a wider search range
               const int qo = 2 * dsearch + 1;
               const int chb = (oi - D + dsearch) * qo + (oj - D + dsearch);
-              for (int e = lane; e < cnt; e += 32) {
-                const int px = e / NDISP, mk = e - px * NDISP, m = mk / Q, k = mk - m * Q;
-                dst[(size_t)px * ops + chb + m * qo + k] = slot[e];
+              // lanes own channels (their (m,k) -> output channel map is loop invariant), pixels are walked
+              // in order: coalesced runs per pixel, no per-element divisions
+              for (int ch = lane; ch < NDISP; ch += 32) {
+                const int m = ch / Q, k = ch - m * Q, och = chb + m * qo + k;
+                for (int px = 0; px < cnt / NDISP; ++px) dst[(size_t)px * ops + och] = slot[px * NDISP + ch];
               }
             }
           }
@@ -429,9 +431,11 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           } else {  // strided output and/or a window of a wider search range
             const int qo = 2 * dsearch + 1;
             const int chb = (oi - D + dsearch) * qo + (oj - D + dsearch);
-            for (int e = tc; e < n; e += NCOL) {
-              const int px = e / NDISP, mk = e - px * NDISP, m = mk / Q, k = mk - m * Q;
-              dst[(size_t)px * ops + chb + m * qo + k] = slot[e];
+            // lanes own channels (their (m,k) -> output channel map is loop invariant), pixels are walked
+            // in order: coalesced runs per pixel, no per-element divisions
+            for (int ch = tc; ch < NDISP; ch += NCOL) {
+              const int m = ch / Q, k = ch - m * Q, och = chb + m * qo + k;
+              for (int px = 0; px < n / NDISP; ++px) dst[(size_t)px * ops + och] = slot[px * NDISP + ch];
             }
           }
         }
