@@ -18,7 +18,7 @@
 // live in a 5-slot ring in shared memory: each row is loaded once per tile (cp.async, in flight
 // under the FMAs of the previous step).  The G' slice of a step is 9 of the 81 gradient channels
 // of 4 rows: its elements are fetched into registers before the previous step's FMAs (element-
-// linear, so a warp touches 4-5 cache lines per load; a per-thread table in shared memory maps
+// linear, so a warp touches 4-5 cache lines per load; a per-thread table held in 21 registers maps
 // element -> global offset / skewed destination) and masked, scaled and stored after them.
 // Two 128-thread CTAs share an SM (three fit with a 4-byte table and 168 registers but run slower, 1130 vs
 // 700 us at the finest level: only ~14 KB of L1 would remain for the gradient sectors shared by consecutive steps).  No atomics: every gradient element is written once, in a fixed
@@ -44,10 +44,11 @@ constexpr int NEL = TH * XW * Q;                 // gradient elements per step (
 constexpr int NK = (NEL + NTHREADS - 1) / NTHREADS;  // 21 per thread
 constexpr int OFF_GS = RING * XROW_BYTES;
 constexpr int OFF_DUMMY = OFF_GS + TH * GS_ROW_BYTES;  // sink for the padding elements of the table
-constexpr int OFF_TAB = OFF_DUMMY + 16;
-constexpr int SMEM_BYTES = OFF_TAB + NK * NTHREADS * 8;
+constexpr int SMEM_BYTES = OFF_DUMMY + 16;
+constexpr int GOFF_BITS = 20;  // per-thread element table entry: global element offset | Gs word offset << 20
 static_assert(SMEM_BYTES <= 113 * 1024, "two CTAs per SM");
-static_assert(GS_ROW_BYTES % 16 == 0 && OFF_TAB % 8 == 0, "alignment");
+static_assert(GS_ROW_BYTES % 16 == 0, "alignment");
+static_assert((OFF_DUMMY - OFF_GS) / 4 + 4 < (1 << (32 - GOFF_BITS)), "Gs word offset fits the table entry");
 }  // namespace bwdcfg
 
 // X ring: [slot][x][8 units of 16 B], unit index XORed with bit 3 of x: the 32 lanes (g, h) of a
@@ -88,27 +89,26 @@ corr_bwd_tiled_kernel(const float* __restrict__ prv, const float* __restrict__ n
   const size_t bpix = (size_t)b * H * W;
   const float inv_c = 1.f / (float)C;
   const int C4 = C >> 2;
-  int2* tab = reinterpret_cast<int2*>(smem + OFF_TAB);
 
   // ---- element table.  Element n of a step = (rr, px, e): tile row, pixel of the slice, channel
   //      of the 9-channel slice.   g_prv: pixel (i0+rr, j0+px), px < 64;  source x = px+e, slot e.
   //      g_nxt: pixel (X row of the step, j0-4+px), px < 72;  source x = px, slot 8-e.
-  //      .x = global element offset relative to (row0 of the step, column 0 of the slice, channel
-  //      0 of the slice), .y = Gs byte offset | rr << 16 | px << 24.  Padding elements (n >= nel)
-  //      re-read element 0 and store into a dummy word.
+  //      entry (one register per element, loop invariant) = global element offset relative to
+  //      (row0 of the step, column 0 of the slice, channel 0 of the slice) in the low 20 bits |
+  //      Gs word offset (relative to OFF_GS) << 20.  Padding elements (n >= nel) re-read element 0
+  //      and store into a dummy word.
   constexpr int npx = which == 0 ? TW : XW;
   constexpr int nel = TH * npx * Q;
-#pragma unroll 1
+  uint32_t tab[NK];
+#pragma unroll
   for (int k = 0; k < NK; ++k) {
     const int n = tid + k * NTHREADS;
-    int2 ent = make_int2(0, OFF_DUMMY);
+    tab[k] = (uint32_t)((OFF_DUMMY - OFF_GS) / 4) << GOFF_BITS;
     if (n < nel) {
-      const int e = n % Q, pr = n / Q, px = pr % npx, rr = pr / npx;
+      const int e = n % Q, pr = n / Q, px = pr % npx, rr = pr / npx;   // compile-time divisors
       const int xs = which == 0 ? px + e : px, es = which == 0 ? e : Q - 1 - e;
-      ent.x = (int)(((long long)rr * W + px) * ops) + e;
-      ent.y = (int)(gs_off(rr, xs) + es * 4) | (rr << 16) | (px << 24);
+      tab[k] = (uint32_t)((rr * W + px) * (int)ops + e) | ((gs_off(rr, xs) - OFF_GS + es * 4) / 4) << GOFF_BITS;
     }
-    tab[k * NTHREADS + tid] = ent;
   }
   // tile classification: can every slice / X pixel of every step be read without bounds checks?
   const int colbase = which == 0 ? j0 : j0 - D;
@@ -143,32 +143,32 @@ corr_bwd_tiled_kernel(const float* __restrict__ prv, const float* __restrict__ n
   auto fetch_gs = [&](int t) {
     int row0;
     const long long base = slice_base(t, row0);
-    if (interior) {  // CTA-uniform: no bounds checks, 32-bit offsets from a uniform base
-      const float* gb_ = g_out + base;
-      const float* ob_ = out + base;
+    const float* gb_ = g_out + base;
+    const float* ob_ = out + base;
+    if (interior) {  // CTA-uniform: no bounds checks
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
-        const unsigned off = (unsigned)tab[k * NTHREADS + tid].x;
+        const uint32_t off = tab[k] & ((1u << GOFF_BITS) - 1);
         gq[k] = __ldg(gb_ + off); oq[k] = __ldg(ob_ + off);
       }
     } else {
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
-        const int2 ent = tab[k * NTHREADS + tid];
-        const int row = row0 + ((ent.y >> 16) & 0xff), col = colbase + ((ent.y >> 24) & 0xff);
-        const bool ok = row >= 0 && row < H && col >= 0 && col < W;
+        const int n = tid + k * NTHREADS;
+        const int pr = n / Q, px = pr % npx, rr = pr / npx;
+        const int row = row0 + rr, col = colbase + px;
+        const bool ok = n < nel && row >= 0 && row < H && col >= 0 && col < W;
+        const uint32_t off = tab[k] & ((1u << GOFF_BITS) - 1);
         gq[k] = 0.f; oq[k] = 1.f;
-        if (ok) { gq[k] = __ldg(g_out + base + ent.x); oq[k] = __ldg(out + base + ent.x); }
+        if (ok) { gq[k] = __ldg(gb_ + off); oq[k] = __ldg(ob_ + off); }
       }
     }
   };
   const float sc_pos = inv_c, sc_neg = slope * inv_c;
   auto store_gs = [&]() {
 #pragma unroll
-    for (int k = 0; k < NK; ++k) {
-      const uint32_t so = (uint32_t)tab[k * NTHREADS + tid].y & 0xffffu;
-      *reinterpret_cast<float*>(smem + so) = gq[k] * (oq[k] > 0.f ? sc_pos : sc_neg);
-    }
+    for (int k = 0; k < NK; ++k)
+      *reinterpret_cast<float*>(smem + OFF_GS + (tab[k] >> GOFF_BITS) * 4u) = gq[k] * (oq[k] > 0.f ? sc_pos : sc_neg);
   };
 
   float2 acc[PXT][CHT / 2];
@@ -261,6 +261,7 @@ int launch_corr_bwd_tiled(const float* prv, const float* nxt, const float* out, 
   if (var && var[0] == 'd') return QPWC_ERR_UNSUPPORTED;
   const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH), ncb = cdiv(C, CB);
   if (ncb > 65535 || B > 65535) return QPWC_ERR_UNSUPPORTED;
+  if (((long long)(TH - 1) * W + XW) * ops + Q >= (1LL << GOFF_BITS)) return QPWC_ERR_UNSUPPORTED;  // table entry range
 #ifndef QPWC_EMU
   static unsigned attr_done = 0;  // one bit per device (the attribute is per device)
   int dev = 0;
