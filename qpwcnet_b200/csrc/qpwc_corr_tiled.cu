@@ -385,7 +385,14 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
 #define QPWC_ACC(m, k) (Cfg::PACKED ? (acc2[m][k].x + acc2[m][k].y) : acc[m][k])
       const int twv = min(TW, W - j0);  // valid pixel columns of this tile
       if (Cfg::AGENT) {
-        // deposit the 9x9 block (transposed into the NHWC 81-vector order) and carry on
+        // scale + leaky relu of all 81 outputs as straight-line code (the per-k range checks below
+        // would otherwise split it into nine short dependent chains), then deposit the 9x9 block
+        // (transposed into the NHWC 81-vector order) and carry on
+        float res[Q][Q];
+#pragma unroll
+        for (int k = 0; k < Q; ++k)
+#pragma unroll
+          for (int m = 0; m < Q; ++m) res[m][k] = lrelu(QPWC_ACC(m, k) * inv_c, slope);
         mbar_wait(&sfree[ti], (tcount & 1u) ^ 1u);  // previous tile's store has drained this slot
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
@@ -393,7 +400,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
           if (lp >= 0 && lp < twv) {
             float* dstp = slot0 + lp * NDISP + k;
 #pragma unroll
-            for (int m = 0; m < Q; ++m) dstp[m * Q] = lrelu(QPWC_ACC(m, k) * inv_c, slope);
+            for (int m = 0; m < Q; ++m) dstp[m * Q] = res[m][k];
           }
         }
         fence_proxy_async();
