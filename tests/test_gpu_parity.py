@@ -450,6 +450,19 @@ def test_empty_and_error_behaviour():
         ops.cost_volume(x, torch.zeros((1, 4, 6, 3), device=DEV), 4)
     with pytest.raises(TypeError):
         ops.cost_volume(x.double(), x.double(), 4)
+    # the entry points added for FrameInterpolate / Upsample
+    f = torch.zeros((1, 4, 5, 2), device=DEV)
+    assert ops.half_flow_warps(e, e, torch.empty((0, 4, 5, 2), device=DEV), torch.empty((0, 4, 5, 2), device=DEV)).shape == (0, 4, 5, 6)
+    assert ops.upsample2x(e, 2.0).shape == (0, 8, 10, 3)
+    with pytest.raises(ValueError, match="coarse flow"):
+        ops.warp_up(x, f, "tfa")                                   # odd width, wrong coarse shape
+    with pytest.raises(ValueError, match="S>=2C"):
+        ops.half_flow_warps_into(torch.zeros((1, 4, 5, 5), device=DEV), x, x, f, f)
+    L = _cabi.lib()
+    assert L.qpwc_warp_pair_fwd(x.data_ptr(), f.data_ptr(), x.data_ptr(), f.data_ptr(), x.data_ptr(), 1, 4, 5, 3, 1, 0.5, 5, None) == 1
+    assert b"out_pixel_stride" in L.qpwc_last_error()
+    assert L.qpwc_warp_fwd_up(x.data_ptr(), f.data_ptr(), x.data_ptr(), 1, 4, 5, 3, 1, 2.0, None) == 1
+    assert b"even" in L.qpwc_last_error()
 
 
 def test_host_buffer_entry_points_match_device_path():
