@@ -55,6 +55,13 @@ const char* qpwc_last_error(void);
 int qpwc_corr_fwd(const float* prv, const float* nxt, float* out, int B, int H, int W, int C,
                   int search_range, float leaky_slope, long long out_pixel_stride, void* stream);
 
+/* The same layer with data_format='channels_first' (layers.py:83-85; the reference's training
+ * layout, pre_train.py:34), natively: prv, nxt (B,C,H,W) -> out (B,(2d+1)^2,H,W), all dense.
+ * Returns QPWC_ERR_UNSUPPORTED (nothing launched) unless search_range == 4, W % 4 == 0 and the
+ * tensors are 16-byte aligned; the caller then transposes and uses qpwc_corr_fwd. */
+int qpwc_corr_fwd_nchw(const float* prv, const float* nxt, float* out, int B, int C, int H, int W,
+                       int search_range, float leaky_slope, void* stream);
+
 /* Gradient of the above (TF autodiff of layers.py:77-99 / tfa CorrelationCostGrad + LeakyReluGrad).
  * `out` is the forward result (sign gives the leaky mask); g_out shares its pixel stride. */
 int qpwc_corr_bwd(const float* prv, const float* nxt, const float* out, const float* g_out,

@@ -23,6 +23,8 @@ def from_nhwc(x: torch.Tensor, fmt: str) -> torch.Tensor:
 
 def cost_volume(inputs, search_range, fmt, leaky_slope=0.1):
     prv, nxt = inputs
+    if fmt == "channels_first" and prv.is_cuda and prv.dim() == 4:
+        return ops.cost_volume_nchw(prv, nxt, search_range, leaky_slope)   # native NCHW kernel
     out = ops.cost_volume(to_nhwc(prv, fmt), to_nhwc(nxt, fmt), search_range, leaky_slope)
     return from_nhwc(out, fmt)
 

@@ -16,6 +16,7 @@ int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int,
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_fwd_ex(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
 int launch_upsample2x_fwd(const float*, float*, int, int, int, int, float, cudaStream_t);
+int launch_corr_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_upsample2x_bwd(const float*, float*, int, int, int, int, float, cudaStream_t);
 int launch_warp_bwd_ex(const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
 int launch_corr_fwd_direct(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
@@ -284,6 +285,21 @@ int qpwc_warp_bwd_ex(const float* img, const float* flow, const float* g_out, fl
   }
   QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "g_out", g_out)); QPWC_TRY(check_ptr(fn, "g_img", g_img));
   return launch_warp_bwd_ex(img, flow, g_out, g_img, g_flow, B, H, W, C, mode, flow_scale, g_out_pixel_stride, (cudaStream_t)stream);
+}
+
+int qpwc_corr_fwd_nchw(const float* prv, const float* nxt, float* out, int B, int C, int H, int W,
+                       int search_range, float leaky_slope, void* stream) {
+  const char* fn = "qpwc_corr_fwd_nchw";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_corr_args(fn, search_range, (long long)(2 * search_range + 1) * (2 * search_range + 1)));
+  if (B == 0 || H == 0 || W == 0) return QPWC_OK;
+  if (C == 0) return set_error(QPWC_ERR_INVALID, "%s: C == 0 (mean over an empty channel axis)", fn);
+  QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt)); QPWC_TRY(check_ptr(fn, "out", out));
+  const int rc = launch_corr_fwd_nchw(prv, nxt, out, B, C, H, W, search_range, leaky_slope, (cudaStream_t)stream);
+  if (rc == QPWC_ERR_UNSUPPORTED)
+    return set_error(QPWC_ERR_UNSUPPORTED, "%s: native channels_first kernel needs search_range 4, W %% 4 == 0 and 16-byte aligned tensors "
+                                           "(transpose to NHWC and call qpwc_corr_fwd instead)", fn);
+  return rc;
 }
 
 static int check_up(const char* fn, int H, int W, float up_scale) {

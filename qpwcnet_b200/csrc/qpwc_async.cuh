@@ -110,15 +110,18 @@ template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile
 // (boxC, boxW, boxH, 1), SWIZZLE_32B, zero fill out of bounds, 128-B L2 promotion.
 // Returns false (and sets the error) on failure.
 bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C, int boxC, int boxW, int boxH);  // swizzle = boxC*4 bytes
+// dense NCHW fp32 tensor, dims (W, H, C, B), box (boxW, boxH, boxC, 1), no swizzle (channel-planar tiles)
+bool make_tmap_nchw(TensorMap* tm, const float* base, int B, int C, int H, int W, int boxW, int boxH, int boxC);
 
 #else
 // ============================================================================ CPU emulation
 #define QPWC_GRID_CONSTANT
 struct TensorMap {
   const float* base;
-  long long dim[4];      // C, W, H, B
+  long long dim[4];      // C, W, H, B  (NCHW maps: W, H, C, B)
   long long stride[4];   // element strides
   int box[4];
+  int swizzle;           // 0 = none, 1 = SWIZZLE_32B, 3 = SWIZZLE_64B (mask of address bits [7:8] folded into [4:5])
 };
 struct EmuMbar { uint16_t init; uint16_t pending; int32_t tx; };  // init bit 15 = phase parity
 static_assert(sizeof(EmuMbar) == 8, "mbarrier is 8 bytes");
@@ -174,7 +177,7 @@ inline void tma_load_4d(void* smem_dst, const TensorMap* tm, uint64_t* bar, int 
           if (in) v = tm->base[x[0] * tm->stride[0] + x[1] * tm->stride[1] + x[2] * tm->stride[2] + x[3] * tm->stride[3]];
           // hardware swizzles on absolute shared-memory address bits
           const uintptr_t abs = reinterpret_cast<uintptr_t>(dst) + lin;
-          const uintptr_t phys = abs ^ (((abs >> 7) & (tm->box[0] * 4 == 32 ? 1u : 3u)) << 4);
+          const uintptr_t phys = abs ^ (((abs >> 7) & (uintptr_t)tm->swizzle) << 4);
           *reinterpret_cast<float*>(phys) = v;
         }
   std::lock_guard<std::mutex> lk(emu_detail::mu());
@@ -197,6 +200,15 @@ inline bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W
   tm->dim[0] = C; tm->dim[1] = W; tm->dim[2] = H; tm->dim[3] = B;
   tm->stride[0] = 1; tm->stride[1] = C; tm->stride[2] = (long long)W * C; tm->stride[3] = (long long)H * W * C;
   tm->box[0] = boxC; tm->box[1] = boxW; tm->box[2] = boxH; tm->box[3] = 1;
+  tm->swizzle = boxC * 4 == 32 ? 1 : 3;
+  return true;
+}
+inline bool make_tmap_nchw(TensorMap* tm, const float* base, int B, int C, int H, int W, int boxW, int boxH, int boxC) {
+  tm->base = base;
+  tm->dim[0] = W; tm->dim[1] = H; tm->dim[2] = C; tm->dim[3] = B;
+  tm->stride[0] = 1; tm->stride[1] = W; tm->stride[2] = (long long)H * W; tm->stride[3] = (long long)C * H * W;
+  tm->box[0] = boxW; tm->box[1] = boxH; tm->box[2] = boxC; tm->box[3] = 1;
+  tm->swizzle = 0;
   return true;
 }
 #endif

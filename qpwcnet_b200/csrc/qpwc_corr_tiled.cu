@@ -486,6 +486,19 @@ bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C
   if (r != CUDA_SUCCESS) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return false; }
   return true;
 }
+bool make_tmap_nchw(TensorMap* tm, const float* base, int B, int C, int H, int W, int boxW, int boxH, int boxC) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available"); return false; }
+  const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxC, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled (NCHW) failed (CUresult %d)", (int)r); return false; }
+  return true;
+}
 static int sm_count() {
   static int n = 0;
   if (!n) {

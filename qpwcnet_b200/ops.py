@@ -230,6 +230,44 @@ class _CostVolume(torch.autograd.Function):
         return g_prv, g_nxt, None, None
 
 
+def _corr_fwd_nchw(prv, nxt, d, slope):
+    """Native channels_first forward; returns None when the library declines the shape (the caller
+    then takes the transposing NHWC route -- still CUDA, never a CPU path)."""
+    from ._cabi import QpwcError, QPWC_ERR_UNSUPPORTED
+    B, C, H, W = prv.shape
+    out = torch.empty((B, (2 * d + 1) ** 2, H, W), dtype=torch.float32, device=prv.device)
+    vp, vn = _views(prv, nxt)
+    with _on_device(prv.device):
+        rc = lib().qpwc_corr_fwd_nchw(vp.ptr, vn.ptr, out.data_ptr(), B, C, H, W, d, slope, _stream_ptr(prv.device))
+    if rc == QPWC_ERR_UNSUPPORTED:
+        return None
+    check(rc)
+    return out
+
+
+class _CostVolumeNCHW(torch.autograd.Function):
+    """channels_first cost volume: native NCHW forward kernel; the backward transposes to NHWC and
+    uses the tiled gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, prv, nxt, d, slope):
+        out = _corr_fwd_nchw(prv, nxt, d, slope)
+        if out is None:
+            out = _corr_fwd(prv.permute(0, 2, 3, 1).contiguous(), nxt.permute(0, 2, 3, 1).contiguous(), d,
+                            slope).permute(0, 3, 1, 2).contiguous()
+        ctx.save_for_backward(prv, nxt, out)
+        ctx.cfg = (d, slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        prv, nxt, out = ctx.saved_tensors
+        d, slope = ctx.cfg
+        nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+        g_prv, g_nxt = _corr_bwd(nhwc(prv), nhwc(nxt), nhwc(out), nhwc(g_out), d, slope)
+        return g_prv.permute(0, 3, 1, 2).contiguous(), g_nxt.permute(0, 3, 1, 2).contiguous(), None, None
+
+
 class _Warp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, flow, mode):
@@ -400,6 +438,18 @@ def cost_volume(prv, nxt, search_range: int = 4, leaky_slope: float = 0.1):
     if not prv.is_cuda:
         return _corr_fwd(prv, nxt, int(search_range), float(leaky_slope))
     return _CostVolume.apply(prv, nxt, int(search_range), float(leaky_slope))
+
+
+def cost_volume_nchw(prv, nxt, search_range: int = 4, leaky_slope: float = 0.1):
+    """``cost_volume`` for channels_first tensors: (B,C,H,W) x2 -> (B,(2d+1)^2,H,W), through the
+    native NCHW kernel (qpwc_corr_nchw.cu) when the shape allows it (d == 4, W % 4 == 0)."""
+    if prv.dim() != 4 or prv.shape != nxt.shape or prv.device != nxt.device:
+        raise ValueError(f"cost_volume_nchw(prv, nxt): {tuple(prv.shape)}@{prv.device} vs {tuple(nxt.shape)}@{nxt.device}")
+    if prv.dtype != torch.float32 or nxt.dtype != torch.float32:
+        raise TypeError("cost_volume_nchw expects float32 tensors")
+    if not prv.is_cuda:
+        raise ValueError("cost_volume_nchw needs CUDA tensors")
+    return _CostVolumeNCHW.apply(prv.contiguous(), nxt.contiguous(), int(search_range), float(leaky_slope))
 
 
 def warp(img, flow, mode="tfa", flow_scale: float = 1.0):

@@ -48,6 +48,15 @@ def corr_fwd(prv, nxt, d=4, slope=0.1, ops=None):
     return out
 
 
+def corr_fwd_nchw(prv, nxt, d=4, slope=0.1):
+    """prv, nxt: (B,C,H,W) -> (B,(2d+1)^2,H,W) through the native channels_first kernel."""
+    prv, nxt = _f(prv), _f(nxt)
+    B, C, H, W = prv.shape
+    out = np.full((B, (2 * d + 1) ** 2, H, W), np.nan, np.float32)
+    _ck(lib().qpwc_corr_fwd_nchw(_p(prv), _p(nxt), _p(out), B, C, H, W, d, ctypes.c_float(slope), None))
+    return out
+
+
 def corr_bwd(prv, nxt, out, g_out, d=4, slope=0.1):
     prv, nxt, out, g_out = _f(prv), _f(nxt), _f(out), _f(g_out)
     B, H, W, C = prv.shape

@@ -131,6 +131,19 @@ def test_emu_corr_fwd_rowpair(B, H, W, C, monkeypatch):
     np.testing.assert_allclose(got, old, rtol=0, atol=2e-6 * np.abs(ref).max())
 
 
+@pytest.mark.parametrize("B,C,H,W", [(1, 8, 7, 124), (2, 12, 9, 60), (1, 3, 5, 252), (1, 20, 16, 16)])
+def test_emu_corr_fwd_nchw(B, C, H, W):
+    """Native channels_first kernel (qpwc_corr_nchw.cu): planar TMA tiles, pixel-pair FFMA2, direct
+    NCHW stores; ragged tiles (W not a multiple of 120), odd heights, channel tails."""
+    r = rng(14)
+    prv = r.standard_normal((B, C, H, W)).astype(np.float32)
+    nxt = r.standard_normal((B, C, H, W)).astype(np.float32)
+    ref = oracle.cost_volume(prv.transpose(0, 2, 3, 1).astype(np.float64), nxt.transpose(0, 2, 3, 1).astype(np.float64), 4)
+    got = emu_lib.corr_fwd_nchw(prv, nxt, 4)
+    assert not np.isnan(got).any()
+    assert np.abs(got.transpose(0, 2, 3, 1) - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
 def test_emu_corr_fwd_rowpair_search_range_8(monkeypatch):
     monkeypatch.setenv("QPWC_CORR_VARIANT", "rowpair")
     r = rng(13)

@@ -288,6 +288,34 @@ def test_upsampled_flow_fused_into_warp_and_upflow(mode, B, H, W, C):
     assert np.abs(host(gfc) - ref_gfc).max() <= 1e-5 * max(1.0, np.abs(ref_gfc).max())
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 24, 128), (1, 256, 14, 32), (1, 64, 33, 252), (1, 5, 7, 20), (2, 16, 9, 124)])
+def test_cost_volume_channels_first_native(B, C, H, W):
+    """data_format='channels_first' (layers.py:83-85; the reference's training layout): native NCHW
+    kernel (qpwc_corr_nchw.cu) vs the oracle, the NHWC kernel, and the layer with its gradient."""
+    from qpwcnet_b200.core import layers
+    r = rng(700 + C)
+    prv = r.standard_normal((B, C, H, W)).astype(np.float32)
+    nxt = r.standard_normal((B, C, H, W)).astype(np.float32)
+    ref = oracle.cost_volume(prv.transpose(0, 2, 3, 1).astype(np.float64), nxt.transpose(0, 2, 3, 1).astype(np.float64), 4)
+    tp, tn = dev(prv).requires_grad_(), dev(nxt).requires_grad_()
+    assert ops._corr_fwd_nchw(tp.detach(), tn.detach(), 4, 0.1) is not None        # the native kernel took it
+    out = layers.CostVolumeV2(search_range=4, data_format="channels_first")((tp, tn))
+    assert tuple(out.shape) == (B, 81, H, W)
+    assert_rel(host(out).transpose(0, 2, 3, 1), ref)
+    nhwc = ops.cost_volume(tp.detach().permute(0, 2, 3, 1).contiguous(), tn.detach().permute(0, 2, 3, 1).contiguous(), 4)
+    assert float((out.detach().permute(0, 2, 3, 1) - nhwc).abs().max()) <= 2e-6 * float(nhwc.abs().max())
+    g = r.standard_normal((B, 81, H, W)).astype(np.float32)
+    gp, gn = torch.autograd.grad(out, (tp, tn), dev(g))
+    rp, rn = oracle.cost_volume_bwd(prv.transpose(0, 2, 3, 1).astype(np.float64), nxt.transpose(0, 2, 3, 1).astype(np.float64),
+                                    host(out).transpose(0, 2, 3, 1).astype(np.float64), g.transpose(0, 2, 3, 1).astype(np.float64), 4)
+    assert_rel(host(gp).transpose(0, 2, 3, 1), rp)
+    assert_rel(host(gn).transpose(0, 2, 3, 1), rn)
+    # shapes the native kernel declines (W % 4 != 0) fall back to the transposing route
+    o2 = layers.CostVolume(search_range=4, data_format="channels_first")((tp.detach()[..., :W - 1].contiguous(), tn.detach()[..., :W - 1].contiguous()))
+    ref2 = oracle.cost_volume(prv[..., :W - 1].transpose(0, 2, 3, 1).astype(np.float64), nxt[..., :W - 1].transpose(0, 2, 3, 1).astype(np.float64), 4)
+    assert_rel(host(o2).transpose(0, 2, 3, 1), ref2)
+
+
 def test_golden_fixtures():
     g = np.load(os.path.join(GOLD, "qpwc_golden.npz"))
     for name in ("cv_a", "cv_b", "cv_c", "cv_d"):
