@@ -84,7 +84,8 @@ corr_fwd_nchw_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CON
 
   // ================================================================================== consumers
   setmaxnreg_inc<Cfg::REG_CONS>();
-  const int ti = tid / (NCOLS / 2), t = tid % (NCOLS / 2), lane = tid & 31;
+  const int ti = tid / (NCOLS / 2), t = tid % (NCOLS / 2), lane = tid & 31;   // column pair t of row ti
+  const int tw0 = t & ~31;                                                      // first column pair of this warp
   // operand byte offsets inside one channel plane of a stage
   const uint32_t n_off = (uint32_t)((ti * NCOLS + 2 * t) * 4);                  // row ti+m: + m * NCOLS * 4
   const uint32_t p_off = (uint32_t)(Cfg::N_BYTES + (ti * PCOLS + 2 * t) * 4);   // pixel q: + q * 4
@@ -139,27 +140,43 @@ corr_fwd_nchw_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CON
     const int i = i0 + ti;
     if (i < H) {
       const int S = j0 - D + 2 * t;
-      // validity of the two pixels per displacement column k (bit k: first pixel, bit 16+k: second)
-      uint32_t okm = 0;
-#pragma unroll
-      for (int k = 0; k < Q; ++k) {
-        const int p = S + 4 - k;
-        if (p >= j0 && p < j0 + TW && p < W) okm |= 1u << k;
-        if (p + 1 >= j0 && p + 1 < j0 + TW && p + 1 < W) okm |= 1u << (16 + k);
-      }
-      // running pointer over the 81 planes in channel order: plane (m,k) at +(m*9+k)*plane, pixel S+4-k
-      float* dst = out + (size_t)b * Cfg::NDISP * plane + (size_t)i * W + (S + 4);
-      const size_t step = plane - 1;   // k -> k+1: next plane, one pixel to the left
-#pragma unroll
-      for (int m = 0; m < Q; ++m) {
+      const size_t plane9 = (size_t)Q * plane;   // m -> m+1 at fixed k
+      float* base = out + (size_t)b * Cfg::NDISP * plane + (size_t)i * W;
+      // A thread's outputs for pixels just outside [j0, j0+120) are COMPLETE and bit-identical to what
+      // the neighbouring tile computes (same operands, same channel order), so they are stored as
+      // well: only the image bounds need checking, and a warp whose pixel range [pmin, pmax] lies
+      // inside the row stores without any predicate.
+      const int pmin = j0 - D + 2 * tw0 - 4, pmax = j0 - D + 2 * tw0 + 67;
+      if (pmin >= 0 && pmax < W) {
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
-          const bool ok0 = (okm >> k) & 1u, ok1 = (okm >> (16 + k)) & 1u;
-          const float v0 = lrelu((k == 8 ? accL[m] : acc2[7 - k][m].x) * inv_c, slope);   // q = 8-k -> index q-1
-          const float v1 = lrelu((k == 0 ? accR[m] : acc2[8 - k][m].y) * inv_c, slope);   // q = 9-k -> index q-1
-          if ((k & 1) == 0 && ok0 && ok1) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
-          else { if (ok0) dst[0] = v0; if (ok1) dst[1] = v1; }
-          dst += (k == Q - 1) ? plane + (Q - 1) : step;   // after k = 8: next m, back to k = 0 (pixel S+4)
+          float* dst = base + (size_t)k * plane + (S + 4 - k);
+#pragma unroll
+          for (int m = 0; m < Q; ++m) {
+            const float v0 = lrelu((k == 8 ? accL[m] : acc2[k == 8 ? 0 : 7 - k][m].x) * inv_c, slope);
+            const float v1 = lrelu((k == 0 ? accR[m] : acc2[k == 0 ? 0 : 8 - k][m].y) * inv_c, slope);
+            if ((k & 1) == 0) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);   // p even: aligned pair
+            else { dst[0] = v0; dst[1] = v1; }
+            dst += plane9;
+          }
+        }
+      } else {
+        // warps that reach over the left / right image border: per-pixel bounds
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+          const int p = S + 4 - k;
+          const bool ok0 = p >= 0 && p < W, ok1 = p + 1 >= 0 && p + 1 < W;
+          float* dst = base + (size_t)k * plane + p;
+          if (ok0 || ok1) {
+#pragma unroll
+            for (int m = 0; m < Q; ++m) {
+              const float v0 = lrelu((k == 8 ? accL[m] : acc2[k == 8 ? 0 : 7 - k][m].x) * inv_c, slope);
+              const float v1 = lrelu((k == 0 ? accR[m] : acc2[k == 0 ? 0 : 8 - k][m].y) * inv_c, slope);
+              if (ok0) dst[0] = v0;
+              if (ok1) dst[1] = v1;
+              dst += plane9;
+            }
+          }
         }
       }
     }
