@@ -73,6 +73,12 @@ int qpwc_corr_bwd(const float* prv, const float* nxt, const float* out, const fl
 int qpwc_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
                   int mode, void* stream);
 
+/* The same layers under data_format='channels_first' (warp.py:36-40 transposes around gather_nd;
+ * layers.py:179-183), natively: img (B,C,H,W), flow (B,2,H,W) with plane 0 = x, out (B,C,H,W);
+ * the flow is multiplied by flow_scale first (1.0 for Warp/WarpV2). */
+int qpwc_warp_fwd_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W,
+                       int mode, float flow_scale, void* stream);
+
 /* Gradient of the above: g_img (zero-filled here, then scatter-added) and g_flow. */
 int qpwc_warp_bwd(const float* img, const float* flow, const float* g_out, float* g_img,
                   float* g_flow, int B, int H, int W, int C, int mode, void* stream);

@@ -34,6 +34,8 @@ def warp(inputs, mode, fmt):
     if img.dim() != 4:
         # tf_warp only defines `is_batch` for rank-4 input (qpwcnet/core/warp.py:75-80)
         raise ValueError("warp expects batched rank-4 input, got shape {}".format(tuple(img.shape)))
+    if fmt == "channels_first" and img.is_cuda:
+        return ops.warp_nchw(img, flo, mode)                                # native NCHW kernel
     out = ops.warp(to_nhwc(img, fmt), to_nhwc(flo, fmt), mode)
     return from_nhwc(out, fmt)
 

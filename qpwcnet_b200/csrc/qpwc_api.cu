@@ -16,6 +16,7 @@ int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int,
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_fwd_ex(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
 int launch_upsample2x_fwd(const float*, float*, int, int, int, int, float, cudaStream_t);
+int launch_warp_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_corr_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_upsample2x_bwd(const float*, float*, int, int, int, int, float, cudaStream_t);
 int launch_warp_bwd_ex(const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
@@ -300,6 +301,16 @@ int qpwc_corr_fwd_nchw(const float* prv, const float* nxt, float* out, int B, in
     return set_error(QPWC_ERR_UNSUPPORTED, "%s: native channels_first kernel needs search_range 4, W %% 4 == 0 and 16-byte aligned tensors "
                                            "(transpose to NHWC and call qpwc_corr_fwd instead)", fn);
   return rc;
+}
+
+int qpwc_warp_fwd_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W,
+                       int mode, float flow_scale, void* stream) {
+  const char* fn = "qpwc_warp_fwd_nchw";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
+  return launch_warp_fwd_nchw(img, flow, out, B, C, H, W, mode, flow_scale, (cudaStream_t)stream);
 }
 
 static int check_up(const char* fn, int H, int W, float up_scale) {

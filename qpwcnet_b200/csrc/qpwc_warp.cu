@@ -108,6 +108,46 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------- channels_first fwd
+// img (B,C,H,W), flow (B,2,H,W) (plane 0 = x, plane 1 = y), out (B,C,H,W).  One thread per pixel:
+// the taps are set up once and every channel plane is sampled with them -- consecutive lanes are
+// consecutive columns, so each of the four gathers of a plane is (flow noise aside) one coalesced
+// row segment.  Same per-element arithmetic as the NHWC kernel (bit-identical results).
+template <int MODE>
+__global__ void __launch_bounds__(256) warp_fwd_nchw_kernel(const float* __restrict__ img,
+                                                            const float* __restrict__ flow,
+                                                            float* __restrict__ out, int C, int H, int W,
+                                                            float scale) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= W) return;
+  const int i = blockIdx.y;
+  const size_t plane = (size_t)H * W;
+  const size_t pix = (size_t)i * W + j;
+  const float* fb = flow + (size_t)blockIdx.z * 2 * plane;
+  const float fx = __fmul_rn(scale, __ldg(fb + pix)), fy = __fmul_rn(scale, __ldg(fb + plane + pix));
+  const Taps t = make_taps<MODE>(i, j, fx, fy, H, W);
+  const float* src = img + (size_t)blockIdx.z * C * plane;
+  float* dst = out + (size_t)blockIdx.z * C * plane + pix;
+#pragma unroll 4
+  for (int c = 0; c < C; ++c, src += plane, dst += plane)
+    *dst = blend<MODE>(t, __ldg(src + t.o00), __ldg(src + t.o01), __ldg(src + t.o10), __ldg(src + t.o11));
+}
+
+int launch_warp_fwd_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W,
+                         int mode, float scale, cudaStream_t stream) {
+  if ((long long)B * C * H * W == 0) return QPWC_OK;
+  if (H > 65535 || B > 65535) return set_error(QPWC_ERR_UNSUPPORTED, "warp_fwd_nchw: H or B > 65535");
+  const dim3 grid((unsigned)cdiv(W, 256), (unsigned)H, (unsigned)B);
+  if (mode == QPWC_MODE_TF) {
+    auto k = warp_fwd_nchw_kernel<QPWC_MODE_TF>;
+    QPWC_LAUNCH(k, grid, 256, 0, stream, img, flow, out, C, H, W, scale);
+  } else {
+    auto k = warp_fwd_nchw_kernel<QPWC_MODE_TFA>;
+    QPWC_LAUNCH(k, grid, 256, 0, stream, img, flow, out, C, H, W, scale);
+  }
+  return check_launch("warp_fwd_nchw");
+}
+
 // ------------------------------------------------------------------------------------------ bwd
 // G lanes per pixel (power of two, <= 32).  Lane l of a group handles channel vectors l, l+G, ...
 // grid = (ceil(W / groups_per_block), H, B): row and batch come from the block index (32-bit maths).

@@ -268,6 +268,30 @@ class _CostVolumeNCHW(torch.autograd.Function):
         return g_prv.permute(0, 3, 1, 2).contiguous(), g_nxt.permute(0, 3, 1, 2).contiguous(), None, None
 
 
+class _WarpNCHW(torch.autograd.Function):
+    """channels_first warp: native NCHW forward kernel; the backward transposes to NHWC and uses the
+    scatter kernel."""
+
+    @staticmethod
+    def forward(ctx, img, flow, mode):
+        B, C, H, W = img.shape
+        out = torch.empty_like(img)
+        vi, vf = _views(img, flow)
+        with _on_device(img.device):
+            check(lib().qpwc_warp_fwd_nchw(vi.ptr, vf.ptr, out.data_ptr(), B, C, H, W, mode, 1.0,
+                                           _stream_ptr(img.device)))
+        ctx.save_for_backward(img, flow)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        img, flow = ctx.saved_tensors
+        nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+        g_img, g_flow = _warp_bwd(nhwc(img), nhwc(flow), nhwc(g_out), ctx.mode)
+        return g_img.permute(0, 3, 1, 2).contiguous(), g_flow.permute(0, 3, 1, 2).contiguous(), None
+
+
 class _Warp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, flow, mode):
@@ -450,6 +474,22 @@ def cost_volume_nchw(prv, nxt, search_range: int = 4, leaky_slope: float = 0.1):
     if not prv.is_cuda:
         raise ValueError("cost_volume_nchw needs CUDA tensors")
     return _CostVolumeNCHW.apply(prv.contiguous(), nxt.contiguous(), int(search_range), float(leaky_slope))
+
+
+def warp_nchw(img, flow, mode="tfa"):
+    """``warp`` for channels_first tensors: img (B,C,H,W), flow (B,2,H,W) (plane 0 = x) -> (B,C,H,W),
+    through the native NCHW kernel."""
+    if img.dim() != 4 or flow.dim() != 4 or flow.shape[1] != 2 or img.shape[0] != flow.shape[0] \
+            or img.shape[2:] != flow.shape[2:] or img.device != flow.device:
+        raise ValueError(f"warp_nchw: img {tuple(img.shape)}@{img.device} vs flow {tuple(flow.shape)}@{flow.device}")
+    if img.dtype != torch.float32 or flow.dtype != torch.float32:
+        raise TypeError("warp_nchw expects float32 tensors")
+    if not img.is_cuda:
+        raise ValueError("warp_nchw needs CUDA tensors")
+    m = _mode(mode)
+    if m == 1 and (img.shape[2] < 2 or img.shape[3] < 2):
+        raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
+    return _WarpNCHW.apply(img.contiguous(), flow.contiguous(), m)
 
 
 def warp(img, flow, mode="tfa", flow_scale: float = 1.0):

@@ -316,6 +316,29 @@ def test_cost_volume_channels_first_native(B, C, H, W):
     assert_rel(host(o2).transpose(0, 2, 3, 1), ref2)
 
 
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 24, 40), (1, 3, 9, 11), (1, 256, 14, 32), (1, 7, 33, 35)])
+def test_warp_channels_first_native(mode, B, C, H, W):
+    """Warp / WarpV2 with data_format='channels_first' (warp.py:36-40, layers.py:179-183): native NCHW
+    forward kernel, bit-exact against the oracle; gradients through the transposing route."""
+    from qpwcnet_b200.core import layers
+    r = rng(800 + C)
+    img = r.random((B, C, H, W)).astype(np.float32)
+    flo = (r.standard_normal((B, 2, H, W)) * 3).astype(np.float32)
+    ti, tf_ = dev(img).requires_grad_(), dev(flo).requires_grad_()
+    layer = (layers.Warp if mode == "tf" else layers.WarpV2)(data_format="channels_first")
+    out = layer((ti, tf_))
+    ref = oracle.warp(img.transpose(0, 2, 3, 1), flo.transpose(0, 2, 3, 1), mode)
+    np.testing.assert_array_equal(host(out).transpose(0, 2, 3, 1), ref)
+    g = r.standard_normal((B, C, H, W)).astype(np.float32)
+    gi, gf = torch.autograd.grad(out, (ti, tf_), dev(g))
+    a = [x.transpose(0, 2, 3, 1) for x in (img, flo, g)]
+    gi64, gf64 = oracle.warp_bwd(*(np.ascontiguousarray(x).astype(np.float64) for x in a), mode)
+    gi32, gf32 = oracle.warp_bwd(*(np.ascontiguousarray(x) for x in a), mode)
+    assert_as_accurate(host(gi).transpose(0, 2, 3, 1), gi32, gi64)
+    assert_as_accurate(host(gf).transpose(0, 2, 3, 1), gf32, gf64, floor=1e-6 * max(1.0, C / 8))
+
+
 def test_golden_fixtures():
     g = np.load(os.path.join(GOLD, "qpwc_golden.npz"))
     for name in ("cv_a", "cv_b", "cv_c", "cv_d"):
