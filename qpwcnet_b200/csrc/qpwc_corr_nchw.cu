@@ -23,15 +23,16 @@
 
 namespace qpwc {
 
+template <int TH_>
 struct NchwCfg {
   static constexpr int D = 4, Q = 9, NDISP = 81;
-  static constexpr int TH = 4, NCOLS = 128, TW = NCOLS - 2 * D;   // 120 valid pixel columns per tile
+  static constexpr int TH = TH_, NCOLS = 128, TW = NCOLS - 2 * D;   // 120 valid pixel columns per tile
   static constexpr int PCOLS = NCOLS + 2 * D;                     // first-frame columns j0-8 .. j0+127
   static constexpr int KC = 8, NROW = TH + 2 * D;
-  static constexpr int NST = 3;
-  static constexpr int N_BYTES = KC * NROW * NCOLS * 4;           // 49152
-  static constexpr int P_BYTES = KC * TH * PCOLS * 4;             // 17408
-  static constexpr int STAGE_BYTES = N_BYTES + P_BYTES;           // 66560
+  static constexpr int NST = TH_ <= 2 ? 4 : 3;
+  static constexpr int N_BYTES = KC * NROW * NCOLS * 4;           // TH = 4: 49152
+  static constexpr int P_BYTES = KC * TH * PCOLS * 4;             //         17408
+  static constexpr int STAGE_BYTES = N_BYTES + P_BYTES;           //         66560
   static constexpr int OFF_BARS = NST * STAGE_BYTES;
   static constexpr int SMEM_BYTES = OFF_BARS + 2 * NST * 8;
   static constexpr int NCONS = TH * (NCOLS / 2), NPROD = 128, NTHREADS = NCONS + NPROD;
@@ -41,11 +42,11 @@ struct NchwCfg {
   static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536, "register budget");
 };
 
-__global__ void __launch_bounds__(NchwCfg::NTHREADS, 1)
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::NTHREADS, 1)
 corr_fwd_nchw_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CONSTANT TensorMap tmN,
                      float* __restrict__ out, int B, int H, int W, int C, float slope,
                      int tiles_x, int tiles_y, int ntiles) {
-  using Cfg = NchwCfg;
   constexpr int D = Cfg::D, Q = Cfg::Q, TH = Cfg::TH, TW = Cfg::TW, NST = Cfg::NST, KC = Cfg::KC;
   constexpr int NCOLS = Cfg::NCOLS, PCOLS = Cfg::PCOLS, NROW = Cfg::NROW, NCONS = Cfg::NCONS;
 
@@ -186,14 +187,9 @@ corr_fwd_nchw_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CON
 // -------------------------------------------------------------------------------------- host
 int sm_count_cached();  // qpwc_corr_tiled.cu
 
-int launch_corr_fwd_nchw(const float* prv, const float* nxt, float* out, int B, int C, int H, int W,
-                         int d, float slope, cudaStream_t stream) {
-  using Cfg = NchwCfg;
-  // domain: d == 4, W a multiple of 4 (TMA strides are multiples of 16 bytes; 8-byte output stores),
-  // 16-byte aligned inputs, 8-byte aligned output
-  if (d != 4 || (W & 3) || C < 1) return QPWC_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15) || (reinterpret_cast<uintptr_t>(out) & 7))
-    return QPWC_ERR_UNSUPPORTED;
+template <class Cfg>
+static int run_nchw(const float* prv, const float* nxt, float* out, int B, int C, int H, int W, float slope,
+                    cudaStream_t stream) {
   TensorMap tmP, tmN;
   if (!make_tmap_nchw(&tmP, prv, B, C, H, W, Cfg::PCOLS, Cfg::TH, Cfg::KC)) return QPWC_ERR_CUDA;
   if (!make_tmap_nchw(&tmN, nxt, B, C, H, W, Cfg::NCOLS, Cfg::NROW, Cfg::KC)) return QPWC_ERR_CUDA;
@@ -202,9 +198,9 @@ int launch_corr_fwd_nchw(const float* prv, const float* nxt, float* out, int B, 
   if (nt >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
   const int ntiles = (int)nt;
   const int grid = ntiles < sm_count_cached() ? ntiles : sm_count_cached();
-  auto k = corr_fwd_nchw_kernel;
+  auto k = corr_fwd_nchw_kernel<Cfg>;
 #ifndef QPWC_EMU
-  static unsigned attr_done = 0;  // one bit per device (the attribute is per device)
+  static unsigned attr_done = 0;  // per instantiation, one bit per device (the attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_done >> (dev & 31) & 1u)) {
@@ -215,6 +211,19 @@ int launch_corr_fwd_nchw(const float* prv, const float* nxt, float* out, int B, 
 #endif
   QPWC_LAUNCH(k, grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream, tmP, tmN, out, B, H, W, C, slope, tiles_x, tiles_y, ntiles);
   return check_launch("corr_fwd_nchw");
+}
+
+int launch_corr_fwd_nchw(const float* prv, const float* nxt, float* out, int B, int C, int H, int W,
+                         int d, float slope, cudaStream_t stream) {
+  // domain: d == 4, W a multiple of 4 (TMA strides are multiples of 16 bytes; 8-byte output stores),
+  // 16-byte aligned inputs, 8-byte aligned output
+  if (d != 4 || (W & 3) || C < 1) return QPWC_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15) || (reinterpret_cast<uintptr_t>(out) & 7))
+    return QPWC_ERR_UNSUPPORTED;
+  // few tiles (coarse pyramid levels): 2-row tiles double the number of busy SMs
+  const long long tiles4 = (long long)cdiv(W, 120) * cdiv(H, 4) * B;
+  if (tiles4 * 2 <= sm_count_cached()) return run_nchw<NchwCfg<2>>(prv, nxt, out, B, C, H, W, slope, stream);
+  return run_nchw<NchwCfg<4>>(prv, nxt, out, B, C, H, W, slope, stream);
 }
 
 }  // namespace qpwc

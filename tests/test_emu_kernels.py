@@ -131,7 +131,7 @@ def test_emu_corr_fwd_rowpair(B, H, W, C, monkeypatch):
     np.testing.assert_allclose(got, old, rtol=0, atol=2e-6 * np.abs(ref).max())
 
 
-@pytest.mark.parametrize("B,C,H,W", [(1, 8, 7, 124), (2, 12, 9, 60), (1, 3, 5, 252), (1, 20, 16, 16)])
+@pytest.mark.parametrize("B,C,H,W", [(1, 8, 7, 124), (2, 12, 9, 60), (1, 3, 5, 252), (1, 20, 16, 16), (1, 8, 3, 16)])   # last: 2-row tiles
 def test_emu_corr_fwd_nchw(B, C, H, W):
     """Native channels_first kernel (qpwc_corr_nchw.cu): planar TMA tiles, pixel-pair FFMA2, direct
     NCHW stores; ragged tiles (W not a multiple of 120), odd heights, channel tails."""
