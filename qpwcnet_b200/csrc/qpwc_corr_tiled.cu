@@ -34,8 +34,10 @@ namespace qpwc {
 template <int TH_, int WARP_, int MODE_, int PACKED_ = 0>
 struct TiledCfg {
   // PACKED: accumulate with packed fp32 FMAs (FFMA2, sm_100): even-/odd-channel partial sums kept
-  // as register pairs.  A 3-register scalar FFMA issues at ~0.55/clk/SMSP on B200 (register-file
-  // port limit, measured: tools/ubench/ffma_bench.cu); FFMA2 sustains ~1.0 FMA/clk/SMSP.
+  // as register pairs (162 accumulator registers).  Measured on B200 (tools/ubench): FFMA2 issues
+  // every 2.2-2.3 clk/SMSP, a scalar 3-register FFMA every 1.22 clk, and with its shared-memory
+  // loads the scalar 81-accumulator loop sustains 0.70 FMA/lane/clk against 0.60 for this packed
+  // loop -- the scalar consumer (PACKED = 0) is the default, the packed one is kept for A/B runs.
   static constexpr int PACKED = PACKED_;
   static constexpr int D = 4, Q = 2 * D + 1, NDISP = Q * Q;
   static constexpr int TH = TH_, TWT = 64, TW = TWT - 2 * D;  // 56 pixel columns per tile

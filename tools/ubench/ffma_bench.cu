@@ -1,4 +1,6 @@
-// Micro-benchmark (dev tool): issue cost of the 9x9 outer-product step in three formulations.
+// Micro-benchmark (dev tool, first half of round 1): issue cost of the 9x9 outer-product step in three
+// formulations.  NOTE: K1 issues its four FMAs per accumulator back to back (dependent), so its "scalar"
+// figure is latency-, not issue-bound; ffma2_patterns.cu / corr_loop_bench.cu supersede these numbers.
 //   K1 scalar FFMA, float4 operands               (current kernel's inner step)
 //   K2 FFMA2, accumulator pairs over m (rows), duplicated a                ("m-pairs")
 //   K3 FFMA2, even/odd-channel accumulator pairs, 5x9 outputs per thread   ("even/odd")
