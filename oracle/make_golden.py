@@ -84,5 +84,33 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def extras():
+    """Fixtures for the entry points added on top of the first set (own file and RNG stream, so the
+    first file stays byte-identical): Upsample (non_layers.py:183-193), FrameInterpolate's half-flow
+    warp pair (non_layers.py:303-311) and the warp fed by the upsampled coarse flow (pwcnet.py:49-56)."""
+    r = np.random.default_rng(20261019)
+    fx = {}
+    for name, (B, H, W, C) in {"up_a": (2, 5, 7, 2), "up_b": (1, 4, 6, 3)}.items():
+        x = f32(r.standard_normal((B, H, W, C)))
+        y = oracle.upsample2x(x.astype(np.float64), 2.0)
+        g = f32(r.standard_normal(y.shape))
+        fx.update({f"{name}/x": x, f"{name}/out": y, f"{name}/g_out": g,
+                   f"{name}/g_x": oracle.upsample2x_bwd(g.astype(np.float64), 2.0)})
+    for name, (B, H, W, C) in {"pair_a": (1, 8, 10, 4), "pair_b": (2, 6, 6, 3)}.items():
+        prv, nxt = f32(r.random((B, H, W, C))), f32(r.random((B, H, W, C)))
+        f01, f10 = f32(r.standard_normal((B, H, W, 2)) * 3), f32(r.standard_normal((B, H, W, 2)) * 3)
+        fc = f32(r.standard_normal((B, H // 2, W // 2, 2)) * 1.5)
+        fx.update({f"{name}/prv": prv, f"{name}/nxt": nxt, f"{name}/flo_01": f01, f"{name}/flo_10": f10,
+                   f"{name}/flow_coarse": fc})
+        up = oracle.upsample2x(fc.astype(np.float64), 2.0)
+        for mode in oracle.MODES:
+            fx[f"{name}/{mode}/prv_w"] = oracle.warp(prv.astype(np.float64), 0.5 * f10.astype(np.float64), mode)
+            fx[f"{name}/{mode}/nxt_w"] = oracle.warp(nxt.astype(np.float64), 0.5 * f01.astype(np.float64), mode)
+            fx[f"{name}/{mode}/nxt_up_w"] = oracle.warp(nxt.astype(np.float64), up, mode)
+    np.savez_compressed(os.path.join(OUT, "qpwc_golden_extras.npz"), **fx)
+
+
 if __name__ == "__main__":
-    main()
+    if "--extras-only" not in sys.argv:
+        main()
+    extras()

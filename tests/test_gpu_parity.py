@@ -372,6 +372,28 @@ def test_golden_fixtures():
             assert_rel(host(gf), g[f"{name}/{mode}/g_flow"], floor=1e-3)
 
 
+def test_golden_extras():
+    """Committed fixtures for Upsample, the FrameInterpolate warp pair and the warp fed by the
+    upsampled coarse flow (tests/golden/qpwc_golden_extras.npz)."""
+    g = np.load(os.path.join(GOLD, "qpwc_golden_extras.npz"))
+    for name in ("up_a", "up_b"):
+        tx = dev(g[f"{name}/x"]).requires_grad_()
+        y = ops.upsample2x(tx, 2.0)
+        np.testing.assert_allclose(host(y), g[f"{name}/out"], rtol=0, atol=1e-6)
+        (gx,) = torch.autograd.grad(y, (tx,), dev(g[f"{name}/g_out"]))
+        np.testing.assert_allclose(host(gx), g[f"{name}/g_x"], rtol=0, atol=2e-6)
+    for name in ("pair_a", "pair_b"):
+        prv, nxt = dev(g[f"{name}/prv"]), dev(g[f"{name}/nxt"])
+        C = prv.shape[-1]
+        for mode in ("tf", "tfa"):
+            pair = host(ops.half_flow_warps(prv, nxt, dev(g[f"{name}/flo_01"]), dev(g[f"{name}/flo_10"]), mode))
+            # vs exact arithmetic: limited by the fp32 rounding of the sampling coordinate
+            np.testing.assert_allclose(pair[..., :C], g[f"{name}/{mode}/prv_w"], rtol=0, atol=1e-5)
+            np.testing.assert_allclose(pair[..., C:], g[f"{name}/{mode}/nxt_w"], rtol=0, atol=1e-5)
+            wu = host(ops.warp_up(nxt, dev(g[f"{name}/flow_coarse"]), mode))
+            np.testing.assert_allclose(wu, g[f"{name}/{mode}/nxt_up_w"], rtol=0, atol=1e-5)
+
+
 def test_golden_cfg1():
     c = np.load(os.path.join(GOLD, "qpwc_cfg1.npz"))
     r1 = np.random.default_rng(int(c["seed"]))

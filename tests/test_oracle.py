@@ -258,3 +258,21 @@ def test_upsample2x_oracle_matches_torch_half_pixel_rule_and_adjoint():
     assert abs((y * g).sum() - (x * gi).sum()) < 1e-10
     x32 = x.astype(np.float32)
     assert np.abs(oracle.upsample2x(x32, 2.0) - y).max() < 2e-6
+
+
+def test_oracle_reproduces_extras_golden():
+    """tests/golden/qpwc_golden_extras.npz (oracle/make_golden.py --extras-only): Upsample, the
+    half-flow warp pair and the warp on the upsampled coarse flow."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qpwc_golden_extras.npz"))
+    for name in ("up_a", "up_b"):
+        x = g[f"{name}/x"].astype(np.float64)
+        np.testing.assert_allclose(oracle.upsample2x(x, 2.0), g[f"{name}/out"], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(oracle.upsample2x_bwd(g[f"{name}/g_out"].astype(np.float64), 2.0), g[f"{name}/g_x"], rtol=0, atol=1e-13)
+    for name in ("pair_a", "pair_b"):
+        up = oracle.upsample2x(g[f"{name}/flow_coarse"].astype(np.float64), 2.0)
+        for mode in oracle.MODES:
+            np.testing.assert_allclose(oracle.warp(g[f"{name}/prv"].astype(np.float64), 0.5 * g[f"{name}/flo_10"].astype(np.float64), mode),
+                                       g[f"{name}/{mode}/prv_w"], rtol=0, atol=1e-14)
+            np.testing.assert_allclose(oracle.warp(g[f"{name}/nxt"].astype(np.float64), up, mode),
+                                       g[f"{name}/{mode}/nxt_up_w"], rtol=0, atol=1e-14)
