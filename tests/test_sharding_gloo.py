@@ -73,7 +73,7 @@ def test_bench_reference_arm_runs_on_rank0_only(tmp_path):
 
 
 # ------------------------------------------------------------------ row-sharded single frame (config 5)
-def _halo_worker(rank, world, port, q):
+def _halo_worker(rank, world, port, q, H=41):
     sys.path.insert(0, ROOT)
     import oracle
     from qpwcnet_b200 import sharded
@@ -81,7 +81,7 @@ def _halo_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     r = np.random.default_rng(7)
-    B, H, W, C, d = 1, 41, 9, 4, 4
+    B, W, C, d = 1, 9, 4, 4
     prv = r.standard_normal((B, H, W, C)).astype(np.float32)
     nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
     flo = (r.standard_normal((B, H, W, 2)) * 1.5).astype(np.float32)
@@ -109,11 +109,11 @@ def _halo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def _run_halo(world):
+def _run_halo(world, H=41):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q, H)) for r in range(world)]
     for p in procs:
         p.start()
     got = sorted(q.get(timeout=180) for _ in range(world))
@@ -124,7 +124,7 @@ def _run_halo(world):
     for rank, r0, r1, ok_cv, ok_tf, ok_tfa in got:
         assert ok_cv and ok_tf and ok_tfa, f"rank {rank} rows [{r0},{r1})"
         rows += r1 - r0
-    assert rows == 41
+    assert rows == H
 
 
 def test_row_sharded_halo_exchange_world_2():
@@ -133,3 +133,12 @@ def test_row_sharded_halo_exchange_world_2():
 
 def test_row_sharded_halo_exchange_world_3():
     _run_halo(3)          # the middle rank has two neighbours
+
+
+def test_row_sharded_thin_bands_fall_back_to_all_gather():
+    """Bands thinner than the halo (coarse levels of a frame cut into many bands, BASELINE config 5 on
+    8 GPUs: 68 rows / 8): the neighbour exchange is replaced by an all-gather of the bands.  World 4:
+    H = 41 -> 10-row bands vs the fused op's ~11-row halo; H = 13 -> 3-row bands vs the 4-row halo of
+    the plain cost volume."""
+    _run_halo(4)
+    _run_halo(4, H=13)
