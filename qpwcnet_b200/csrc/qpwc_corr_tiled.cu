@@ -286,7 +286,10 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
   } else {
     // ========================================================================== consumers
     setmaxnreg_inc<Cfg::REG_CONS>();
-    const int ti = tid / NCOL, tc = tid % NCOL, lane = tid & 31;
+    // warp w owns columns (w / TH) * 32 .. +31 of tile row w % TH: the two half-row warps of a row
+    // sit on the same SM sub-partition (w and w + TH, TH even), so in a ragged tile whose right half
+    // is dead (see dead_warp below) every sub-partition keeps exactly one live warp
+    const int lane = tid & 31, ti = (tid >> 5) % TH, tc = ((tid >> 5) / TH) * 32 + lane;
     // byte offsets inside a stage (channel quad 0; quad q = offset ^ (q << 4), see swz<>)
     // column part of the second-frame operand offset (the swizzle depends on the column only: the
     // row pitch is a multiple of the swizzle period); the row part is brow[m], per tile
@@ -320,11 +323,15 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
 #pragma unroll
         for (int k = 0; k < Q; ++k) { acc[m][k] = 0.f; acc2[m][k] = make_float2(0.f, 0.f); }
 
+      // pixel columns of this warp's accumulators: lp = tc - k in [(tc & ~31) - 8, (tc | 31)]
+      const bool dead_warp = (tc & ~31) - (Q - 1) >= min(TW, W - j0);
       for (int c = 0; c < nchunks; ++c, ++g) {
         const int stage = fixed_stage ? c : (int)(g % NST);
         if (!(ablate & 4)) mbar_wait(&full[stage], fixed_stage ? (ctile & 1u) : ((g / NST) & 1u));
         const unsigned char* sb = smem + stage * Cfg::STAGE_BYTES;
-        if (!(ablate & 1))
+        // a warp none of whose columns reaches a valid pixel of a ragged tile (e.g. W = 512: the last
+        // tile column is 8 pixels wide, so columns 32..63 feed nothing) only keeps the pipeline going
+        if (!(ablate & 1) && !dead_warp)
 #pragma unroll
         for (int qd = 0; qd < Cfg::NQ; ++qd) {
           const unsigned char* nbp = sb + (nb_off ^ (uint32_t)(qd << 4));
