@@ -64,6 +64,7 @@ template <> __device__ __forceinline__ void vatomic_add<1>(float* p, const float
 // `scale` first (0.5 * flo; one rounded multiply, exactly the reference's op), the output pixel
 // stride `ops` may exceed C (channel slice of a concat buffer), and batch entries z >= bsplit take
 // a second (image, flow) pair and write C channels further -- two warps in one launch.
+#define WARP_FWD_ROWS 8
 template <int MODE, int V, int NV>  // NV channel vectors per thread (2: taps amortised over 32 bytes per tap)
 __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__ img,
                                                        const float* __restrict__ flow,
@@ -76,10 +77,12 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
   // up_scale * bilinear_x2(flow), interpolated here instead of being read back from HBM
   // (Upsample(scale=2.0) feeding UpFlow's warp, non_layers.py:183-193, pwcnet.py:49-56)
   const int CV = C / (V * NV);
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // j * CV + cv
-  if (idx >= W * CV) return;
+  // a block covers WARP_FWD_ROWS image rows x 64 (pixel, vector) slots: the bottom taps of one row are
+  // the top taps of the next, so vertically adjacent pixels share their source lines in L1
+  const int idx = blockIdx.x * (256 / WARP_FWD_ROWS) + (threadIdx.x % (256 / WARP_FWD_ROWS));  // j * CV + cv
+  const int i = blockIdx.y * WARP_FWD_ROWS + threadIdx.x / (256 / WARP_FWD_ROWS);
+  if (idx >= W * CV || i >= H) return;
   const int j = idx / CV, cv = idx - j * CV;
-  const int i = blockIdx.y;
   const bool second = (int)blockIdx.z >= bsplit;
   const int b = second ? (int)blockIdx.z - bsplit : (int)blockIdx.z;
   if (second) { img = img2; flow = flow2; }
@@ -285,14 +288,14 @@ static void run_warp_fwd_nv(const float* img, const float* flow, const float* im
   const int CV = C / (V * NV);
   auto k = warp_fwd_kernel<MODE, V, NV>;
   if (img2) {  // pair: grid.z = 2B (B <= 32767 checked by the caller)
-    const dim3 grid((unsigned)cdiv(W * CV, block), (unsigned)H, (unsigned)(2 * B));
+    const dim3 grid((unsigned)cdiv(W * CV, block / WARP_FWD_ROWS), (unsigned)cdiv(H, WARP_FWD_ROWS), (unsigned)(2 * B));
     QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, img2, flow2, out, H, W, C, B, scale, ops, up_scale);
     return;
   }
   // gridDim.y/z are limited to 65535: chunk the batch (and refuse absurd heights upstream)
   for (int b0 = 0; b0 < B; b0 += 65535) {
     const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
-    const dim3 grid((unsigned)cdiv(W * CV, block), (unsigned)H, (unsigned)nb);
+    const dim3 grid((unsigned)cdiv(W * CV, block / WARP_FWD_ROWS), (unsigned)cdiv(H, WARP_FWD_ROWS), (unsigned)nb);
     const size_t off = (size_t)b0 * H * W;
     const size_t foff = up_scale != 0.f ? (size_t)b0 * (H / 2) * (W / 2) * 2 : off * 2;
     QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + foff, img2, flow2, out + off * ops, H, W, C,
