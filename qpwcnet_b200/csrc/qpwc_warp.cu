@@ -93,21 +93,23 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
   else f = __ldg(reinterpret_cast<const float2*>(flow) + pix);    // ch0 = x, ch1 = y
   f.x = __fmul_rn(scale, f.x); f.y = __fmul_rn(scale, f.y);       // exact for scale == 1
   const Taps t = make_taps<MODE>(i, j, f.x, f.y, H, W);
-  const float* base = img + (size_t)b * H * W * C + (size_t)cv * (V * NV);
+  // vector n of lane cv is channel vector n*CV + cv: per load/store instruction the CV lanes of a
+  // pixel cover CV*V contiguous floats (whole 32-byte sectors), not every other 16 bytes
+  const float* base = img + (size_t)b * H * W * C + (size_t)cv * V;
   float v00[NV][V], v01[NV][V], v10[NV][V], v11[NV][V], o[NV][V];
 #pragma unroll
   for (int n = 0; n < NV; ++n) {
-    vload<V>(base + (size_t)t.o00 * C + n * V, v00[n]);
-    vload<V>(base + (size_t)t.o01 * C + n * V, v01[n]);
-    vload<V>(base + (size_t)t.o10 * C + n * V, v10[n]);
-    vload<V>(base + (size_t)t.o11 * C + n * V, v11[n]);
+    vload<V>(base + (size_t)t.o00 * C + n * CV * V, v00[n]);
+    vload<V>(base + (size_t)t.o01 * C + n * CV * V, v01[n]);
+    vload<V>(base + (size_t)t.o10 * C + n * CV * V, v10[n]);
+    vload<V>(base + (size_t)t.o11 * C + n * CV * V, v11[n]);
   }
-  float* dst = out + pix * (size_t)ops + (second ? C : 0) + (size_t)cv * (V * NV);
+  float* dst = out + pix * (size_t)ops + (second ? C : 0) + (size_t)cv * V;
 #pragma unroll
   for (int n = 0; n < NV; ++n) {
 #pragma unroll
     for (int k = 0; k < V; ++k) o[n][k] = blend<MODE>(t, v00[n][k], v01[n][k], v10[n][k], v11[n][k]);
-    vstore<V>(dst + n * V, o[n]);
+    vstore<V>(dst + n * CV * V, o[n]);
   }
 }
 
