@@ -105,6 +105,13 @@ int qpwc_warp_bwd_ex(const float* img, const float* flow, const float* g_out, fl
 int qpwc_upsample2x_fwd(const float* src, float* dst, int B, int H, int W, int C, float scale, void* stream);
 int qpwc_upsample2x_bwd(const float* g_dst, float* g_src, int B, int H, int W, int C, float scale, void* stream);
 
+/* estimate_occlusion_map(flow, data_format) -- qpwcnet/core/occlusion.py:27-118.  flow is
+ * (B,H,W,2) (channels_first = 0) or (B,2,H,W) (channels_first = 1), channel 0 = dx, 1 = dy;
+ * out (B,H,W) = max(oob, map3): oob = the flow target leaves the image (occlusion.py:74), map3 = 0
+ * where some pixel's naive inverse flow -tf_warp(flow, flow) lands (int cast, clipped), else 1
+ * (occlusion.py:83-96).  The self-warp is evaluated in registers; two launches on `stream`. */
+int qpwc_occlusion_map(const float* flow, float* out, int B, int H, int W, int channels_first, void* stream);
+
 /* The flow upsampling fused into its consumers (pwcnet.py:49-56: flo = Upsample(2.0)(flo) feeds
  * UpFlow): flow_coarse is (B,H/2,W/2,2); the kernels sample with up_scale * bilinear_x2(flow_coarse)
  * interpolated in registers, so the upsampled flow is not read back from HBM.  H, W (output size) even. */

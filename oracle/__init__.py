@@ -154,6 +154,24 @@ def warp_cost_volume_bwd(prv, nxt, flow, g_out, mode: str = "tfa", search_range:
 
 
 # ------------------------------------------------------------------ x2 bilinear upsampling (numpy)
+def occlusion_map(flow):
+    """estimate_occlusion_map (qpwcnet/core/occlusion.py:27-118) on an NHWC flow (B,H,W,2), fp32.
+    Parity unpinned (no TF here): a restatement on top of the pinned `warp(mode='tf')`."""
+    flow = _c(flow, np.float32)
+    B, H, W, _ = flow.shape
+    i, j = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    dj, di = flow[..., 0], flow[..., 1]                               # occlusion.py:59
+    i2, j2 = i + di, j + dj
+    oob = ((i2 < 0) | (i2 >= H) | (j2 < 0) | (j2 >= W)).astype(np.float32)   # occlusion.py:74
+    inv = -warp(flow, flow, "tf")                                     # occlusion.py:83
+    i3 = np.clip(np.trunc(i + inv[..., 1]), 0, H - 1).astype(np.int64)       # occlusion.py:85-90
+    j3 = np.clip(np.trunc(j + inv[..., 0]), 0, W - 1).astype(np.int64)
+    map3 = np.ones((B, H, W), np.float32)
+    b = np.broadcast_to(np.arange(B)[:, None, None], (B, H, W))
+    map3[b, i3, j3] = 0.0                                             # scatter-min of zeros, occlusion.py:92-93
+    return np.maximum(oob, map3)                                      # occlusion.py:96
+
+
 def _up2_coords(n_out, n_in, dtype):
     """tf.image.resize bilinear, half-pixel centres (ResizeBilinear kernel, restated from its
     published algorithm; TF is not installable here => parity for this op is UNPINNED):

@@ -19,6 +19,7 @@ int launch_upsample2x_fwd(const float*, float*, int, int, int, int, float, cudaS
 int launch_warp_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_corr_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_upsample2x_bwd(const float*, float*, int, int, int, int, float, cudaStream_t);
+int launch_occlusion_map(const float*, float*, int, int, int, int, cudaStream_t);
 int launch_warp_bwd_ex(const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
 int launch_corr_fwd_direct(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
 int launch_corr_bwd_direct(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
@@ -333,6 +334,16 @@ int qpwc_upsample2x_bwd(const float* g_dst, float* g_src, int B, int H, int W, i
   if (empty(B, H, W, C)) return QPWC_OK;
   QPWC_TRY(check_ptr(fn, "g_dst", g_dst)); QPWC_TRY(check_ptr(fn, "g_src", g_src));
   return launch_upsample2x_bwd(g_dst, g_src, B, H, W, C, scale, (cudaStream_t)stream);
+}
+
+int qpwc_occlusion_map(const float* flow, float* out, int B, int H, int W, int channels_first, void* stream) {
+  const char* fn = "qpwc_occlusion_map";
+  QPWC_TRY(check_shape(fn, B, H, W, 2));
+  if (empty(B, H, W, 2)) return QPWC_OK;
+  QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
+  if (!channels_first && reinterpret_cast<uintptr_t>(flow) % 8) return set_error(QPWC_ERR_INVALID, "%s: flow must be 8-byte aligned", fn);
+  if ((long long)H * W > 0x7fffffffLL) return set_error(QPWC_ERR_UNSUPPORTED, "%s: H*W exceeds 2^31-1", fn);
+  return launch_occlusion_map(flow, out, B, H, W, channels_first ? 1 : 0, (cudaStream_t)stream);
 }
 
 int qpwc_warp_fwd_up(const float* img, const float* flow_coarse, float* out, int B, int H, int W, int C,

@@ -523,6 +523,29 @@ def upsample2x(x, scale: float = 1.0):
     return _Upsample2x.apply(x, float(scale))
 
 
+def occlusion_map(flow, data_format: str = "channels_last"):
+    """``estimate_occlusion_map(flow, data_format)`` (qpwcnet/core/occlusion.py:27-118): (B,H,W)
+    float map, 1 where the next frame has no value -- the flow target leaves the image, or no
+    pixel's naive inverse flow ``-tf_warp(flow, flow)`` lands there.  ``flow``: (B,H,W,2), or
+    (B,2,H,W) for 'channels_first'; channel 0 = dx, 1 = dy.  Not differentiable (integer scatter)."""
+    if not isinstance(flow, torch.Tensor) or flow.dim() != 4:
+        raise ValueError("occlusion_map expects a batched rank-4 flow")
+    if flow.dtype != torch.float32:
+        raise TypeError("occlusion_map expects a float32 flow")
+    if not flow.is_cuda:
+        raise ValueError("occlusion_map needs a CUDA tensor")
+    cf = data_format == "channels_first"
+    if flow.shape[1 if cf else 3] != 2:
+        raise ValueError(f"occlusion_map: flow {tuple(flow.shape)} needs 2 channels ({data_format})")
+    flow = flow.detach().contiguous()
+    B = flow.shape[0]
+    H, W = (flow.shape[2], flow.shape[3]) if cf else (flow.shape[1], flow.shape[2])
+    out = torch.empty((B, H, W), dtype=torch.float32, device=flow.device)
+    with _on_device(flow.device):
+        check(lib().qpwc_occlusion_map(flow.data_ptr(), out.data_ptr(), B, H, W, int(cf), _stream_ptr(flow.device)))
+    return out
+
+
 def _check_coarse(img, flow_c, what):
     B, H, W, _ = img.shape
     if H % 2 or W % 2 or tuple(flow_c.shape) != (B, H // 2, W // 2, 2) or flow_c.device != img.device:

@@ -57,6 +57,15 @@ def corr_fwd_nchw(prv, nxt, d=4, slope=0.1):
     return out
 
 
+def occlusion_map(flow, channels_first=False):
+    flow = _f(flow)
+    B = flow.shape[0]
+    H, W = (flow.shape[2], flow.shape[3]) if channels_first else (flow.shape[1], flow.shape[2])
+    out = np.full((B, H, W), np.nan, np.float32)
+    _ck(lib().qpwc_occlusion_map(_p(flow), _p(out), B, H, W, int(channels_first), None))
+    return out
+
+
 def corr_bwd(prv, nxt, out, g_out, d=4, slope=0.1):
     prv, nxt, out, g_out = _f(prv), _f(nxt), _f(out), _f(g_out)
     B, H, W, C = prv.shape

@@ -216,3 +216,12 @@ print("ok")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-c", code, str(C)], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("B,H,W,sigma", [(2, 9, 13, 2.0), (1, 16, 24, 6.0), (1, 1, 5, 1.0), (1, 7, 1, 1.0)])
+def test_emu_occlusion_map(B, H, W, sigma):
+    """estimate_occlusion_map (occlusion.py:27-118): same map as the oracle, both layouts."""
+    flow = (rng(70 + H).standard_normal((B, H, W, 2)) * sigma).astype(np.float32)
+    ref = oracle.occlusion_map(flow)
+    np.testing.assert_array_equal(emu_lib.occlusion_map(flow), ref)
+    np.testing.assert_array_equal(emu_lib.occlusion_map(np.ascontiguousarray(flow.transpose(0, 3, 1, 2)), True), ref)

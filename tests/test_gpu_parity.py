@@ -608,3 +608,24 @@ def test_unaligned_and_odd_width_inputs():
     flo = dev(r.standard_normal((B, H, W, 2)))
     i_un = flat_p[1:].view(B, H, W, C); i_un.copy_(img)
     np.testing.assert_array_equal(host(ops.warp(i_un, flo, "tf")), oracle.warp(host(img), host(flo), "tf"))
+
+
+@pytest.mark.parametrize("B,H,W,sigma", [(2, 28, 64, 2.0), (1, 112, 256, 8.0), (3, 7, 5, 1.0), (1, 1, 9, 1.0), (1, 436, 1024, 12.0)])
+def test_occlusion_map(B, H, W, sigma):
+    """estimate_occlusion_map (occlusion.py:27-118): the map is a 0/1 integer decision, so the CUDA
+    path must reproduce the oracle exactly, in both data formats and through the core mirror."""
+    from qpwcnet_b200.core.occlusion import estimate_occlusion_map
+    flow = (rng(800 + H).standard_normal((B, H, W, 2)) * sigma).astype(np.float32)
+    ref = oracle.occlusion_map(flow)
+    t = dev(flow)
+    np.testing.assert_array_equal(host(ops.occlusion_map(t)), ref)
+    np.testing.assert_array_equal(host(estimate_occlusion_map(t, "channels_last")), ref)
+    np.testing.assert_array_equal(host(estimate_occlusion_map(t.permute(0, 3, 1, 2).contiguous(), "channels_first")), ref)
+    # the naive inverse flow really is -tf_warp(flow, flow): zero flow -> nothing occluded
+    assert float(ops.occlusion_map(torch.zeros_like(t)).abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        ops.occlusion_map(t[0])
+    with pytest.raises(ValueError):
+        ops.occlusion_map(t, "channels_first")
+    with pytest.raises(ValueError):
+        estimate_occlusion_map(t, "NHWC")

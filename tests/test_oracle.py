@@ -276,3 +276,32 @@ def test_oracle_reproduces_extras_golden():
                                        g[f"{name}/{mode}/prv_w"], rtol=0, atol=1e-14)
             np.testing.assert_allclose(oracle.warp(g[f"{name}/nxt"].astype(np.float64), up, mode),
                                        g[f"{name}/{mode}/nxt_up_w"], rtol=0, atol=1e-14)
+
+
+def test_occlusion_map_properties():
+    """estimate_occlusion_map (occlusion.py:27-118) restated on the pinned tf-mode warp."""
+    B, H, W = 2, 12, 17
+    # zero flow: every pixel is hit by its own inverse flow and nothing leaves the image
+    assert (oracle.occlusion_map(np.zeros((B, H, W, 2), np.float32)) == 0).all()
+    # a uniform shift by (+3, +2): sources whose target leaves the image are flagged (oob) ...
+    flow = np.zeros((B, H, W, 2), np.float32)
+    flow[..., 0], flow[..., 1] = 3.0, 2.0
+    m = oracle.occlusion_map(flow)
+    assert set(np.unique(m)) <= {0.0, 1.0}
+    assert (m[:, H - 2:, :] == 1).all() and (m[:, :, W - 3:] == 1).all()
+    # ... and an explicit evaluation of the definition agrees pixel by pixel on a random flow
+    r = np.random.default_rng(5)
+    flow = (r.standard_normal((1, 6, 8, 2)) * 2).astype(np.float32)
+    inv = -oracle.warp(flow, flow, "tf")
+    want = np.ones((6, 8), np.float32)
+    for i in range(6):
+        for j in range(8):
+            p = int(np.clip(np.trunc(np.float32(i) + inv[0, i, j, 1]), 0, 5))
+            q = int(np.clip(np.trunc(np.float32(j) + inv[0, i, j, 0]), 0, 7))
+            want[p, q] = 0
+    for i in range(6):
+        for j in range(8):
+            i2, j2 = np.float32(i) + flow[0, i, j, 1], np.float32(j) + flow[0, i, j, 0]
+            if i2 < 0 or i2 >= 6 or j2 < 0 or j2 >= 8:
+                want[i, j] = 1
+    np.testing.assert_array_equal(oracle.occlusion_map(flow)[0], want)
