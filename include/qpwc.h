@@ -105,6 +105,11 @@ int qpwc_warp_bwd_ex(const float* img, const float* flow, const float* g_out, fl
 int qpwc_upsample2x_fwd(const float* src, float* dst, int B, int H, int W, int C, float scale, void* stream);
 int qpwc_upsample2x_bwd(const float* g_dst, float* g_src, int B, int H, int W, int C, float scale, void* stream);
 
+/* Gradient of qpwc_warp_fwd_nchw: g_out (B,C,H,W) -> g_img (B,C,H,W) (zeroed here, accumulated with
+ * atomics like the NHWC kernel) and g_flow (B,2,H,W) (per-pixel sum over the channels in order). */
+int qpwc_warp_bwd_nchw(const float* img, const float* flow, const float* g_out, float* g_img,
+                       float* g_flow, int B, int C, int H, int W, int mode, float flow_scale, void* stream);
+
 /* estimate_occlusion_map(flow, data_format) -- qpwcnet/core/occlusion.py:27-118.  flow is
  * (B,H,W,2) (channels_first = 0) or (B,2,H,W) (channels_first = 1), channel 0 = dx, 1 = dy;
  * out (B,H,W) = max(oob, map3): oob = the flow target leaves the image (occlusion.py:74), map3 = 0

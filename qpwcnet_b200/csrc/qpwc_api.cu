@@ -19,6 +19,7 @@ int launch_upsample2x_fwd(const float*, float*, int, int, int, int, float, cudaS
 int launch_warp_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_corr_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_upsample2x_bwd(const float*, float*, int, int, int, int, float, cudaStream_t);
+int launch_warp_bwd_nchw(const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_occlusion_map(const float*, float*, int, int, int, int, cudaStream_t);
 int launch_warp_bwd_ex(const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
 int launch_corr_fwd_direct(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
@@ -312,6 +313,17 @@ int qpwc_warp_fwd_nchw(const float* img, const float* flow, float* out, int B, i
   QPWC_TRY(check_mode(fn, mode, H, W));
   QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
   return launch_warp_fwd_nchw(img, flow, out, B, C, H, W, mode, flow_scale, (cudaStream_t)stream);
+}
+
+int qpwc_warp_bwd_nchw(const float* img, const float* flow, const float* g_out, float* g_img,
+                       float* g_flow, int B, int C, int H, int W, int mode, float flow_scale, void* stream) {
+  const char* fn = "qpwc_warp_bwd_nchw";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, H, W));
+  QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "g_out", g_out));
+  QPWC_TRY(check_ptr(fn, "g_img", g_img)); QPWC_TRY(check_ptr(fn, "g_flow", g_flow));
+  return launch_warp_bwd_nchw(img, flow, g_out, g_img, g_flow, B, C, H, W, mode, flow_scale, (cudaStream_t)stream);
 }
 
 static int check_up(const char* fn, int H, int W, float up_scale) {

@@ -153,6 +153,98 @@ int launch_warp_fwd_nchw(const float* img, const float* flow, float* out, int B,
   return check_launch("warp_fwd_nchw");
 }
 
+// ------------------------------------------------------------------------- channels_first bwd
+// One thread per pixel, looping over the channel planes: consecutive lanes are consecutive columns,
+// so the g_out reads, the four tap gathers and the four atomics of a plane are (flow noise aside)
+// coalesced row segments, and the flow gradient is a per-thread sum over the channels in order -- no
+// cross-lane reduction.  Per-element arithmetic of warp_bwd_kernel (V = 1).  g_img pre-zeroed.
+template <int MODE>
+__global__ void __launch_bounds__(256) warp_bwd_nchw_kernel(const float* __restrict__ img,
+                                                            const float* __restrict__ flow,
+                                                            const float* __restrict__ g_out,
+                                                            float* __restrict__ g_img,
+                                                            float* __restrict__ g_flow, int C, int H, int W,
+                                                            float scale) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= W) return;
+  const int i = blockIdx.y;
+  const size_t plane = (size_t)H * W;
+  const size_t pix = (size_t)i * W + j;
+  const float* fb = flow + (size_t)blockIdx.z * 2 * plane;
+  const float fx = __fmul_rn(scale, __ldg(fb + pix)), fy = __fmul_rn(scale, __ldg(fb + plane + pix));
+  bool px = true, py = true;
+  Taps t;
+  if (MODE == QPWC_MODE_TF) t = taps_tf(i, j, fx, fy, H, W);
+  else t = taps_tfa(i, j, fx, fy, H, W, &px, &py);
+  float ax1 = 0.f, ax0 = 0.f, ay1 = 0.f, ay0 = 0.f;
+  if (MODE == QPWC_MODE_TF) {
+    const float x = __fadd_rn((float)j, fx), y = __fadd_rn((float)i, fy);
+    const int y0 = t.o00 / W, x0 = t.o00 - y0 * W, y1 = t.o11 / W, x1 = t.o11 - y1 * W;
+    ax1 = __fsub_rn((float)x1, x); ax0 = __fsub_rn(x, (float)x0);
+    ay1 = __fsub_rn((float)y1, y); ay0 = __fsub_rn(y, (float)y0);
+  }
+  const bool dupx = (MODE == QPWC_MODE_TF) && (t.o00 == t.o01);
+  const bool dupy = (MODE == QPWC_MODE_TF) && (t.o00 == t.o10);
+  const float* src = img + (size_t)blockIdx.z * C * plane;
+  const float* gsrc = g_out + (size_t)blockIdx.z * C * plane + pix;
+  float* gi = g_img + (size_t)blockIdx.z * C * plane;
+  float gx = 0.f, gy = 0.f;
+#pragma unroll 2
+  for (int c = 0; c < C; ++c, src += plane, gsrc += plane, gi += plane) {
+    const float v00 = __ldg(src + t.o00), v01 = __ldg(src + t.o01), v10 = __ldg(src + t.o10), v11 = __ldg(src + t.o11);
+    const float g = __ldg(gsrc);
+    float a00, a01, a10, a11;
+    if (MODE == QPWC_MODE_TF) {
+      a00 = __fmul_rn(t.w00, g); a10 = __fmul_rn(t.w10, g);
+      a01 = __fmul_rn(t.w01, g); a11 = __fmul_rn(t.w11, g);
+      const float sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-ay1, v00), __fmul_rn(-ay0, v10)),
+                                           __fmul_rn(ay1, v01)), __fmul_rn(ay0, v11));
+      const float sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-ax1, v00), __fmul_rn(ax1, v10)),
+                                           __fmul_rn(-ax0, v01)), __fmul_rn(ax0, v11));
+      gx = __fadd_rn(gx, __fmul_rn(g, sx));
+      gy = __fadd_rn(gy, __fmul_rn(g, sy));
+    } else {
+      const float ax = t.w00, ay = t.w01;
+      const float top = __fadd_rn(__fmul_rn(ax, __fsub_rn(v01, v00)), v00);
+      const float bot = __fadd_rn(__fmul_rn(ax, __fsub_rn(v11, v10)), v10);
+      gy = __fadd_rn(gy, __fmul_rn(g, __fsub_rn(bot, top)));
+      const float g_bot = __fmul_rn(ay, g);
+      const float g_top = __fsub_rn(g, g_bot);
+      gx = __fadd_rn(gx, __fadd_rn(__fmul_rn(g_top, __fsub_rn(v01, v00)), __fmul_rn(g_bot, __fsub_rn(v11, v10))));
+      const float g_tr = __fmul_rn(ax, g_top), g_br = __fmul_rn(ax, g_bot);
+      a01 = g_tr; a00 = __fsub_rn(g_top, g_tr); a11 = g_br; a10 = __fsub_rn(g_bot, g_br);
+    }
+    // clipped taps coincide (mode TF): fold in registers so that they cancel exactly (see below)
+    if (dupx) { a00 = __fadd_rn(a00, a01); a10 = __fadd_rn(a10, a11); }
+    if (dupy) { a00 = __fadd_rn(a00, a10); a01 = __fadd_rn(a01, a11); }
+    atomicAdd(gi + t.o00, a00);
+    if (!dupx) atomicAdd(gi + t.o01, a01);
+    if (!dupy) atomicAdd(gi + t.o10, a10);
+    if (!dupx && !dupy) atomicAdd(gi + t.o11, a11);
+  }
+  float* gf = g_flow + (size_t)blockIdx.z * 2 * plane + pix;
+  gf[0] = px ? __fmul_rn(scale, gx) : 0.f;
+  gf[plane] = py ? __fmul_rn(scale, gy) : 0.f;
+}
+
+int launch_warp_bwd_nchw(const float* img, const float* flow, const float* g_out, float* g_img,
+                         float* g_flow, int B, int C, int H, int W, int mode, float scale, cudaStream_t stream) {
+  const long long n = (long long)B * C * H * W;
+  if (n == 0) return QPWC_OK;
+  if (H > 65535 || B > 65535) return set_error(QPWC_ERR_UNSUPPORTED, "warp_bwd_nchw: H or B > 65535");
+  cudaError_t e = cudaMemsetAsync(g_img, 0, sizeof(float) * (size_t)n, stream);
+  if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "warp_bwd_nchw: memset g_img: %s", cudaGetErrorString(e));
+  const dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)B);
+  if (mode == QPWC_MODE_TF) {
+    auto k = warp_bwd_nchw_kernel<QPWC_MODE_TF>;
+    QPWC_LAUNCH(k, grid, 128, 0, stream, img, flow, g_out, g_img, g_flow, C, H, W, scale);
+  } else {
+    auto k = warp_bwd_nchw_kernel<QPWC_MODE_TFA>;
+    QPWC_LAUNCH(k, grid, 128, 0, stream, img, flow, g_out, g_img, g_flow, C, H, W, scale);
+  }
+  return check_launch("warp_bwd_nchw");
+}
+
 // ------------------------------------------------------------------------------------------ bwd
 // G lanes per pixel (power of two, <= 32).  Lane l of a group handles channel vectors l, l+G, ...
 // grid = (ceil(W / groups_per_block), H, B): row and batch come from the block index (32-bit maths).

@@ -269,8 +269,7 @@ class _CostVolumeNCHW(torch.autograd.Function):
 
 
 class _WarpNCHW(torch.autograd.Function):
-    """channels_first warp: native NCHW forward kernel; the backward transposes to NHWC and uses the
-    scatter kernel."""
+    """channels_first warp: native NCHW forward and backward kernels."""
 
     @staticmethod
     def forward(ctx, img, flow, mode):
@@ -287,9 +286,13 @@ class _WarpNCHW(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out):
         img, flow = ctx.saved_tensors
-        nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
-        g_img, g_flow = _warp_bwd(nhwc(img), nhwc(flow), nhwc(g_out), ctx.mode)
-        return g_img.permute(0, 3, 1, 2).contiguous(), g_flow.permute(0, 3, 1, 2).contiguous(), None
+        B, C, H, W = img.shape
+        g_out = g_out.contiguous()
+        g_img, g_flow = torch.empty_like(img), torch.empty_like(flow)
+        with _on_device(img.device):
+            check(lib().qpwc_warp_bwd_nchw(img.data_ptr(), flow.data_ptr(), g_out.data_ptr(), g_img.data_ptr(),
+                                           g_flow.data_ptr(), B, C, H, W, ctx.mode, 1.0, _stream_ptr(img.device)))
+        return g_img, g_flow, None
 
 
 class _Warp(torch.autograd.Function):

@@ -91,6 +91,23 @@ def warp_bwd(img, flow, g_out, mode):
     return gi, gf
 
 
+def warp_fwd_nchw(img, flow, mode):
+    img, flow = _f(img), _f(flow)
+    B, C, H, W = img.shape
+    out = np.full_like(img, np.nan)
+    _ck(lib().qpwc_warp_fwd_nchw(_p(img), _p(flow), _p(out), B, C, H, W, MODES[mode], ctypes.c_float(1.0), None))
+    return out
+
+
+def warp_bwd_nchw(img, flow, g_out, mode):
+    img, flow, g_out = _f(img), _f(flow), _f(g_out)
+    B, C, H, W = img.shape
+    gi, gf = np.full_like(img, np.nan), np.full_like(flow, np.nan)
+    _ck(lib().qpwc_warp_bwd_nchw(_p(img), _p(flow), _p(g_out), _p(gi), _p(gf), B, C, H, W, MODES[mode],
+                                 ctypes.c_float(1.0), None))
+    return gi, gf
+
+
 def warp_corr_fwd(prv, nxt, flow, mode, d=4, slope=0.1, ops=None):
     prv, nxt, flow = _f(prv), _f(nxt), _f(flow)
     B, H, W, C = prv.shape

@@ -225,3 +225,22 @@ def test_emu_occlusion_map(B, H, W, sigma):
     ref = oracle.occlusion_map(flow)
     np.testing.assert_array_equal(emu_lib.occlusion_map(flow), ref)
     np.testing.assert_array_equal(emu_lib.occlusion_map(np.ascontiguousarray(flow.transpose(0, 3, 1, 2)), True), ref)
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,C,H,W", [(2, 3, 6, 7), (1, 8, 5, 9), (1, 5, 2, 130)])
+def test_emu_warp_nchw_fwd_bwd(mode, B, C, H, W):
+    """channels_first warp (warp.py:36-40, layers.py:179-183): native kernels, forward + gradients."""
+    r = rng(80 + C)
+    img = r.random((B, C, H, W)).astype(np.float32)
+    flow = (r.standard_normal((B, 2, H, W)) * 2.5).astype(np.float32)
+    nhwc = lambda a: np.ascontiguousarray(a.transpose(0, 2, 3, 1))
+    np.testing.assert_array_equal(nhwc(emu_lib.warp_fwd_nchw(img, flow, mode)), oracle.warp(nhwc(img), nhwc(flow), mode))
+    g = r.standard_normal(img.shape).astype(np.float32)
+    gi, gf = oracle.warp_bwd(*(nhwc(a).astype(np.float64) for a in (img, flow, g)), mode)
+    gi2, gf2 = emu_lib.warp_bwd_nchw(img, flow, g, mode)
+    # far out-of-image samples extrapolate with large weights (mode tf): fp32 itself is then the
+    # limit, so the bound is the fp32 oracle's own distance from the fp64 one
+    gi32, gf32 = oracle.warp_bwd(*(nhwc(a) for a in (img, flow, g)), mode)
+    assert np.abs(nhwc(gi2) - gi).max() <= max(2e-6, 2 * np.abs(gi32 - gi).max())
+    assert np.abs(nhwc(gf2) - gf).max() <= max(1e-5, 2 * np.abs(gf32 - gf).max())

@@ -320,7 +320,7 @@ def test_cost_volume_channels_first_native(B, C, H, W):
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 24, 40), (1, 3, 9, 11), (1, 256, 14, 32), (1, 7, 33, 35)])
 def test_warp_channels_first_native(mode, B, C, H, W):
     """Warp / WarpV2 with data_format='channels_first' (warp.py:36-40, layers.py:179-183): native NCHW
-    forward kernel, bit-exact against the oracle; gradients through the transposing route."""
+    forward kernel, bit-exact against the oracle; gradients through the native NCHW scatter kernel."""
     from qpwcnet_b200.core import layers
     r = rng(800 + C)
     img = r.random((B, C, H, W)).astype(np.float32)
