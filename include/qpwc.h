@@ -105,6 +105,14 @@ int qpwc_warp_bwd_ex(const float* img, const float* flow, const float* g_out, fl
 int qpwc_upsample2x_fwd(const float* src, float* dst, int B, int H, int W, int C, float scale, void* stream);
 int qpwc_upsample2x_bwd(const float* g_dst, float* g_src, int B, int H, int W, int C, float scale, void* stream);
 
+/* Gradients of qpwc_corr_fwd_nchw (autodiff of the channels_first layer): out / g_out (B,81,H,W),
+ * g_prv / g_nxt (B,C,H,W), every element written exactly once (no atomics, no zero-init).  Same
+ * domain as the forward kernel (search_range 4, W % 4 == 0, 16-byte aligned tensors); returns
+ * QPWC_ERR_UNSUPPORTED otherwise (transpose to NHWC and call qpwc_corr_bwd). */
+int qpwc_corr_bwd_nchw(const float* prv, const float* nxt, const float* out, const float* g_out,
+                       float* g_prv, float* g_nxt, int B, int C, int H, int W, int search_range,
+                       float leaky_slope, void* stream);
+
 /* Gradient of qpwc_warp_fwd_nchw: g_out (B,C,H,W) -> g_img (B,C,H,W) (zeroed here, accumulated with
  * atomics like the NHWC kernel) and g_flow (B,2,H,W) (per-pixel sum over the channels in order). */
 int qpwc_warp_bwd_nchw(const float* img, const float* flow, const float* g_out, float* g_img,

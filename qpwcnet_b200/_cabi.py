@@ -60,6 +60,7 @@ def lib() -> ctypes.CDLL:
         "qpwc_warp_bwd_ex": ([fp, fp, fp, fp, fp, i, i, i, i, i, f, ll, vp], c_int),
         "qpwc_upsample2x_fwd": ([fp, fp, i, i, i, i, f, vp], c_int),
         "qpwc_upsample2x_bwd": ([fp, fp, i, i, i, i, f, vp], c_int),
+        "qpwc_corr_bwd_nchw": ([fp, fp, fp, fp, fp, fp, i, i, i, i, i, f, vp], c_int),
         "qpwc_warp_bwd_nchw": ([fp, fp, fp, fp, fp, i, i, i, i, i, f, vp], c_int),
         "qpwc_occlusion_map": ([fp, fp, i, i, i, i, vp], c_int),
         "qpwc_warp_fwd_up": ([fp, fp, fp, i, i, i, i, i, f, vp], c_int),
@@ -83,7 +84,7 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = (
     "qpwc_version", "qpwc_last_error", "qpwc_corr_fwd", "qpwc_corr_fwd_nchw", "qpwc_corr_bwd", "qpwc_warp_fwd",
-    "qpwc_warp_fwd_nchw", "qpwc_warp_bwd", "qpwc_warp_fwd_ex", "qpwc_warp_pair_fwd", "qpwc_warp_bwd_ex", "qpwc_upsample2x_fwd", "qpwc_upsample2x_bwd", "qpwc_occlusion_map", "qpwc_warp_bwd_nchw",
+    "qpwc_warp_fwd_nchw", "qpwc_warp_bwd", "qpwc_warp_fwd_ex", "qpwc_warp_pair_fwd", "qpwc_warp_bwd_ex", "qpwc_upsample2x_fwd", "qpwc_upsample2x_bwd", "qpwc_occlusion_map", "qpwc_warp_bwd_nchw", "qpwc_corr_bwd_nchw",
     "qpwc_warp_fwd_up", "qpwc_warp_corr_fwd_up", "qpwc_warp_corr_fwd", "qpwc_warp_corr_bwd_workspace", "qpwc_warp_corr_bwd",
     "qpwc_corr_fwd_host", "qpwc_warp_fwd_host", "qpwc_warp_corr_fwd_host",
     "qpwc_host_set_deferred", "qpwc_host_sync",

@@ -20,6 +20,7 @@ int launch_warp_fwd_nchw(const float*, const float*, float*, int, int, int, int,
 int launch_corr_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_upsample2x_bwd(const float*, float*, int, int, int, int, float, cudaStream_t);
 int launch_warp_bwd_nchw(const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, cudaStream_t);
+int launch_corr_bwd_nchw(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_occlusion_map(const float*, float*, int, int, int, int, cudaStream_t);
 int launch_warp_bwd_ex(const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
 int launch_corr_fwd_direct(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
@@ -302,6 +303,22 @@ int qpwc_corr_fwd_nchw(const float* prv, const float* nxt, float* out, int B, in
   if (rc == QPWC_ERR_UNSUPPORTED)
     return set_error(QPWC_ERR_UNSUPPORTED, "%s: native channels_first kernel needs search_range 4, W %% 4 == 0 and 16-byte aligned tensors "
                                            "(transpose to NHWC and call qpwc_corr_fwd instead)", fn);
+  return rc;
+}
+
+int qpwc_corr_bwd_nchw(const float* prv, const float* nxt, const float* out, const float* g_out,
+                       float* g_prv, float* g_nxt, int B, int C, int H, int W, int search_range,
+                       float leaky_slope, void* stream) {
+  const char* fn = "qpwc_corr_bwd_nchw";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  QPWC_TRY(check_corr_args(fn, search_range, (long long)(2 * search_range + 1) * (2 * search_range + 1)));
+  if (B == 0 || H == 0 || W == 0 || C == 0) return QPWC_OK;
+  QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt)); QPWC_TRY(check_ptr(fn, "out", out));
+  QPWC_TRY(check_ptr(fn, "g_out", g_out)); QPWC_TRY(check_ptr(fn, "g_prv", g_prv)); QPWC_TRY(check_ptr(fn, "g_nxt", g_nxt));
+  const int rc = launch_corr_bwd_nchw(prv, nxt, out, g_out, g_prv, g_nxt, B, C, H, W, search_range, leaky_slope, (cudaStream_t)stream);
+  if (rc == QPWC_ERR_UNSUPPORTED)
+    return set_error(QPWC_ERR_UNSUPPORTED, "%s: native channels_first kernel needs search_range 4, W %% 4 == 0 and 16-byte aligned tensors "
+                                           "(transpose to NHWC and call qpwc_corr_bwd instead)", fn);
   return rc;
 }
 

@@ -482,8 +482,14 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled is a driver call and needs a current context; a thread that has only had
+// cudaSetDevice applied (e.g. an autograd worker running a backward pass) has none until its first
+// runtime call that touches the device.  cudaFree(nullptr) is that call (a no-op afterwards).
+static void bind_primary_context() { (void)cudaFree(nullptr); }
+
 bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C, int boxC, int boxW, int boxH) {
   EncodeTiledFn enc = get_encode_fn();
+  bind_primary_context();
   if (!enc) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available"); return false; }
   const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
@@ -497,6 +503,7 @@ bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C
 }
 bool make_tmap_nchw(TensorMap* tm, const float* base, int B, int C, int H, int W, int boxW, int boxH, int boxC) {
   EncodeTiledFn enc = get_encode_fn();
+  bind_primary_context();
   if (!enc) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available"); return false; }
   const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
   const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};

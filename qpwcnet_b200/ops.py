@@ -246,8 +246,8 @@ def _corr_fwd_nchw(prv, nxt, d, slope):
 
 
 class _CostVolumeNCHW(torch.autograd.Function):
-    """channels_first cost volume: native NCHW forward kernel; the backward transposes to NHWC and
-    uses the tiled gradient kernels."""
+    """channels_first cost volume: native NCHW forward and gradient kernels; shapes outside their
+    domain take the transposing route through the NHWC kernels (still CUDA)."""
 
     @staticmethod
     def forward(ctx, prv, nxt, d, slope):
@@ -263,6 +263,17 @@ class _CostVolumeNCHW(torch.autograd.Function):
     def backward(ctx, g_out):
         prv, nxt, out = ctx.saved_tensors
         d, slope = ctx.cfg
+        from ._cabi import QPWC_ERR_UNSUPPORTED
+        B, C, H, W = prv.shape
+        g_out = g_out.contiguous()
+        g_prv, g_nxt = torch.empty_like(prv), torch.empty_like(nxt)
+        with _on_device(prv.device):
+            rc = lib().qpwc_corr_bwd_nchw(prv.data_ptr(), nxt.data_ptr(), out.data_ptr(), g_out.data_ptr(),
+                                          g_prv.data_ptr(), g_nxt.data_ptr(), B, C, H, W, d, slope,
+                                          _stream_ptr(prv.device))
+        if rc != QPWC_ERR_UNSUPPORTED:
+            check(rc)
+            return g_prv, g_nxt, None, None
         nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
         g_prv, g_nxt = _corr_bwd(nhwc(prv), nhwc(nxt), nhwc(out), nhwc(g_out), d, slope)
         return g_prv.permute(0, 3, 1, 2).contiguous(), g_nxt.permute(0, 3, 1, 2).contiguous(), None, None

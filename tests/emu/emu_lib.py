@@ -66,6 +66,15 @@ def occlusion_map(flow, channels_first=False):
     return out
 
 
+def corr_bwd_nchw(prv, nxt, out, g_out, d=4, slope=0.1):
+    prv, nxt, out, g_out = _f(prv), _f(nxt), _f(out), _f(g_out)
+    B, C, H, W = prv.shape
+    gp, gn = np.full_like(prv, np.nan), np.full_like(prv, np.nan)
+    _ck(lib().qpwc_corr_bwd_nchw(_p(prv), _p(nxt), _p(out), _p(g_out), _p(gp), _p(gn), B, C, H, W, d,
+                                 ctypes.c_float(slope), None))
+    return gp, gn
+
+
 def corr_bwd(prv, nxt, out, g_out, d=4, slope=0.1):
     prv, nxt, out, g_out = _f(prv), _f(nxt), _f(out), _f(g_out)
     B, H, W, C = prv.shape

@@ -244,3 +244,21 @@ def test_emu_warp_nchw_fwd_bwd(mode, B, C, H, W):
     gi32, gf32 = oracle.warp_bwd(*(nhwc(a) for a in (img, flow, g)), mode)
     assert np.abs(nhwc(gi2) - gi).max() <= max(2e-6, 2 * np.abs(gi32 - gi).max())
     assert np.abs(nhwc(gf2) - gf).max() <= max(1e-5, 2 * np.abs(gf32 - gf).max())
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 5, 6, 8), (2, 9, 5, 132), (1, 17, 9, 260), (1, 3, 1, 4)])
+def test_emu_corr_bwd_nchw(B, C, H, W):
+    """Gradients of the channels_first cost volume: native kernel (coefficients in registers, planar
+    TMA tiles), multi-tile in x and y, ragged channel chunks, against the fp64 oracle."""
+    r = rng(90 + C)
+    prv = r.standard_normal((B, C, H, W)).astype(np.float32)
+    nxt = r.standard_normal((B, C, H, W)).astype(np.float32)
+    nhwc = lambda a: np.ascontiguousarray(a.transpose(0, 2, 3, 1))
+    out = oracle.cost_volume(nhwc(prv), nhwc(nxt), 4)
+    g = r.standard_normal(out.shape).astype(np.float32)
+    gp, gn = oracle.cost_volume_bwd(*(a.astype(np.float64) for a in (nhwc(prv), nhwc(nxt), out, g)), 4)
+    nchw = lambda a: np.ascontiguousarray(a.transpose(0, 3, 1, 2))
+    gp2, gn2 = emu_lib.corr_bwd_nchw(prv, nxt, nchw(out), nchw(g))
+    assert not np.isnan(gp2).any() and not np.isnan(gn2).any()      # every element written
+    assert np.abs(nhwc(gp2) - gp).max() <= 1e-5 * np.abs(gp).max()
+    assert np.abs(nhwc(gn2) - gn).max() <= 1e-5 * np.abs(gn).max()
