@@ -42,6 +42,9 @@ def warp(inputs, mode, fmt):
 
 def warp_cost_volume(inputs, mode, search_range, fmt, leaky_slope=0.1):
     prv, nxt, flo = inputs
+    if fmt == "channels_first" and prv.is_cuda and prv.dim() == 4:
+        # native NCHW kernels end to end (warp, cost volume and both gradients): no transposes
+        return ops.cost_volume_nchw(prv, ops.warp_nchw(nxt, flo, mode), search_range, leaky_slope)
     out = ops.warp_cost_volume(to_nhwc(prv, fmt), to_nhwc(nxt, fmt), to_nhwc(flo, fmt), mode,
                                search_range, leaky_slope)
     return from_nhwc(out, fmt)

@@ -629,3 +629,35 @@ def test_occlusion_map(B, H, W, sigma):
         ops.occlusion_map(t, "channels_first")
     with pytest.raises(ValueError):
         estimate_occlusion_map(t, "NHWC")
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 24, 128), (1, 64, 17, 36), (1, 6, 9, 22)])
+def test_warp_cost_volume_channels_first(mode, B, C, H, W):
+    """The UpFlow pair (non_layers.py:377-380) under channels_first: native NCHW warp + cost volume +
+    both gradients (W % 4 == 0), or the transposing route (W = 22) -- same results as the oracle."""
+    from qpwcnet_b200.core import layers
+    r = rng(900 + C)
+    prv = r.standard_normal((B, C, H, W)).astype(np.float32)
+    nxt = r.standard_normal((B, C, H, W)).astype(np.float32)
+    flo = (r.standard_normal((B, 2, H, W)) * 2).astype(np.float32)
+    nh = lambda a: np.ascontiguousarray(a.transpose(0, 2, 3, 1))
+    tp, tn, tf_ = (dev(a).requires_grad_() for a in (prv, nxt, flo))
+    out = layers.WarpCostVolume(search_range=4, warp_mode=mode, data_format="channels_first")((tp, tn, tf_))
+    ref = oracle.warp_cost_volume(nh(prv).astype(np.float64), nh(nxt).astype(np.float64), nh(flo).astype(np.float64), mode, 4)
+    assert_rel(nh(host(out)), ref)
+    g = r.standard_normal((B, 81, H, W)).astype(np.float32)
+    gp, gn, gf = torch.autograd.grad(out, (tp, tn, tf_), dev(g))
+    rp, rn, rf = oracle.warp_cost_volume_bwd(nh(prv).astype(np.float64), nh(nxt).astype(np.float64),
+                                             nh(flo).astype(np.float64), nh(g).astype(np.float64), mode, 4)
+    assert_rel(nh(host(gp)), rp)
+    assert_rel(nh(host(gn)), rn)
+    assert np.abs(nh(host(gf)) - rf).max() <= 1e-5 * max(1.0, np.abs(rf).max())
+    # plain cost volume on the declined shape: gradients through the transposing route
+    if W % 4:
+        o2 = layers.CostVolumeV2(search_range=4, data_format="channels_first")((tp, tn))
+        g2p, g2n = torch.autograd.grad(o2, (tp, tn), dev(g))
+        q = oracle.cost_volume_bwd(nh(prv).astype(np.float64), nh(nxt).astype(np.float64), nh(host(o2)).astype(np.float64),
+                                   nh(g).astype(np.float64), 4)
+        assert_rel(nh(host(g2p)), q[0])
+        assert_rel(nh(host(g2n)), q[1])
