@@ -484,8 +484,25 @@ static EncodeTiledFn get_encode_fn() {
 
 // cuTensorMapEncodeTiled is a driver call and needs a current context; a thread that has only had
 // cudaSetDevice applied (e.g. an autograd worker running a backward pass) has none until its first
-// runtime call that touches the device.  cudaFree(nullptr) is that call (a no-op afterwards).
-static void bind_primary_context() { (void)cudaFree(nullptr); }
+// runtime call that touches the device.  cudaFree(nullptr) is that call.
+// Only when no context is current: cudaFree is not allowed while a stream is being captured, and a
+// capturing thread always has its context bound already.
+static void bind_primary_context() {
+  typedef CUresult (*CtxGetCurrentFn)(CUcontext*);
+  static CtxGetCurrentFn get_current = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      get_current = reinterpret_cast<CtxGetCurrentFn>(p);
+  }
+  CUcontext ctx = nullptr;
+  if (get_current && get_current(&ctx) == CUDA_SUCCESS && ctx != nullptr) return;
+  (void)cudaFree(nullptr);
+}
 
 bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C, int boxC, int boxW, int boxH) {
   EncodeTiledFn enc = get_encode_fn();
