@@ -40,8 +40,15 @@ def main():
             torch.autograd.grad(o.permute(0, 3, 1, 2).contiguous(), (img, flo), go)
 
         fwd = timed(lambda: ops.warp_nchw(img.detach(), flo.detach(), "tfa"))
-        out.append({"shape": [B, C, H, W], "native_fwd_us": fwd, "native_fwd_bwd_us": timed(native),
-                    "transposing_fwd_bwd_us": timed(transposing)})
+        rec = {"shape": [B, C, H, W], "flow": "N(0,2^2) px per pixel", "native_fwd_us": fwd,
+               "native_fwd_bwd_us": timed(native), "transposing_fwd_bwd_us": timed(transposing)}
+        # a smooth flow (what a network predicts): neighbouring pixels sample neighbouring columns
+        yy, xx = torch.meshgrid(torch.arange(H, device="cuda"), torch.arange(W, device="cuda"), indexing="ij")
+        smooth = torch.stack([1.3 + 2.0 * torch.sin(yy / 37.0), -0.7 + 2.0 * torch.cos(xx / 53.0)])[None].expand(B, 2, H, W)
+        flo = smooth.contiguous().requires_grad_()
+        rec.update({"smooth_native_fwd_us": timed(lambda: ops.warp_nchw(img.detach(), flo.detach(), "tfa")),
+                    "smooth_native_fwd_bwd_us": timed(native), "smooth_transposing_fwd_bwd_us": timed(transposing)})
+        out.append(rec)
     json.dump(out, sys.stdout)
     print()
 
