@@ -110,7 +110,21 @@ def extras():
     np.savez_compressed(os.path.join(OUT, "qpwc_golden_extras.npz"), **fx)
 
 
+def occlusion():
+    """estimate_occlusion_map (occlusion.py:27-118) fixtures, own file and RNG stream."""
+    r = np.random.default_rng(20261020)
+    fx = {}
+    for name, (B, H, W, sigma) in {"occ_a": (2, 9, 13, 2.0), "occ_b": (1, 16, 12, 7.0)}.items():
+        flow = f32(r.standard_normal((B, H, W, 2)) * sigma)
+        fx.update({f"{name}/flow": flow, f"{name}/map": oracle.occlusion_map(flow)})
+    np.savez_compressed(os.path.join(OUT, "qpwc_golden_occlusion.npz"), **fx)
+
+
 if __name__ == "__main__":
+    if "--occlusion-only" in sys.argv:
+        occlusion()
+        sys.exit(0)
     if "--extras-only" not in sys.argv:
         main()
     extras()
+    occlusion()

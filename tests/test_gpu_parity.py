@@ -688,3 +688,12 @@ def test_kernels_are_capturable_in_a_cuda_graph():
     torch.cuda.synchronize()
     for a, b in zip(eager, cap):
         assert torch.equal(a, b)
+
+
+def test_golden_occlusion():
+    """estimate_occlusion_map against the committed fixture, both data formats."""
+    g = np.load(os.path.join(GOLD, "qpwc_golden_occlusion.npz"))
+    for name in ("occ_a", "occ_b"):
+        t = dev(g[f"{name}/flow"])
+        np.testing.assert_array_equal(host(ops.occlusion_map(t)), g[f"{name}/map"])
+        np.testing.assert_array_equal(host(ops.occlusion_map(t.permute(0, 3, 1, 2).contiguous(), "channels_first")), g[f"{name}/map"])

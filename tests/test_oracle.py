@@ -305,3 +305,12 @@ def test_occlusion_map_properties():
             if i2 < 0 or i2 >= 6 or j2 < 0 or j2 >= 8:
                 want[i, j] = 1
     np.testing.assert_array_equal(oracle.occlusion_map(flow)[0], want)
+
+
+def test_oracle_reproduces_occlusion_golden():
+    """tests/golden/qpwc_golden_occlusion.npz (oracle/make_golden.py --occlusion-only)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qpwc_golden_occlusion.npz"))
+    for name in ("occ_a", "occ_b"):
+        m = oracle.occlusion_map(g[f"{name}/flow"])
+        np.testing.assert_array_equal(m, g[f"{name}/map"])
+        assert 0.0 < m.mean() < 1.0                       # both classes present
