@@ -123,9 +123,11 @@ __global__ void __launch_bounds__(256) warp_fwd_nchw_kernel(const float* __restr
                                                             const float* __restrict__ flow,
                                                             float* __restrict__ out, int C, int H, int W,
                                                             float scale) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= W) return;
-  const int i = blockIdx.y;
+  // block = 32 columns x 8 rows: a warp is one 128-byte row segment, and vertically adjacent pixels
+  // (whose taps share source rows) sit in the same block, i.e. the same L1
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (j >= W || i >= H) return;
   const size_t plane = (size_t)H * W;
   const size_t pix = (size_t)i * W + j;
   const float* fb = flow + (size_t)blockIdx.z * 2 * plane;
@@ -141,8 +143,8 @@ __global__ void __launch_bounds__(256) warp_fwd_nchw_kernel(const float* __restr
 int launch_warp_fwd_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W,
                          int mode, float scale, cudaStream_t stream) {
   if ((long long)B * C * H * W == 0) return QPWC_OK;
-  if (H > 65535 || B > 65535) return set_error(QPWC_ERR_UNSUPPORTED, "warp_fwd_nchw: H or B > 65535");
-  const dim3 grid((unsigned)cdiv(W, 256), (unsigned)H, (unsigned)B);
+  if (H > 8 * 65535 || B > 65535) return set_error(QPWC_ERR_UNSUPPORTED, "warp_fwd_nchw: H > 524280 or B > 65535");
+  const dim3 grid((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), (unsigned)B);
   if (mode == QPWC_MODE_TF) {
     auto k = warp_fwd_nchw_kernel<QPWC_MODE_TF>;
     QPWC_LAUNCH(k, grid, 256, 0, stream, img, flow, out, C, H, W, scale);
