@@ -19,8 +19,12 @@
  *    library with a stream-ordered memset.
  *  - Errors: no exception crosses the ABI.  Every function returns QPWC_OK (0) or a non-zero code
  *    and records a message retrievable (per calling thread) with qpwc_last_error().
- *  - Threading: stateless and re-entrant; concurrent calls from several host threads / devices are
- *    legal.  ctypes releases the GIL for the duration of a call.
+ *  - Threading: device-pointer entry points keep no state between calls except caches that are
+ *    per device and published with atomics (SM count, kernel attributes) or per calling thread (TMA
+ *    descriptors, the last error); concurrent calls from several host threads, streams and devices
+ *    are legal (tests/test_gpu_parity.py::test_two_threads_two_streams).  The _host entry points
+ *    serialise per device on an internal mutex (they share that device's staging slots); their
+ *    deferred-completion switch is per calling thread.  ctypes releases the GIL during a call.
  *  - `search_range` d >= 1: D = (2d+1)^2 output channels, channel = (di+d)*(2d+1) + (dj+d), row
  *    displacement outer (qpwcnet/core/layers.py:80-81).  `out_pixel_stride` (in floats, >= D) lets
  *    the cost volume be written straight into its slice of a wider concat buffer
@@ -163,8 +167,10 @@ int qpwc_warp_corr_fwd_host(const float* prv, const float* nxt, const float* flo
 /* Deferred completion for the _host entry points: after qpwc_host_set_deferred(1) a _host call
  * returns as soon as its copies and kernels are enqueued (on the library's internal streams), so
  * that consecutive calls -- e.g. the five levels of one pyramid pass -- overlap their H2D, compute
- * and D2H phases; qpwc_host_sync(device) then waits for everything enqueued so far.  The caller must
- * keep input and output host buffers alive and unmodified until the sync.  Process-wide setting. */
+ * and D2H phases; qpwc_host_sync(device) then waits for everything enqueued so far on that device
+ * (device = -1: on every device).  The caller must keep input and output host buffers alive and
+ * unmodified until the sync.  The switch is per calling thread: other threads' _host calls keep
+ * returning completed outputs. */
 int qpwc_host_set_deferred(int on);
 int qpwc_host_sync(int device);
 

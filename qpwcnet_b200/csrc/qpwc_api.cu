@@ -96,10 +96,13 @@ struct HostStage {
   cudaStream_t stream[NSLOT] = {};
   float* buf[NSLOT] = {};
   size_t cap[NSLOT] = {};
+  int next_slot = 0;  // keeps rotating across calls: consecutive deferred calls overlap (guarded by mu)
   std::mutex mu;
 };
 static HostStage g_stage[16];
-static bool g_host_deferred = false;  // qpwc_host_set_deferred(): _host calls return after enqueueing
+// qpwc_host_set_deferred(): _host calls of THIS thread return after enqueueing (per-thread state: a
+// thread that did not ask for deferral always gets completed outputs)
+static thread_local bool g_host_deferred = false;
 
 static int stage_reserve(HostStage& hs, int slot, size_t bytes) {
   if (!hs.stream[slot]) {
@@ -126,6 +129,9 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
   const size_t px = (size_t)H * W;
   const size_t n_a = px * C, n_b = (kind == 1) ? 0 : px * C, n_f = (kind == 0) ? 0 : px * 2;
   const size_t n_o = (kind == 1) ? px * C : px * D;
+  // sub-buffers of a slot are packed back to back; each starts on a 16-byte boundary (float4 / float2
+  // accesses of the kernels, TMA) whatever the tensor sizes are
+  auto pad4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
   const size_t item = (n_a + n_b + n_f + n_o) * sizeof(float);
   // slice the batch so that one slice moves >= ~8 MiB (amortises per-slice launch/copy latency)
   int per = (int)((((size_t)8 << 20) + item - 1) / item);
@@ -133,17 +139,17 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
   if (per > B) per = B;
   HostStage& hs = g_stage[device];
   std::lock_guard<std::mutex> lock(hs.mu);
-  static int next_slot = 0;  // keeps rotating across calls: consecutive deferred calls overlap
-  int rc = QPWC_OK, slot = next_slot;
+  int rc = QPWC_OK, slot = hs.next_slot;
+  const size_t slot_floats = pad4(n_a * per) + pad4(n_b * per) + pad4(n_f * per) + pad4(n_o * per);
   for (int b0 = 0; b0 < B && rc == QPWC_OK; b0 += per, slot = (slot + 1) % HostStage::NSLOT) {
     const int nb = (B - b0 < per) ? (B - b0) : per;
-    rc = stage_reserve(hs, slot, item * per);
+    rc = stage_reserve(hs, slot, slot_floats * sizeof(float));
     if (rc != QPWC_OK) break;
     cudaStream_t st = hs.stream[slot];
     float* da = hs.buf[slot];
-    float* db = da + n_a * per;
-    float* df = db + n_b * per;
-    float* dout = df + n_f * per;
+    float* db = da + pad4(n_a * per);
+    float* df = db + pad4(n_b * per);
+    float* dout = df + pad4(n_f * per);
     e = cudaMemcpyAsync(da, a + n_a * b0, n_a * nb * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && n_b) e = cudaMemcpyAsync(db, b + n_b * b0, n_b * nb * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && n_f) e = cudaMemcpyAsync(df, f + n_f * b0, n_f * nb * sizeof(float), cudaMemcpyHostToDevice, st);
@@ -154,7 +160,7 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
     if (rc != QPWC_OK) break;
     e = cudaMemcpyAsync(out + n_o * b0, dout, n_o * nb * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) { rc = set_error(QPWC_ERR_CUDA, "host call: D2H: %s", cudaGetErrorString(e)); break; }
-    next_slot = (slot + 1) % HostStage::NSLOT;
+    hs.next_slot = (slot + 1) % HostStage::NSLOT;
   }
   if (g_host_deferred && rc == QPWC_OK) return rc;  // completion is collected by qpwc_host_sync()
   for (int s = 0; s < HostStage::NSLOT; ++s)
@@ -166,15 +172,18 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
 }
 
 static int host_sync(int device) {
-  if (device < 0 || device >= 16) return set_error(QPWC_ERR_INVALID, "qpwc_host_sync: device ordinal %d outside [0,16)", device);
-  HostStage& hs = g_stage[device];
-  std::lock_guard<std::mutex> lock(hs.mu);
+  // device == -1: every device that has received host-buffer work from this process
+  if (device < -1 || device >= 16) return set_error(QPWC_ERR_INVALID, "qpwc_host_sync: device ordinal %d outside [-1,16)", device);
   int rc = QPWC_OK;
-  for (int s = 0; s < HostStage::NSLOT; ++s)
-    if (hs.stream[s]) {
-      const cudaError_t e = cudaStreamSynchronize(hs.stream[s]);
-      if (e != cudaSuccess && rc == QPWC_OK) rc = set_error(QPWC_ERR_CUDA, "qpwc_host_sync: %s", cudaGetErrorString(e));
-    }
+  for (int dv = (device < 0 ? 0 : device); dv <= (device < 0 ? 15 : device); ++dv) {
+    HostStage& hs = g_stage[dv];
+    std::lock_guard<std::mutex> lock(hs.mu);
+    for (int s = 0; s < HostStage::NSLOT; ++s)
+      if (hs.stream[s]) {
+        const cudaError_t e = cudaStreamSynchronize(hs.stream[s]);
+        if (e != cudaSuccess && rc == QPWC_OK) rc = set_error(QPWC_ERR_CUDA, "qpwc_host_sync(device %d): %s", dv, cudaGetErrorString(e));
+      }
+  }
   return rc;
 }
 

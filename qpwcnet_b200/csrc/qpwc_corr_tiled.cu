@@ -31,8 +31,11 @@
 
 namespace qpwc {
 
-template <int TH_, int WARP_, int MODE_, int PACKED_ = 0>
+template <int TH_, int WARP_, int MODE_, int PACKED_ = 0, int OCC_ = 1>
 struct TiledCfg {
+  // OCC: CTAs per SM.  2 (TH = 2): two independent CTAs share an SM, so one CTA's tile prologue and
+  // epilogue overlap the other's FFMA loop instead of all eight consumer warps marching in lock-step
+  static constexpr int OCC = OCC_;
   // PACKED: accumulate with packed fp32 FMAs (FFMA2, sm_100): even-/odd-channel partial sums kept
   // as register pairs (162 accumulator registers).  Measured on B200 (tools/ubench): FFMA2 issues
   // every 2.2-2.3 clk/SMSP, a scalar 3-register FFMA every 1.22 clk, and with its shared-memory
@@ -47,7 +50,7 @@ struct TiledCfg {
   // (measured ~2 clk each), so wider per-pixel reads halve the producer's L1 time
   static constexpr int KC = WARP_ ? 16 : 8, PXB = KC * 4, NQ = KC / 4;
   static constexpr int NROW = TH + 2 * D, NCOL = TWT, PCOL = TW;         // P tile: the 56 valid columns only
-  static constexpr int NST = WARP_ ? 2 : ((PACKED_ || TH_ <= 4) ? 4 : 3);
+  static constexpr int NST = WARP_ ? 2 : (OCC_ == 2 ? 3 : ((PACKED_ || TH_ <= 4) ? 4 : 3));
   static constexpr int P_BYTES = TH * PCOL * PXB, N_BYTES = NROW * NCOL * PXB;
   static constexpr int STAGE_BYTES = P_BYTES + N_BYTES;
   // producers (128-thread warpgroups, the unit of setmaxnreg): plain = 1 TMA thread + 3 store-agent
@@ -66,7 +69,7 @@ struct TiledCfg {
   static constexpr int OFF_TAPS = OFF_STAGING + TH * NSLOT * SLOT_BYTES;
   static constexpr int OFF_BARS = OFF_TAPS + TAPS_BYTES;
   static constexpr int SMEM_BYTES = OFF_BARS + 2 * NST * 8 + 2 * TH * 8;
-  static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
+  static_assert(SMEM_BYTES <= (OCC_ == 2 ? 115712 : 232448), "shared memory budget (227 KB per SM, 1 KB reserved per CTA)");
   static constexpr int FULL_COUNT = 1 + (WARP ? NPROD / 32 : 0);
   static constexpr int EMPTY_COUNT = NCONS / 32;
   // register split (setmaxnreg), sum <= 65536:  scalar TH=4 plain: 256*200 + 128*56;  scalar TH=6:
@@ -77,7 +80,7 @@ struct TiledCfg {
   static constexpr int UB = 2;  // fused producer: units in flight per thread (8 independent 16-byte gathers)
   static_assert(!(WARP_ && (PACKED_ || TH_ > 4)), "fused variant: scalar consumers, TH <= 4");
   static_assert(TW % 8 == 0 && P_BYTES % 512 == 0 && N_BYTES % 512 == 0 && TH <= 14, "tile shape");
-  static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536, "register budget");
+  static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536 / OCC_, "register budget");
 };
 
 struct TapsEntry { int o00, o01, o10, o11; float w00, w01, w10, w11; };  // 32 bytes
@@ -104,7 +107,7 @@ struct TapsEntry { int o00, o01, o10, o11; float w00, w01, w10, w11; };  // 32 b
 
 // ---------------------------------------------------------------------------------------------
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::NTHREADS, 1)
+__global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::OCC)
 corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CONSTANT TensorMap tmN,
                       const float* __restrict__ nxt, const float* __restrict__ flow,
                       float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
@@ -577,7 +580,7 @@ static int run_tiled(const float* prv, const float* nxt, const float* flow, floa
   const long long ns = (long long)tiles_x * B * nwin * segs_per_strip;
   if (ns >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
   const int nsegs = (int)ns;
-  const int grid = nsegs < sm_count() ? nsegs : sm_count();
+  const int grid = nsegs < Cfg::OCC * sm_count() ? nsegs : Cfg::OCC * sm_count();
   auto k = corr_fwd_tiled_kernel<Cfg>;
 #ifndef QPWC_EMU
   static unsigned attr_done = 0;  // per instantiation, one bit per device (the attribute is per device)
@@ -630,6 +633,8 @@ int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow,
     // accumulators (tools/ubench/corr_loop_bench.cu), the packed loop 0.60 with 162.
     if (var && var[0] == 'p')
       return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+    if (var && var[0] == 't')
+      return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 0, 2>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
     return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
   }
   if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d, up_scale);

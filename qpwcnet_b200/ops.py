@@ -512,11 +512,8 @@ def warp(img, flow, mode="tfa", flow_scale: float = 1.0):
     fuses the reference's ``warp((img, 0.5 * flo))`` (FrameInterpolate, non_layers.py:303-304)."""
     img = _prep(img, "img")
     flow = _prep(flow, "flow", last=2)
-    if img.shape[:3] != flow.shape[:3] or img.device != flow.device:
-        raise ValueError(f"warp: img {tuple(img.shape)}@{img.device} vs flow {tuple(flow.shape)}@{flow.device}")
     m = _mode(mode)
-    if m == 1 and (img.shape[1] < 2 or img.shape[2] < 2):
-        raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
+    _check_flow("warp", img, flow, m)
     _no_host_grad(img, flow)
     if float(flow_scale) != 1.0:
         if not img.is_cuda:
@@ -630,17 +627,31 @@ def half_flow_warps_into(out, prv, nxt, flo_01, flo_10, mode="tfa", flow_scale: 
     return _warp_pair_fwd(out, prv, flo_10, nxt, flo_01, m, float(flow_scale))
 
 
+def _check_flow(what, ref, flow, m):
+    """Shape / device / mode checks shared by the autograd entry points and their `_into` twins: the
+    C ABI only sees B, H, W of the image, so a smaller or other-device flow would be read out of
+    bounds."""
+    if ref.shape[:3] != flow.shape[:3] or ref.device != flow.device:
+        raise ValueError(f"{what}: image {tuple(ref.shape)} @ {ref.device} vs flow {tuple(flow.shape)} @ {flow.device}")
+    if m == 1 and (ref.shape[1] < 2 or ref.shape[2] < 2):
+        raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
+
+
+def _no_grad_into(what, *ts):
+    """The `_into` entry points are inference-only: refuse silently dropping a graph."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
+        raise RuntimeError(f"{what} is inference-only (no autograd graph is recorded); call it under "
+                           "torch.no_grad() / with detached inputs, or use the differentiable twin")
+
+
 def warp_cost_volume(prv, nxt, flow, mode="tfa", search_range: int = 4, leaky_slope: float = 0.1):
     """Fused ``cost_volume(prv, warp(nxt, flow))`` (UpFlow): one kernel, the warped frame never
     reaches HBM."""
     prv, nxt = _prep(prv, "prv"), _prep(nxt, "nxt")
     flow = _prep(flow, "flow", last=2)
     _same(prv, nxt, "warp_cost_volume(prv, nxt)")
-    if prv.shape[:3] != flow.shape[:3] or prv.device != flow.device:
-        raise ValueError(f"warp_cost_volume: prv {tuple(prv.shape)} vs flow {tuple(flow.shape)}")
     m = _mode(mode)
-    if m == 1 and (prv.shape[1] < 2 or prv.shape[2] < 2):
-        raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
+    _check_flow("warp_cost_volume", prv, flow, m)
     _no_host_grad(prv, nxt, flow)
     if not prv.is_cuda:
         return _warp_corr_fwd(prv, nxt, flow, m, int(search_range), float(leaky_slope))
@@ -654,6 +665,7 @@ def cost_volume_into(out, prv, nxt, search_range: int = 4, leaky_slope: float = 
     prv, nxt = _prep(prv, "prv"), _prep(nxt, "nxt")
     _same(prv, nxt, "cost_volume_into(prv, nxt)")
     _check_out(out, prv)
+    _no_grad_into("cost_volume_into", prv, nxt)
     return _corr_fwd(prv, nxt, int(search_range), float(leaky_slope), out=out, out_stride=out.shape[-1])
 
 
@@ -664,6 +676,8 @@ def warp_cost_volume_into(out, prv, nxt, flow, mode="tfa", search_range: int = 4
     flow = _prep(flow, "flow", last=2)
     _same(prv, nxt, "warp_cost_volume_into(prv, nxt)")
     _check_out(out, prv)
+    _check_flow("warp_cost_volume_into", prv, flow, _mode(mode))
+    _no_grad_into("warp_cost_volume_into", prv, nxt, flow)
     return _warp_corr_fwd(prv, nxt, flow, _mode(mode), int(search_range), float(leaky_slope),
                           out=out, out_stride=out.shape[-1])
 
@@ -674,6 +688,8 @@ def warp_into(out, img, flow, mode="tfa"):
     flow = _prep(flow, "flow", last=2)
     if out.shape != img.shape or out.dtype != torch.float32 or out.device != img.device or not out.is_contiguous():
         raise ValueError("out must be a dense float32 tensor shaped like img on the same device")
+    _check_flow("warp_into", img, flow, _mode(mode))
+    _no_grad_into("warp_into", img, flow)
     return _warp_fwd(img, flow, _mode(mode), out=out)
 
 
@@ -695,7 +711,7 @@ class host_batch:
 
     def __exit__(self, *exc):
         check(lib().qpwc_host_set_deferred(0))
-        check(lib().qpwc_host_sync(torch.cuda.current_device()))
+        check(lib().qpwc_host_sync(-1))      # every device that received deferred work
         return False
 
 

@@ -107,7 +107,7 @@ def cost_volume(prv_band, nxt_band, search_range=4, leaky_slope=0.1, group=None,
 
 
 def warp_cost_volume(prv_band, nxt_band, flow_band, mode="tfa", search_range=4, leaky_slope=0.1,
-                     group=None, op=None, row_offset_fix=True):
+                     group=None, op=None):
     """Fused warp -> cost volume of this rank's band.  The warp samples absolute image rows, so the
     padded band is processed with the flow expressed in band coordinates (unchanged: the flow is a
     displacement) and a halo deep enough for the largest vertical displacement."""
@@ -115,10 +115,16 @@ def warp_cost_volume(prv_band, nxt_band, flow_band, mode="tfa", search_range=4, 
     op = op or _ops.warp_cost_volume
     d = int(search_range)
     # one collective for both scalars: the largest vertical displacement and the thinnest band
-    m = torch.stack([flow_band[..., 1].abs().max().to(torch.float32),
-                     torch.tensor(-float(flow_band.shape[1]), device=flow_band.device)])
+    # (an empty band -- H < world size -- contributes 0; non-finite flow is clamped: the warp itself
+    # saturates such samples at the border, so a halo of the whole image is always enough)
+    fy = flow_band[..., 1].abs()
+    fmax = torch.nan_to_num(fy, nan=0.0, posinf=3.0e38).max().to(torch.float32) if fy.numel() else \
+        torch.zeros((), device=flow_band.device)
+    m = torch.stack([fmax, torch.tensor(-float(flow_band.shape[1]), device=flow_band.device)])
     dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
-    rows = d + int(math.ceil(float(m[0].item()))) + 1
+    h_total = torch.tensor(float(flow_band.shape[1]), device=flow_band.device)
+    dist.all_reduce(h_total, op=dist.ReduceOp.SUM, group=group)
+    rows = d + int(math.ceil(min(float(m[0].item()), float(h_total.item())))) + 1
     hmin = int(-m[1].item())
     nxt_h, top, bot = exchange_halo_ex(nxt_band, rows, group, hmin)
     flow_h, _, _ = exchange_halo_ex(flow_band, rows, group, hmin)

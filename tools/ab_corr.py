@@ -22,7 +22,7 @@ def main():
         prv = torch.randn((B, H, W, C), device=dev, generator=g)
         nxt = torch.randn((B, H, W, C), device=dev, generator=g)
         res = {}
-        for var in ("packed", "rowpair", "default"):
+        for var in ("packed", "rowpair", "two", "default"):
             os.environ["QPWC_CORR_VARIANT"] = var
             out = torch.full((B, H, W, 81), float("nan"), device=dev)
             ops.cost_volume_into(out, prv, nxt, 4)
@@ -32,7 +32,8 @@ def main():
         a, b = res["default"][0], res["rowpair"][0]
         err = (a - b).abs().max().item() / a.abs().max().item()
         nan = int(torch.isnan(b).sum().item())
-        print(f"{H}x{W}x{C} B={B}: packed {res['packed'][1]*1e6:8.1f} us  rowpair {res['rowpair'][1]*1e6:8.1f} us  default(scalar) {res['default'][1]*1e6:8.1f} us  "
+        err2 = (a - res["two"][0]).abs().max().item() / a.abs().max().item()
+        print(f"{H}x{W}x{C} B={B}: two-CTA {res['two'][1]*1e6:8.1f} us (diff {err2:.1e})  packed {res['packed'][1]*1e6:8.1f} us  rowpair {res['rowpair'][1]*1e6:8.1f} us  default(scalar) {res['default'][1]*1e6:8.1f} us  "
               f"rel diff {err:.2e}  nan {nan}", flush=True)
 
 
