@@ -54,6 +54,18 @@ int qpwc_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* qpwc_last_error(void);
 
+/* Process-wide options.  QPWC_OPT_CORR_ENGINE selects the arithmetic of the cost-volume forward
+ * kernels: QPWC_ENGINE_AUTO (default) = tensor cores where the shape allows (search_range 4,
+ * C % 8 == 0): fp32 operands split into tf32 hi + lo, three tcgen05.mma passes, fp32 accumulation,
+ * measured error <= 8e-7 * mean|prv*nxt| (the reference contract is 1e-5); QPWC_ENGINE_FFMA = plain
+ * fp32 FFMA kernels only; QPWC_ENGINE_TC = tensor cores or QPWC_ERR_UNSUPPORTED. */
+#define QPWC_OPT_CORR_ENGINE 0
+#define QPWC_ENGINE_AUTO 0
+#define QPWC_ENGINE_FFMA 1
+#define QPWC_ENGINE_TC 2
+int qpwc_set_option(int key, int value);
+int qpwc_get_option(int key); /* -1 for an unknown key */
+
 /* CostVolume.call / CostVolumeV2.call -- qpwcnet/core/layers.py:72-100, 117-132
  * (functors: qpwcnet/core/non_layers.py:72-104, 112-123), leaky_relu(slope) included. */
 int qpwc_corr_fwd(const float* prv, const float* nxt, float* out, int B, int H, int W, int C,

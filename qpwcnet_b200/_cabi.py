@@ -73,6 +73,8 @@ def lib() -> ctypes.CDLL:
         "qpwc_warp_corr_fwd_host": ([fp, fp, fp, fp, i, i, i, i, i, f, i, i], c_int),
         "qpwc_host_set_deferred": ([i], c_int),
         "qpwc_host_sync": ([i], c_int),
+        "qpwc_set_option": ([i, i], c_int),
+        "qpwc_get_option": ([i], c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(L, name)          # AttributeError here = header/library mismatch: be loud
@@ -87,7 +89,7 @@ EXPORTED_SYMBOLS = (
     "qpwc_warp_fwd_nchw", "qpwc_warp_bwd", "qpwc_warp_fwd_ex", "qpwc_warp_pair_fwd", "qpwc_warp_bwd_ex", "qpwc_upsample2x_fwd", "qpwc_upsample2x_bwd", "qpwc_occlusion_map", "qpwc_warp_bwd_nchw", "qpwc_corr_bwd_nchw",
     "qpwc_warp_fwd_up", "qpwc_warp_corr_fwd_up", "qpwc_warp_corr_fwd", "qpwc_warp_corr_bwd_workspace", "qpwc_warp_corr_bwd",
     "qpwc_corr_fwd_host", "qpwc_warp_fwd_host", "qpwc_warp_corr_fwd_host",
-    "qpwc_host_set_deferred", "qpwc_host_sync",
+    "qpwc_host_set_deferred", "qpwc_host_sync", "qpwc_set_option", "qpwc_get_option",
 )
 
 

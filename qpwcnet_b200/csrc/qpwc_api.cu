@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "qpwc_common.cuh"
@@ -28,6 +29,8 @@ int launch_corr_bwd_direct(const float*, const float*, const float*, const float
 // returns QPWC_ERR_UNSUPPORTED (without setting an error) when the shape is outside its domain
 int launch_corr_fwd_tiled(const float*, const float*, const float*, int, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
 int launch_corr_bwd_tiled(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
+// tensor-core (3xTF32) cost volume, qpwc_corr_tc.cu; QPWC_ERR_UNSUPPORTED outside its domain
+int launch_corr_fwd_tc(const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t);
 
 static thread_local char g_err[512] = "";
 
@@ -73,9 +76,19 @@ static int check_mode(const char* fn, int mode, int H, int W) {
   return QPWC_OK;
 }
 
+// qpwc_set_option(QPWC_OPT_CORR_ENGINE, ...): 0 = auto (tensor cores where the shape allows), 1 = FFMA
+// kernels only (plain fp32 arithmetic), 2 = tensor cores (3xTF32 split) or fail
+static std::atomic<int> g_corr_engine{0};
+
 static int corr_fwd_any(const float* prv, const float* nxt, const float* flow, int mode, float* out,
                         int B, int H, int W, int C, int d, float slope, long long ops, cudaStream_t st,
                         float up_scale = 0.f) {
+  const int engine = g_corr_engine.load(std::memory_order_relaxed);
+  if (!flow && engine != 1) {
+    const int rt = launch_corr_fwd_tc(prv, nxt, out, B, H, W, C, d, slope, ops, st);
+    if (rt != QPWC_ERR_UNSUPPORTED) return rt;
+    if (engine == 2) return set_error(QPWC_ERR_UNSUPPORTED, "corr_fwd: tensor-core engine needs search_range 4, C %% 8 == 0 and 16-byte aligned inputs");
+  }
   const int rc = launch_corr_fwd_tiled(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);
   if (rc != QPWC_ERR_UNSUPPORTED) return rc;
   return launch_corr_fwd_direct(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);
@@ -193,7 +206,12 @@ using namespace qpwc;
 
 extern "C" {
 
-int qpwc_version(void) { return 100; /* 0.1.0 */ }
+int qpwc_version(void) { return 200; /* 0.2.0 */ }
+int qpwc_set_option(int key, int value) {
+  if (key == QPWC_OPT_CORR_ENGINE && value >= 0 && value <= 2) { g_corr_engine.store(value); return QPWC_OK; }
+  return set_error(QPWC_ERR_INVALID, "qpwc_set_option: unknown key %d or value %d", key, value);
+}
+int qpwc_get_option(int key) { return key == QPWC_OPT_CORR_ENGINE ? g_corr_engine.load() : -1; }
 int qpwc_host_set_deferred(int on) { g_host_deferred = on != 0; return QPWC_OK; }
 int qpwc_host_sync(int device) { return host_sync(device); }
 const char* qpwc_last_error(void) { return g_err; }

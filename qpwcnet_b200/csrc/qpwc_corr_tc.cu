@@ -1,0 +1,499 @@
+// qpwc_corr_tc.cu -- local-correlation cost volume on the 5th-generation tensor cores (tcgen05 + TMEM),
+// fp32 in / fp32 out through a 3xTF32 operand split, for sm_100a.
+//
+//   out[b,i,j,(di+4)*9+(dj+4)] = lrelu( (1/C) sum_c P[b,i,j,c] * N[b,i+di,j+dj,c] ),  N == 0 outside
+//   (CostVolume / CostVolumeV2, qpwcnet/core/layers.py:72-100,117-132)
+//
+// Formulation.  An 8x16 tile of first-frame pixels (M = 128 rows of A) against its 16x24 halo tile of
+// second-frame pixels (N = 384 rows of B) is the dense product D[128 x 384] = A[128 x C] . B[384 x C]^T;
+// the 81 wanted displacements of pixel (r, c) are the 9x9 window D[(r,c), (r+m, c+k)], m,k in [0,9) --
+// 81/384 = 21 % of the dense tile.  fp32 operands are split x = hi + lo with hi = the fp32 word itself
+// (the tensor core ignores the 13 low mantissa bits of a tf32 operand: tools/ubench/tf32x3_tile.cu,
+// raw and masked words give bit-identical products) and lo = rna_tf32(x - trunc_tf32(x)); three
+// tcgen05.mma kind::tf32 passes hi.hi + lo.hi + hi.lo accumulate in fp32 in TMEM.  Measured error
+// against fp64: <= 8e-7 * mean|p.n| (fp32 FFMA in sequence: 2.4e-7; the contract is 1e-5), and the
+// tile sustains 104 clk per 128x192x8 MMA = 2.9x the useful FMA rate of the FFMA kernel
+// (profiles/r02_tf32x3_ubench.txt).
+//
+// Structure: one persistent CTA per SM, warp-specialised.
+//   warp 0    TMA producer: per 8-channel K chunk, 4 boxes of A (4 rows x 8 cols each, so that TMEM
+//             lane quadrant q holds a 4x8 pixel block) + 1 box of B (16 x 24, zero fill == ZeroPadding2D),
+//             SWIZZLE_32B = the canonical K-major UMMA layout (pixel rows 32 B apart).
+//   warp 1    MMA issuer (one thread): 6 MMAs (2 halves of N x 3 passes) per chunk into 384 TMEM
+//             columns; tcgen05.commit releases the stage / publishes the accumulator.
+//   warps 2-5 operand split: lo = rna(x - trunc(x)) for the 16 KB of a stage, elementwise.
+//   warps 6-9 epilogue: warp = TMEM lane quadrant = 4x8 pixel block; reads its 12 x 16 window of the
+//             accumulator (tcgen05.ld 32x32b.x16), scales, leaky-relu, and scatters each lane's 9x9 band
+//             into a bank-conflict-free staging buffer (82-float pixel pitch); then copies the staged
+//             rows to global memory as contiguous 16 x 324-byte runs.
+#include <stdlib.h>
+
+#include "qpwc_async.cuh"
+
+namespace qpwc {
+
+#ifndef QPWC_EMU
+
+struct TcCfg {
+  static constexpr int NDISP = 81;
+  static constexpr int TH = 8, TW = 16, NROW = 16, NCOL = 24, NHALF = 192;
+  static constexpr int KC = 8, PXB = 32;
+  static constexpr int A_BYTES = TH * TW * PXB, B_BYTES = NROW * NCOL * PXB, BH_BYTES = B_BYTES / 2;  // 4096, 12288, 6144
+  static constexpr int ROW_FLOATS = TW * NDISP;           // staging: the tile's NHWC output image, 8 rows of 16 x 81
+  static constexpr int STAGING_BYTES = TH * ROW_FLOATS * 4;
+  static constexpr int NEPI = 12;                         // epilogue warps: 3 per TMEM lane quadrant
+  static constexpr int NTHREADS = (2 + 4 + NEPI) * 32;    // TMA, MMA, 4 split warps, epilogue
+  // ---- streaming kernel (any C % 8 == 0): NST stages of one 8-channel chunk, [A raw | B raw | A lo | B lo]
+  static constexpr int RAW_BYTES = A_BYTES + B_BYTES, STAGE_BYTES = 2 * RAW_BYTES;
+  static constexpr int NST = 5;
+  static constexpr int S_OFF_STAGING = NST * STAGE_BYTES;
+  static constexpr int S_OFF_BARS = S_OFF_STAGING + STAGING_BYTES;
+  static constexpr int S_SMEM_BYTES = S_OFF_BARS + (3 * NST + 4) * 8 + 16;
+  // ---- resident kernel (C <= 32: all K chunks of a tile stay in shared memory): two A buffers and two
+  // half-tile B blocks (8 second-frame rows each), raw + lo, MAXCH chunks each
+  static constexpr int MAXCH = 4;
+  static constexpr int RA_BYTES = MAXCH * A_BYTES, RB_BYTES = MAXCH * BH_BYTES;   // 16 KB, 24 KB (raw; lo follows)
+  static constexpr int R_OFF_A = 0, R_OFF_B = 2 * 2 * RA_BYTES;                   // A: 64 KB, B: 96 KB
+  static constexpr int R_OFF_STAGING = R_OFF_B + 2 * 2 * RB_BYTES;
+  static constexpr int R_OFF_BARS = R_OFF_STAGING + STAGING_BYTES;
+  static constexpr int R_SMEM_BYTES = R_OFF_BARS + 16 * 8 + 16;
+  static_assert(S_SMEM_BYTES <= 232448 && R_SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0 && BH_BYTES % 256 == 0, "swizzle phase of every operand block");
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+  // cute::UMMA::SmemDescriptor, K-major SWIZZLE_32B: start address, LBO (unused), SBO = 8 rows x 32 B,
+  // version 1, layout type 6
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+}
+// kind::tf32, fp32 accumulator, A and B K-major, M = 128, N = 192
+static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TcCfg::NHALF >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(da), "l"(db), "r"(kIdesc), "r"(acc) : "memory");
+}
+// the three passes of the split product for one K chunk and one half of N: hi.hi + lo.hi + hi.lo
+__device__ __forceinline__ void umma_x3(uint32_t d, uint32_t a_raw, uint32_t a_lo, uint32_t b_raw, uint32_t b_lo, uint32_t acc) {
+  umma_tf32(d, umma_desc_sw32(a_raw), umma_desc_sw32(b_raw), acc);
+  umma_tf32(d, umma_desc_sw32(a_lo), umma_desc_sw32(b_raw), 1u);
+  umma_tf32(d, umma_desc_sw32(a_raw), umma_desc_sw32(b_lo), 1u);
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);  // exact
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
+  return __uint_as_float(t);
+}
+// lo = rna(x - trunc(x)) for `bytes` of a raw operand block, elementwise (any swizzle: same offsets)
+__device__ __forceinline__ void split_block(const unsigned char* src, unsigned char* dst, int bytes, int st) {
+  for (int off = st * 16; off < bytes; off += 128 * 16) {
+    const float4 v = *reinterpret_cast<const float4*>(src + off);
+    *reinterpret_cast<float4*>(dst + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+  }
+}
+#define QPWC_TMEM_LD16(v, taddr)                                                                          \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),   \
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
+               : "r"(taddr))
+
+// Epilogue of one tile, executed by the 12 epilogue warps (ew = 0..11).  TMEM lane quadrant q = warp
+// id % 4 holds the 4x8 pixel block (rows 4*(q&1).., cols 8*(q>>1)..) of the tile; the three warps of a
+// quadrant take four rows each of its 12 x 16 accumulator window, every four-row group lies in one
+// half of N (tfull/tempty[h]).  Per window row a lane needs the 9 columns c..c+8 of the 16 it
+// loaded: a 3-level conditional shift on the bits of c brings them to registers 0..8, they are scaled,
+// leaky-relu'd and stored as row (y - r) of the lane's 9x9 band in the NHWC staging image of the tile
+// (compact 81-float pixels: at most 2-way bank conflicts).  After a barrier the 8 staged rows leave
+// as TMA bulk stores (one contiguous 16 x 324-byte run each).
+__device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, uint64_t* tfull, uint64_t* tempty,
+                                                 uint32_t tcount, int q, int part, int ew, int lane,
+                                                 float* __restrict__ out, int b, int i0, int j0, int H, int W,
+                                                 long long ops, float inv_c, float slope, int ablate) {
+  using Cfg = TcCfg;
+  const int rb = q & 1, cb = q >> 1, r = lane >> 3, c = lane & 7;
+  const int h = (rb + part) >= 2 ? 1 : 0;
+  const int y0 = 4 * part;
+  const bool c4 = c & 4, c2 = c & 2, c1 = c & 1;
+  // row (y - r) of the band of pixel (rb*4 + r, cb*8 + c) starts at lane_base[9*y]
+  float* lane_base = staging + (rb * 4 + r) * Cfg::ROW_FLOATS + (cb * 8 + c) * Cfg::NDISP - 9 * r;
+  const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((rb * 4 + y0) * Cfg::NCOL + cb * 8);
+  // the bulk stores of the previous tile must have finished reading the staging image
+  if (ew < Cfg::TH && lane == 0) bulk_wait_read<0>();
+  named_bar_sync(1, Cfg::NEPI * 32);
+  mbar_wait(&tfull[h], tcount & 1u);
+  tc_fence_after();
+  if (!(ablate & 1)) {
+#pragma unroll
+    for (int yy = 0; yy < 4; yy += 2) {
+      uint32_t u0[16], u1[16];
+      QPWC_TMEM_LD16(u0, tq + (uint32_t)(yy * Cfg::NCOL));
+      QPWC_TMEM_LD16(u1, tq + (uint32_t)((yy + 1) * Cfg::NCOL));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) v[x] = __uint_as_float(half ? u1[x] : u0[x]);
+#pragma unroll
+        for (int x = 0; x < 12; ++x) v[x] = c4 ? v[x + 4] : v[x];
+#pragma unroll
+        for (int x = 0; x < 10; ++x) v[x] = c2 ? v[x + 2] : v[x];
+#pragma unroll
+        for (int x = 0; x < 9; ++x) v[x] = c1 ? v[x + 1] : v[x];
+        const int y = y0 + yy + half;
+        if ((unsigned)(y - r) <= 8u) {
+          float* sp = lane_base + 9 * y;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) sp[k] = lrelu(v[k] * inv_c, slope);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  fence_proxy_async();                           // staging stores -> bulk-store (async proxy) reads
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&tempty[h]);        // this half of the accumulator may be overwritten
+  named_bar_sync(2, Cfg::NEPI * 32);             // all pixel blocks staged
+  if (ablate & 16) return;
+  const int wv = min(Cfg::TW, W - j0);
+  const bool bulk = ops == Cfg::NDISP && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (bulk) {
+    if (ew < Cfg::TH && lane == 0) {
+      const int i = i0 + ew;
+      if (i < H)
+        bulk_store(out + ((size_t)((size_t)b * H + i) * W + j0) * Cfg::NDISP, staging + ew * Cfg::ROW_FLOATS,
+                   (uint32_t)(wv * Cfg::NDISP * 4));
+      bulk_commit();
+    }
+  } else {
+    // strided / unaligned output: 8 rows x 3 thirds = 24 items over the 12 warps, coalesced scalar copies
+    const int n = wv * Cfg::NDISP;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int item = ew + it * Cfg::NEPI, row = item / 3, third = item - row * 3, i = i0 + row;
+      if (i >= H) continue;
+      const float* src = staging + row * Cfg::ROW_FLOATS;
+      float* dst = out + ((size_t)((size_t)b * H + i) * W + j0) * (size_t)ops;
+      const int g0 = third * 432 + lane, gend = min(n, (third + 1) * 432);
+      int p = g0 / Cfg::NDISP, e = g0 - p * Cfg::NDISP;  // element e of pixel p
+      for (int g = g0; g < gend; g += 32) {
+        dst[(size_t)p * ops + e] = src[g];
+        e += 32;
+        if (e >= Cfg::NDISP) { e -= Cfg::NDISP; ++p; }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t tc_prologue(uint64_t* bars, int nbars_1, int nbars_4, int nbars_e, uint32_t* tmem_slot,
+                                                const unsigned char* smem, int tid, int warp) {
+  // bars: [0, nbars_1) count 1, then nbars_4 with count 4 (split warps), then nbars_e with count 6
+  // (epilogue warps of one half).  Warp 1 allocates all 512 TMEM columns (384 used; one CTA per SM).
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    for (int k = 0; k < nbars_1 + nbars_4 + nbars_e; ++k)
+      mbar_init(&bars[k], k < nbars_1 ? 1 : (k < nbars_1 + nbars_4 ? 4 : TcCfg::NEPI / 2));
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *tmem_slot;
+}
+__device__ __forceinline__ void tc_teardown(uint32_t tmem, int warp) {
+  bulk_wait_read<0>();  // (epilogue issuer lanes) shared memory must outlive the engine's reads
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming kernel: any C % 8 == 0.  K chunks flow through NST stages; the six MMAs of a chunk cover
+// both halves of N, so the accumulator is published once per tile.
+__global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
+corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
+                          float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
+                          int tiles_x, int tiles_y, int ntiles, int ablate) {
+  // ablate (dev, QPWC_ABLATE): bit0 no accumulator drain, bit1 no operand split, bit2 no MMAs, bit3 no loads,
+  // bit4 no copy-out
+  using Cfg = TcCfg;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::S_OFF_BARS);
+  uint64_t* raw_full = bars;                      // count 1 (+tx)
+  uint64_t* stage_free = raw_full + Cfg::NST;     // count 1 (commit)
+  uint64_t* tfull = stage_free + Cfg::NST;        // [2] count 1 (commit)
+  uint64_t* lo_full = tfull + 2;                  // count 4
+  uint64_t* tempty = lo_full + Cfg::NST;          // [2] count 6
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* staging = reinterpret_cast<float*>(smem + Cfg::S_OFF_STAGING);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nchunks = C / Cfg::KC;
+  const uint32_t tmem = tc_prologue(bars, 2 * Cfg::NST + 2, Cfg::NST, 2, tmem_slot, smem, tid, warp);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ------------------------------------------------------------- TMA producer
+      tma_prefetch_desc(&tmP);
+      tma_prefetch_desc(&tmN);
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = tile % tiles_x, rest = tile / tiles_x, ty = rest % tiles_y, b = rest / tiles_y;
+        const int i0 = ty * Cfg::TH, j0 = tx * Cfg::TW;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const int s = (int)(g % Cfg::NST);
+          mbar_wait_parked(&stage_free[s], ((g / Cfg::NST) & 1u) ^ 1u);
+          unsigned char* sb = smem + s * Cfg::STAGE_BYTES;
+          if (ablate & 8) { mbar_arrive(&raw_full[s]); continue; }
+          mbar_arrive_expect_tx(&raw_full[s], Cfg::RAW_BYTES);
+          // A: two boxes of 8 cols x 8 rows; TMEM lane quadrant q = 2*cb + rb is the block rows 4*rb.., cols 8*cb..
+          tma_load_4d(sb, &tmP, &raw_full[s], c * Cfg::KC, j0, i0, b);
+          tma_load_4d(sb + 2048, &tmP, &raw_full[s], c * Cfg::KC, j0 + 8, i0, b);
+          tma_load_4d(sb + Cfg::A_BYTES, &tmN, &raw_full[s], c * Cfg::KC, j0 - 4, i0 - 4, b);
+          tma_load_4d(sb + Cfg::A_BYTES + Cfg::BH_BYTES, &tmN, &raw_full[s], c * Cfg::KC, j0 - 4, i0 + 4, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // --------------------------------------------------------------- MMA issuer
+      uint32_t g = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        mbar_wait_parked(&tempty[0], (tcount & 1u) ^ 1u);  // the epilogue has drained both halves
+        mbar_wait_parked(&tempty[1], (tcount & 1u) ^ 1u);
+        tc_fence_after();
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const int s = (int)(g % Cfg::NST);
+          mbar_wait_parked(&lo_full[s], (g / Cfg::NST) & 1u);
+          tc_fence_after();
+          const uint32_t a_raw = smem_u32(smem + s * Cfg::STAGE_BYTES), b_raw = a_raw + Cfg::A_BYTES;
+          if (!(ablate & 4))
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            umma_x3(tmem + (uint32_t)(h * Cfg::NHALF), a_raw, a_raw + Cfg::RAW_BYTES, b_raw + h * Cfg::BH_BYTES,
+                    b_raw + Cfg::RAW_BYTES + h * Cfg::BH_BYTES, c > 0 ? 1u : 0u);
+          umma_commit(&stage_free[s]);  // stage reusable once these MMAs have read it
+        }
+        umma_commit(&tfull[0]);
+        umma_commit(&tfull[1]);
+      }
+    }
+  } else if (warp < 6) {  // ---------------------------------------------------------- operand split
+    const int st = tid - 64;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int c = 0; c < nchunks; ++c, ++g) {
+        const int s = (int)(g % Cfg::NST);
+        mbar_wait(&raw_full[s], (g / Cfg::NST) & 1u);
+        if (!(ablate & 2)) split_block(smem + s * Cfg::STAGE_BYTES, smem + s * Cfg::STAGE_BYTES + Cfg::RAW_BYTES, Cfg::RAW_BYTES, st);
+        fence_proxy_async();  // generic-proxy stores -> tensor-core (async proxy) reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&lo_full[s]);
+      }
+    }
+  } else {  // --------------------------------------------------------------------------- epilogue
+    const int ew = warp - 6, q = warp & 3, part = ew >> 2;
+    const float inv_c = 1.f / (float)C;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int tx = tile % tiles_x, rest = tile / tiles_x, ty = rest % tiles_y, b = rest / tiles_y;
+      tc_epilogue_tile(staging, tmem, tfull, tempty, tcount, q, part, ew, lane, out, b, ty * Cfg::TH, tx * Cfg::TW,
+                       H, W, ops, inv_c, slope, ablate);
+    }
+  }
+  tc_teardown(tmem, warp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resident kernel: C <= 32.  All K chunks of a tile fit in shared memory, so (1) the MMAs run half-major
+// -- the first half of N is published (and drained by the epilogue) while the second is being
+// computed, and the next tile's first half while this tile's second drains -- and (2) a CTA walks
+// vertically consecutive tiles of one strip: the lower half-tile of second-frame rows of tile k is the
+// upper half-tile of tile k+1 and stays where it is ("rolling rows"): only 8 new second-frame rows are
+// loaded and split per tile instead of 16.
+__global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
+corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
+                       float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
+                       int tiles_x, int tiles_y, int seg, int nseg, int nunits, int ablate) {
+  using Cfg = TcCfg;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::R_OFF_BARS);
+  uint64_t* afull = bars;        // [2] count 1 (+tx)
+  uint64_t* bfull = afull + 2;   // [2]
+  uint64_t* afree = bfull + 2;   // [2] count 1 (commit)
+  uint64_t* bfree = afree + 2;   // [2]
+  uint64_t* tfull = bfree + 2;   // [2]
+  uint64_t* alo = tfull + 2;     // [2] count 4
+  uint64_t* blo = alo + 2;       // [2]
+  uint64_t* tempty = blo + 2;    // [2] count 6
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* staging = reinterpret_cast<float*>(smem + Cfg::R_OFF_STAGING);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nchunks = C / Cfg::KC;
+  const uint32_t tmem = tc_prologue(bars, 10, 4, 2, tmem_slot, smem, tid, warp);
+  // operand buffers: A buffer a: raw at R_OFF_A + a*2*RA_BYTES, lo RA_BYTES further, chunk c at c*A_BYTES;
+  // B block p: raw at R_OFF_B + p*2*RB_BYTES, lo RB_BYTES further, chunk c at c*BH_BYTES
+#define QPWC_ABUF(a) (smem + Cfg::R_OFF_A + (a) * 2 * Cfg::RA_BYTES)
+#define QPWC_BBLK(p) (smem + Cfg::R_OFF_B + (p) * 2 * Cfg::RB_BYTES)
+#define QPWC_FOR_UNITS                                                                           \
+  for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {                                \
+    const int tx = unit % tiles_x, rest_ = unit / tiles_x, sg = rest_ % nseg, b = rest_ / nseg;  \
+    const int ty0 = sg * seg, nt = min(seg, tiles_y - ty0), j0 = tx * Cfg::TW;                   \
+    (void)b; (void)j0;                                                                           \
+    for (int k = 0; k < nt; ++k, ++T) {                                                          \
+      const int i0 = (ty0 + k) * Cfg::TH;                                                        \
+      (void)i0;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ------------------------------------------------------------- TMA producer
+      tma_prefetch_desc(&tmP);
+      tma_prefetch_desc(&tmN);
+      uint32_t T = 0, ua = 0, ub = 0;  // bit a / bit p: parity of the fills of that buffer so far
+      QPWC_FOR_UNITS
+        const int a = (int)(T & 1u);
+        mbar_wait_parked(&afree[a], ((ua >> a) & 1u) ^ 1u);
+        ua ^= 1u << a;
+        if (ablate & 8) mbar_arrive(&afull[a]);
+        else {
+          mbar_arrive_expect_tx(&afull[a], (uint32_t)(nchunks * Cfg::A_BYTES));
+          for (int c = 0; c < nchunks; ++c) {
+            tma_load_4d(QPWC_ABUF(a) + c * Cfg::A_BYTES, &tmP, &afull[a], c * Cfg::KC, j0, i0, b);
+            tma_load_4d(QPWC_ABUF(a) + c * Cfg::A_BYTES + 2048, &tmP, &afull[a], c * Cfg::KC, j0 + 8, i0, b);
+          }
+        }
+        // second-frame half-tile blocks: tile k reads block k&1 (rows i0-4..i0+3) and block (k+1)&1
+        // (rows i0+4..i0+11); only the first tile of a segment loads both
+        for (int hb = (k == 0 ? 0 : 1); hb < 2; ++hb) {
+          const int p = (k + hb) & 1;
+          mbar_wait_parked(&bfree[p], ((ub >> p) & 1u) ^ 1u);
+          ub ^= 1u << p;
+          if (ablate & 8) { mbar_arrive(&bfull[p]); continue; }
+          mbar_arrive_expect_tx(&bfull[p], (uint32_t)(nchunks * Cfg::BH_BYTES));
+          for (int c = 0; c < nchunks; ++c)
+            tma_load_4d(QPWC_BBLK(p) + c * Cfg::BH_BYTES, &tmN, &bfull[p], c * Cfg::KC, j0 - 4, i0 - 4 + hb * 8, b);
+        }
+      }}
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // --------------------------------------------------------------- MMA issuer
+      uint32_t T = 0, ma = 0, mb = 0;
+      QPWC_FOR_UNITS
+        const int a = (int)(T & 1u), top = k & 1, bot = (k + 1) & 1;
+        const uint32_t a_raw = smem_u32(QPWC_ABUF(a)), a_lo = a_raw + Cfg::RA_BYTES;
+        mbar_wait_parked(&alo[a], (ma >> a) & 1u);
+        ma ^= 1u << a;
+        if (k == 0) { mbar_wait_parked(&blo[top], (mb >> top) & 1u); mb ^= 1u << top; }  // k > 0: waited for as `bot` of tile k-1
+        mbar_wait_parked(&tempty[0], (T & 1u) ^ 1u);
+        tc_fence_after();
+        {
+          const uint32_t b_raw = smem_u32(QPWC_BBLK(top)), b_lo = b_raw + Cfg::RB_BYTES;
+          if (!(ablate & 4))
+            for (int c = 0; c < nchunks; ++c)
+              umma_x3(tmem, a_raw + c * Cfg::A_BYTES, a_lo + c * Cfg::A_BYTES, b_raw + c * Cfg::BH_BYTES, b_lo + c * Cfg::BH_BYTES, c > 0 ? 1u : 0u);
+          umma_commit(&tfull[0]);
+          umma_commit(&bfree[top]);  // the upper block is dead once these MMAs have read it
+        }
+        mbar_wait_parked(&blo[bot], (mb >> bot) & 1u);
+        mb ^= 1u << bot;
+        mbar_wait_parked(&tempty[1], (T & 1u) ^ 1u);
+        tc_fence_after();
+        {
+          const uint32_t b_raw = smem_u32(QPWC_BBLK(bot)), b_lo = b_raw + Cfg::RB_BYTES;
+          if (!(ablate & 4))
+            for (int c = 0; c < nchunks; ++c)
+              umma_x3(tmem + Cfg::NHALF, a_raw + c * Cfg::A_BYTES, a_lo + c * Cfg::A_BYTES, b_raw + c * Cfg::BH_BYTES, b_lo + c * Cfg::BH_BYTES, c > 0 ? 1u : 0u);
+          umma_commit(&tfull[1]);
+          umma_commit(&afree[a]);
+          if (k == nt - 1) umma_commit(&bfree[bot]);  // end of the segment: nobody inherits the lower block
+        }
+      }}
+    }
+  } else if (warp < 6) {  // ---------------------------------------------------------- operand split
+    const int st = tid - 64;
+    uint32_t T = 0, ja = 0, jb = 0;
+    QPWC_FOR_UNITS
+      const int a = (int)(T & 1u);
+      mbar_wait(&afull[a], (ja >> a) & 1u);
+      ja ^= 1u << a;
+      if (!(ablate & 2)) split_block(QPWC_ABUF(a), QPWC_ABUF(a) + Cfg::RA_BYTES, nchunks * Cfg::A_BYTES, st);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&alo[a]);
+      for (int hb = (k == 0 ? 0 : 1); hb < 2; ++hb) {
+        const int p = (k + hb) & 1;
+        mbar_wait(&bfull[p], (jb >> p) & 1u);
+        jb ^= 1u << p;
+        if (!(ablate & 2)) split_block(QPWC_BBLK(p), QPWC_BBLK(p) + Cfg::RB_BYTES, nchunks * Cfg::BH_BYTES, st);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&blo[p]);
+      }
+    }}
+  } else {  // --------------------------------------------------------------------------- epilogue
+    const int ew = warp - 6, q = warp & 3, part = ew >> 2;
+    const float inv_c = 1.f / (float)C;
+    uint32_t T = 0;
+    QPWC_FOR_UNITS
+      tc_epilogue_tile(staging, tmem, tfull, tempty, T, q, part, ew, lane, out, b, i0, j0, H, W, ops, inv_c, slope, ablate);
+    }}
+  }
+  tc_teardown(tmem, warp);
+#undef QPWC_FOR_UNITS
+#undef QPWC_ABUF
+#undef QPWC_BBLK
+}
+
+int sm_count_cached();
+
+int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, int H, int W, int C, int d,
+                       float slope, long long ops, cudaStream_t stream) {
+  // domain: d == 4, C a multiple of 8, 16-byte aligned inputs (TMA)
+  if (d != 4 || (C & 7) || C < 8) return QPWC_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15)) return QPWC_ERR_UNSUPPORTED;
+  using Cfg = TcCfg;
+  TensorMap tmP, tmN;
+  if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::KC, 8, 8)) return QPWC_ERR_CUDA;           // A: 8 cols x 8 rows
+  if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, Cfg::KC, Cfg::NCOL, 8)) return QPWC_ERR_CUDA;   // B: 24 cols x 8 rows (half tile)
+  const int tiles_x = cdiv(W, Cfg::TW), tiles_y = cdiv(H, Cfg::TH);
+  const long long nt = (long long)tiles_x * tiles_y * B;
+  if (nt >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
+  static int ablate = -1;
+  if (ablate < 0) { const char* ev = getenv("QPWC_ABLATE"); ablate = ev ? atoi(ev) : 0; }
+  const int sms = sm_count_cached();
+  if (C <= Cfg::MAXCH * Cfg::KC && !(ablate & 32)) {
+    // segments of vertically consecutive tiles; short enough that every SM gets several
+    int seg = tiles_y;
+    while (seg > 2 && (long long)tiles_x * B * cdiv(tiles_y, seg) < 4LL * sms) seg = cdiv(seg, 2);
+    const int nseg = cdiv(tiles_y, seg);
+    const int nunits = tiles_x * B * nseg;
+    const cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::R_SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_fwd_tc: smem attribute (%d B): %s", Cfg::R_SMEM_BYTES, cudaGetErrorString(e));
+    corr_fwd_tc_res_kernel<<<nunits < sms ? nunits : sms, Cfg::NTHREADS, Cfg::R_SMEM_BYTES, stream>>>(
+        tmP, tmN, out, B, H, W, C, slope, ops, tiles_x, tiles_y, seg, nseg, nunits, ablate);
+    return check_launch("corr_fwd_tc_res");
+  }
+  const int ntiles = (int)nt;
+  const cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::S_SMEM_BYTES);
+  if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_fwd_tc: smem attribute (%d B): %s", Cfg::S_SMEM_BYTES, cudaGetErrorString(e));
+  corr_fwd_tc_stream_kernel<<<ntiles < sms ? ntiles : sms, Cfg::NTHREADS, Cfg::S_SMEM_BYTES, stream>>>(
+      tmP, tmN, out, B, H, W, C, slope, ops, tiles_x, tiles_y, ntiles, ablate);
+  return check_launch("corr_fwd_tc_stream");
+}
+
+#else  // CPU emulation build: the tensor-core kernel has no stand-in; callers fall back to the FFMA kernels
+int launch_corr_fwd_tc(const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t) {
+  return QPWC_ERR_UNSUPPORTED;
+}
+#endif
+
+}  // namespace qpwc

@@ -715,5 +715,19 @@ class host_batch:
         return False
 
 
+_ENGINES = {"auto": 0, "ffma": 1, "tc": 2}
+
+
+def set_corr_engine(name: str) -> None:
+    """Cost-volume forward arithmetic: 'auto' (tensor cores, 3xTF32 split, where the shape allows),
+    'ffma' (plain fp32 FFMA kernels only) or 'tc' (tensor cores or an error).  Process-wide."""
+    check(lib().qpwc_set_option(0, _ENGINES[name]))
+
+
+def get_corr_engine() -> str:
+    v = int(lib().qpwc_get_option(0))
+    return {v_: k for k, v_ in _ENGINES.items()}[v]
+
+
 def library_version() -> int:
     return int(lib().qpwc_version())
