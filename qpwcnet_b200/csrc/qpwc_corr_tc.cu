@@ -42,7 +42,13 @@ struct TcCfg {
   static constexpr int ROW_FLOATS = TW * NDISP;           // staging: the tile's NHWC output image, 8 rows of 16 x 81
   static constexpr int STAGING_BYTES = TH * ROW_FLOATS * 4;
   static constexpr int NEPI = 12;                         // epilogue warps: 3 per TMEM lane quadrant
-  static constexpr int NTHREADS = (2 + 4 + NEPI) * 32;    // TMA, MMA, 4 split warps, epilogue
+  // warpgroup 0: TMA warp, MMA warp (+2 idle); warpgroup 1: 4 split warps; warpgroups 2-4: epilogue.
+  // Roles are warpgroup-aligned so that setmaxnreg can move registers to the epilogue warps, which
+  // hold four accumulator rows (64 registers) at a time.
+  static constexpr int W_SPLIT = 4, W_EPI = 8;
+  static constexpr int NTHREADS = (W_EPI + NEPI) * 32;
+  static constexpr int REG_CTRL = 40, REG_SPLIT = 56, REG_EPI = 128;  // launch: 96 each; the decs free exactly what the incs take
+  static_assert(128 * REG_CTRL + 128 * REG_SPLIT + NEPI * 32 * REG_EPI <= 96 * NTHREADS, "register budget (the pool is the launch allocation)");
   // ---- streaming kernel (any C % 8 == 0): NST stages of one 8-channel chunk, [A raw | B raw | A lo | B lo]
   static constexpr int RAW_BYTES = A_BYTES + B_BYTES, STAGE_BYTES = 2 * RAW_BYTES;
   static constexpr int NST = 5;
@@ -52,11 +58,14 @@ struct TcCfg {
   // ---- resident kernel (C <= 32: all K chunks of a tile stay in shared memory): two A buffers and two
   // half-tile B blocks (8 second-frame rows each), raw + lo, MAXCH chunks each
   static constexpr int MAXCH = 4;
-  static constexpr int RA_BYTES = MAXCH * A_BYTES, RB_BYTES = MAXCH * BH_BYTES;   // 16 KB, 24 KB (raw; lo follows)
-  static constexpr int R_OFF_A = 0, R_OFF_B = 2 * 2 * RA_BYTES;                   // A: 64 KB, B: 96 KB
-  static constexpr int R_OFF_STAGING = R_OFF_B + 2 * 2 * RB_BYTES;
+  static constexpr int RA_BYTES = MAXCH * A_BYTES, RB_BYTES = MAXCH * BH_BYTES;   // 16 KB (raw), 24 KB (raw; lo follows)
+  static constexpr int NBLK = 3;                                                  // ring of half-tile B blocks
+  static constexpr int R_OFF_A = 0, R_OFF_B = 2 * RA_BYTES;                       // A: 32 KB, B: 144 KB
+  static constexpr int R_OFF_STAGING = R_OFF_B + NBLK * 2 * RB_BYTES;
   static constexpr int R_OFF_BARS = R_OFF_STAGING + STAGING_BYTES;
-  static constexpr int R_SMEM_BYTES = R_OFF_BARS + 16 * 8 + 16;
+  static constexpr int R_SMEM_BYTES = R_OFF_BARS + 24 * 8 + 16;
+  // TMEM columns: accumulator 0..383; A operand (hi, lo) of buffer a, chunk c at 384 + 64*a + 16*c (+8 for lo)
+  static constexpr int TM_A = 384;
   static_assert(S_SMEM_BYTES <= 232448 && R_SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0 && BH_BYTES % 256 == 0, "swizzle phase of every operand block");
 };
@@ -82,16 +91,29 @@ __device__ __forceinline__ void umma_x3(uint32_t d, uint32_t a_raw, uint32_t a_l
   umma_tf32(d, umma_desc_sw32(a_lo), umma_desc_sw32(b_raw), 1u);
   umma_tf32(d, umma_desc_sw32(a_raw), umma_desc_sw32(b_lo), 1u);
 }
+// A operand from tensor memory (lane = pixel, one column per channel of the chunk), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(kIdesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_x3_ts(uint32_t d, uint32_t a_tm, uint32_t b_raw, uint32_t b_lo, uint32_t acc) {
+  umma_tf32_ts(d, a_tm, umma_desc_sw32(b_raw), acc);       // hi.hi
+  umma_tf32_ts(d, a_tm + 8, umma_desc_sw32(b_raw), 1u);    // lo.hi
+  umma_tf32_ts(d, a_tm, umma_desc_sw32(b_lo), 1u);         // hi.lo
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ float tf32_lo(float x) {
-  const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);  // exact
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
-  return __uint_as_float(t);
+  // lo = x - trunc_tf32(x) is exact (<= 13 significant bits).  Adding half a tf32 ulp to its bit
+  // pattern makes the tensor core's own truncation of the operand a round-to-nearest (cvt.rna.tf32
+  // is a ~8-instruction sequence on sm_100; this is 3 instructions per element).
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float(__float_as_uint(r) + 0x1000u);
 }
 // lo = rna(x - trunc(x)) for `bytes` of a raw operand block, elementwise (any swizzle: same offsets)
 __device__ __forceinline__ void split_block(const unsigned char* src, unsigned char* dst, int bytes, int st) {
@@ -126,42 +148,44 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
   // row (y - r) of the band of pixel (rb*4 + r, cb*8 + c) starts at lane_base[9*y]
   float* lane_base = staging + (rb * 4 + r) * Cfg::ROW_FLOATS + (cb * 8 + c) * Cfg::NDISP - 9 * r;
   const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((rb * 4 + y0) * Cfg::NCOL + cb * 8);
-  // the bulk stores of the previous tile must have finished reading the staging image
-  if (ew < Cfg::TH && lane == 0) bulk_wait_read<0>();
-  named_bar_sync(1, Cfg::NEPI * 32);
-  mbar_wait(&tfull[h], tcount & 1u);
+  mbar_wait_parked(&tfull[h], tcount & 1u);
   tc_fence_after();
+  // all four rows of this warp's share into registers first: the accumulator half is released as soon
+  // as the loads have landed, before the shifting and staging work
+  uint32_t u[4][16];
   if (!(ablate & 1)) {
 #pragma unroll
-    for (int yy = 0; yy < 4; yy += 2) {
-      uint32_t u0[16], u1[16];
-      QPWC_TMEM_LD16(u0, tq + (uint32_t)(yy * Cfg::NCOL));
-      QPWC_TMEM_LD16(u1, tq + (uint32_t)((yy + 1) * Cfg::NCOL));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int yy = 0; yy < 4; ++yy) QPWC_TMEM_LD16(u[yy], tq + (uint32_t)(yy * Cfg::NCOL));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&tempty[h]);        // this half of the accumulator may be overwritten
+  // the bulk stores of the previous tile must have finished reading the staging image (waited for
+  // here, after the accumulator loads, so that the engine's reads overlap the wait for the MMAs)
+  if (ew < Cfg::TH && lane == 0) bulk_wait_read<0>();
+  named_bar_sync(1, Cfg::NEPI * 32);
+  if (!(ablate & 1)) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float v[16];
+    for (int yy = 0; yy < 4; ++yy) {
+      float v[16];
 #pragma unroll
-        for (int x = 0; x < 16; ++x) v[x] = __uint_as_float(half ? u1[x] : u0[x]);
+      for (int x = 0; x < 16; ++x) v[x] = __uint_as_float(u[yy][x]);
 #pragma unroll
-        for (int x = 0; x < 12; ++x) v[x] = c4 ? v[x + 4] : v[x];
+      for (int x = 0; x < 12; ++x) v[x] = c4 ? v[x + 4] : v[x];
 #pragma unroll
-        for (int x = 0; x < 10; ++x) v[x] = c2 ? v[x + 2] : v[x];
+      for (int x = 0; x < 10; ++x) v[x] = c2 ? v[x + 2] : v[x];
 #pragma unroll
-        for (int x = 0; x < 9; ++x) v[x] = c1 ? v[x + 1] : v[x];
-        const int y = y0 + yy + half;
-        if ((unsigned)(y - r) <= 8u) {
-          float* sp = lane_base + 9 * y;
+      for (int x = 0; x < 9; ++x) v[x] = c1 ? v[x + 1] : v[x];
+      const int y = y0 + yy;
+      if ((unsigned)(y - r) <= 8u) {
+        float* sp = lane_base + 9 * y;
 #pragma unroll
-          for (int k = 0; k < 9; ++k) sp[k] = lrelu(v[k] * inv_c, slope);
-        }
+        for (int k = 0; k < 9; ++k) sp[k] = lrelu(v[k] * inv_c, slope);
       }
     }
   }
-  tc_fence_before();
   fence_proxy_async();                           // staging stores -> bulk-store (async proxy) reads
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&tempty[h]);        // this half of the accumulator may be overwritten
   named_bar_sync(2, Cfg::NEPI * 32);             // all pixel blocks staged
   if (ablate & 16) return;
   const int wv = min(Cfg::TW, W - j0);
@@ -243,7 +267,9 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
   const int nchunks = C / Cfg::KC;
   const uint32_t tmem = tc_prologue(bars, 2 * Cfg::NST + 2, Cfg::NST, 2, tmem_slot, smem, tid, warp);
 
-  if (warp == 0) {
+  if (warp < Cfg::W_SPLIT) {
+   setmaxnreg_dec<Cfg::REG_CTRL>();
+   if (warp == 0) {
     if (lane == 0) {  // ------------------------------------------------------------- TMA producer
       tma_prefetch_desc(&tmP);
       tma_prefetch_desc(&tmN);
@@ -253,7 +279,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
         const int i0 = ty * Cfg::TH, j0 = tx * Cfg::TW;
         for (int c = 0; c < nchunks; ++c, ++g) {
           const int s = (int)(g % Cfg::NST);
-          mbar_wait_parked(&stage_free[s], ((g / Cfg::NST) & 1u) ^ 1u);
+          mbar_wait(&stage_free[s], ((g / Cfg::NST) & 1u) ^ 1u);
           unsigned char* sb = smem + s * Cfg::STAGE_BYTES;
           if (ablate & 8) { mbar_arrive(&raw_full[s]); continue; }
           mbar_arrive_expect_tx(&raw_full[s], Cfg::RAW_BYTES);
@@ -269,12 +295,12 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
     if (lane == 0) {  // --------------------------------------------------------------- MMA issuer
       uint32_t g = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-        mbar_wait_parked(&tempty[0], (tcount & 1u) ^ 1u);  // the epilogue has drained both halves
-        mbar_wait_parked(&tempty[1], (tcount & 1u) ^ 1u);
+        mbar_wait(&tempty[0], (tcount & 1u) ^ 1u);  // the epilogue has drained both halves
+        mbar_wait(&tempty[1], (tcount & 1u) ^ 1u);
         tc_fence_after();
         for (int c = 0; c < nchunks; ++c, ++g) {
           const int s = (int)(g % Cfg::NST);
-          mbar_wait_parked(&lo_full[s], (g / Cfg::NST) & 1u);
+          mbar_wait(&lo_full[s], (g / Cfg::NST) & 1u);
           tc_fence_after();
           const uint32_t a_raw = smem_u32(smem + s * Cfg::STAGE_BYTES), b_raw = a_raw + Cfg::A_BYTES;
           if (!(ablate & 4))
@@ -288,13 +314,15 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
         umma_commit(&tfull[1]);
       }
     }
-  } else if (warp < 6) {  // ---------------------------------------------------------- operand split
-    const int st = tid - 64;
+   }
+  } else if (warp < Cfg::W_EPI) {  // ------------------------------------------------- operand split
+    setmaxnreg_dec<Cfg::REG_SPLIT>();
+    const int st = tid - Cfg::W_SPLIT * 32;
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int c = 0; c < nchunks; ++c, ++g) {
         const int s = (int)(g % Cfg::NST);
-        mbar_wait(&raw_full[s], (g / Cfg::NST) & 1u);
+        mbar_wait_parked(&raw_full[s], (g / Cfg::NST) & 1u);
         if (!(ablate & 2)) split_block(smem + s * Cfg::STAGE_BYTES, smem + s * Cfg::STAGE_BYTES + Cfg::RAW_BYTES, Cfg::RAW_BYTES, st);
         fence_proxy_async();  // generic-proxy stores -> tensor-core (async proxy) reads
         __syncwarp();
@@ -302,7 +330,8 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
       }
     }
   } else {  // --------------------------------------------------------------------------- epilogue
-    const int ew = warp - 6, q = warp & 3, part = ew >> 2;
+    setmaxnreg_inc<Cfg::REG_EPI>();
+    const int ew = warp - Cfg::W_EPI, q = warp & 3, part = ew >> 2;
     const float inv_c = 1.f / (float)C;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
@@ -315,12 +344,16 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Resident kernel: C <= 32.  All K chunks of a tile fit in shared memory, so (1) the MMAs run half-major
-// -- the first half of N is published (and drained by the epilogue) while the second is being
-// computed, and the next tile's first half while this tile's second drains -- and (2) a CTA walks
-// vertically consecutive tiles of one strip: the lower half-tile of second-frame rows of tile k is the
-// upper half-tile of tile k+1 and stays where it is ("rolling rows"): only 8 new second-frame rows are
-// loaded and split per tile instead of 16.
+// Resident kernel: C <= 32.  All K chunks of a tile fit on chip, so (1) the MMAs run half-major -- the
+// first half of N is published (and drained by the epilogue) while the second is being computed, and
+// the next tile's first half while this tile's second drains -- and (2) a CTA walks vertically
+// consecutive tiles of one strip: the lower half-tile of second-frame rows of tile k is the upper
+// half-tile of tile k+1 and stays where it is ("rolling rows"): only 8 new second-frame rows are
+// loaded and split per tile instead of 16.  The half-tile blocks form a ring of three, so the block a
+// tile frees after its first pass is refilled two tile periods before it is needed.  The first-frame
+// operand goes through TMEM: the split warps (warp = TMEM lane quadrant, lane = pixel) read their
+// pixel's channels from the TMA landing buffer and tcgen05.st hi and lo into spare TMEM columns
+// (double-buffered), which halves A's shared-memory footprint and removes its operand reads.
 __global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
 corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
                        float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
@@ -328,23 +361,26 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
   using Cfg = TcCfg;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::R_OFF_BARS);
-  uint64_t* afull = bars;        // [2] count 1 (+tx)
-  uint64_t* bfull = afull + 2;   // [2]
-  uint64_t* afree = bfull + 2;   // [2] count 1 (commit)
-  uint64_t* bfree = afree + 2;   // [2]
-  uint64_t* tfull = bfree + 2;   // [2]
-  uint64_t* alo = tfull + 2;     // [2] count 4
-  uint64_t* blo = alo + 2;       // [2]
-  uint64_t* tempty = blo + 2;    // [2] count 6
+  uint64_t* afull = bars;          // [2] count 1 (+tx): A landed in landing buffer a
+  uint64_t* bfull = afull + 2;     // [3] count 1 (+tx): B block p landed
+  uint64_t* afree = bfull + 3;     // [2] count 1 (commit): TMEM A buffer a no longer read
+  uint64_t* bfree = afree + 2;     // [3] count 1 (commit): B block p no longer read
+  uint64_t* tfull = bfree + 3;     // [2] count 1 (commit)
+  uint64_t* arawfree = tfull + 2;  // [2] count 4: landing buffer a consumed by the split warps
+  uint64_t* alo = arawfree + 2;    // [2] count 4: TMEM A buffer a written
+  uint64_t* blo = alo + 2;         // [3] count 4: B block p split
+  uint64_t* tempty = blo + 3;      // [2] count 6
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* staging = reinterpret_cast<float*>(smem + Cfg::R_OFF_STAGING);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunks = C / Cfg::KC;
-  const uint32_t tmem = tc_prologue(bars, 10, 4, 2, tmem_slot, smem, tid, warp);
-  // operand buffers: A buffer a: raw at R_OFF_A + a*2*RA_BYTES, lo RA_BYTES further, chunk c at c*A_BYTES;
+  const uint32_t tmem = tc_prologue(bars, 12, 7, 2, tmem_slot, smem, tid, warp);
   // B block p: raw at R_OFF_B + p*2*RB_BYTES, lo RB_BYTES further, chunk c at c*BH_BYTES
-#define QPWC_ABUF(a) (smem + Cfg::R_OFF_A + (a) * 2 * Cfg::RA_BYTES)
+#define QPWC_ABUF(a) (smem + Cfg::R_OFF_A + (a) * Cfg::RA_BYTES)
 #define QPWC_BBLK(p) (smem + Cfg::R_OFF_B + (p) * 2 * Cfg::RB_BYTES)
+  // every role walks the same tile sequence; `ring` counts the B blocks allocated so far (block = ring % 3):
+  // the first tile of a segment takes two fresh blocks (top, bot), every other tile inherits its top
+  // from the previous tile's bot and takes one fresh block
 #define QPWC_FOR_UNITS                                                                           \
   for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {                                \
     const int tx = unit % tiles_x, rest_ = unit / tiles_x, sg = rest_ % nseg, b = rest_ / nseg;  \
@@ -352,16 +388,22 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
     (void)b; (void)j0;                                                                           \
     for (int k = 0; k < nt; ++k, ++T) {                                                          \
       const int i0 = (ty0 + k) * Cfg::TH;                                                        \
+      if (k == 0) { top = (int)(ring % 3u); ++ring; } else top = bot;                            \
+      bot = (int)(ring % 3u); ++ring;                                                            \
       (void)i0;
+#define QPWC_PAR(mask, idx) (((mask) >> (idx)) & 1u)
 
-  if (warp == 0) {
+  if (warp < Cfg::W_SPLIT) {
+   setmaxnreg_dec<Cfg::REG_CTRL>();
+   if (warp == 0) {
     if (lane == 0) {  // ------------------------------------------------------------- TMA producer
       tma_prefetch_desc(&tmP);
       tma_prefetch_desc(&tmN);
-      uint32_t T = 0, ua = 0, ub = 0;  // bit a / bit p: parity of the fills of that buffer so far
+      uint32_t T = 0, ring = 0, ua = 0, ub = 0;
+      int top = 0, bot = 0;
       QPWC_FOR_UNITS
         const int a = (int)(T & 1u);
-        mbar_wait_parked(&afree[a], ((ua >> a) & 1u) ^ 1u);
+        mbar_wait(&arawfree[a], QPWC_PAR(ua, a) ^ 1u);
         ua ^= 1u << a;
         if (ablate & 8) mbar_arrive(&afull[a]);
         else {
@@ -371,11 +413,11 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
             tma_load_4d(QPWC_ABUF(a) + c * Cfg::A_BYTES + 2048, &tmP, &afull[a], c * Cfg::KC, j0 + 8, i0, b);
           }
         }
-        // second-frame half-tile blocks: tile k reads block k&1 (rows i0-4..i0+3) and block (k+1)&1
-        // (rows i0+4..i0+11); only the first tile of a segment loads both
+        // second-frame half-tile blocks: rows i0-4..i0+3 (top) and i0+4..i0+11 (bot); only the first
+        // tile of a segment loads its top
         for (int hb = (k == 0 ? 0 : 1); hb < 2; ++hb) {
-          const int p = (k + hb) & 1;
-          mbar_wait_parked(&bfree[p], ((ub >> p) & 1u) ^ 1u);
+          const int p = hb ? bot : top;
+          mbar_wait(&bfree[p], QPWC_PAR(ub, p) ^ 1u);
           ub ^= 1u << p;
           if (ablate & 8) { mbar_arrive(&bfull[p]); continue; }
           mbar_arrive_expect_tx(&bfull[p], (uint32_t)(nchunks * Cfg::BH_BYTES));
@@ -386,52 +428,76 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {  // --------------------------------------------------------------- MMA issuer
-      uint32_t T = 0, ma = 0, mb = 0;
+      uint32_t T = 0, ring = 0, ma = 0, mb = 0;
+      int top = 0, bot = 0;
       QPWC_FOR_UNITS
-        const int a = (int)(T & 1u), top = k & 1, bot = (k + 1) & 1;
-        const uint32_t a_raw = smem_u32(QPWC_ABUF(a)), a_lo = a_raw + Cfg::RA_BYTES;
-        mbar_wait_parked(&alo[a], (ma >> a) & 1u);
+        const int a = (int)(T & 1u);
+        const uint32_t a_tm = tmem + (uint32_t)(Cfg::TM_A + a * 64);
+        mbar_wait(&alo[a], QPWC_PAR(ma, a));
         ma ^= 1u << a;
-        if (k == 0) { mbar_wait_parked(&blo[top], (mb >> top) & 1u); mb ^= 1u << top; }  // k > 0: waited for as `bot` of tile k-1
-        mbar_wait_parked(&tempty[0], (T & 1u) ^ 1u);
+        if (k == 0) { mbar_wait(&blo[top], QPWC_PAR(mb, top)); mb ^= 1u << top; }  // k > 0: waited for as `bot` of tile k-1
+        mbar_wait(&tempty[0], (T & 1u) ^ 1u);
         tc_fence_after();
         {
           const uint32_t b_raw = smem_u32(QPWC_BBLK(top)), b_lo = b_raw + Cfg::RB_BYTES;
           if (!(ablate & 4))
             for (int c = 0; c < nchunks; ++c)
-              umma_x3(tmem, a_raw + c * Cfg::A_BYTES, a_lo + c * Cfg::A_BYTES, b_raw + c * Cfg::BH_BYTES, b_lo + c * Cfg::BH_BYTES, c > 0 ? 1u : 0u);
+              umma_x3_ts(tmem, a_tm + c * 16, b_raw + c * Cfg::BH_BYTES, b_lo + c * Cfg::BH_BYTES, c > 0 ? 1u : 0u);
           umma_commit(&tfull[0]);
           umma_commit(&bfree[top]);  // the upper block is dead once these MMAs have read it
         }
-        mbar_wait_parked(&blo[bot], (mb >> bot) & 1u);
+        mbar_wait(&blo[bot], QPWC_PAR(mb, bot));
         mb ^= 1u << bot;
-        mbar_wait_parked(&tempty[1], (T & 1u) ^ 1u);
+        mbar_wait(&tempty[1], (T & 1u) ^ 1u);
         tc_fence_after();
         {
           const uint32_t b_raw = smem_u32(QPWC_BBLK(bot)), b_lo = b_raw + Cfg::RB_BYTES;
           if (!(ablate & 4))
             for (int c = 0; c < nchunks; ++c)
-              umma_x3(tmem + Cfg::NHALF, a_raw + c * Cfg::A_BYTES, a_lo + c * Cfg::A_BYTES, b_raw + c * Cfg::BH_BYTES, b_lo + c * Cfg::BH_BYTES, c > 0 ? 1u : 0u);
+              umma_x3_ts(tmem + Cfg::NHALF, a_tm + c * 16, b_raw + c * Cfg::BH_BYTES, b_lo + c * Cfg::BH_BYTES, c > 0 ? 1u : 0u);
           umma_commit(&tfull[1]);
           umma_commit(&afree[a]);
           if (k == nt - 1) umma_commit(&bfree[bot]);  // end of the segment: nobody inherits the lower block
         }
       }}
     }
-  } else if (warp < 6) {  // ---------------------------------------------------------- operand split
-    const int st = tid - 64;
-    uint32_t T = 0, ja = 0, jb = 0;
+   }
+  } else if (warp < Cfg::W_EPI) {  // ------------------------------------------------- operand split
+    setmaxnreg_dec<Cfg::REG_SPLIT>();
+    const int st = tid - Cfg::W_SPLIT * 32, qd = warp & 3;  // qd: the TMEM lane quadrant this warp may write
+    const int m = qd * 32 + lane;            // its pixel = row of A = TMEM lane
+    uint32_t T = 0, ring = 0, ja = 0, jf = 0, jb = 0;
+    int top = 0, bot = 0;
     QPWC_FOR_UNITS
       const int a = (int)(T & 1u);
-      mbar_wait(&afull[a], (ja >> a) & 1u);
+      mbar_wait_parked(&afull[a], QPWC_PAR(ja, a));
       ja ^= 1u << a;
-      if (!(ablate & 2)) split_block(QPWC_ABUF(a), QPWC_ABUF(a) + Cfg::RA_BYTES, nchunks * Cfg::A_BYTES, st);
-      fence_proxy_async();
+      mbar_wait_parked(&afree[a], QPWC_PAR(jf, a) ^ 1u);  // the MMAs of two tiles ago have finished reading TMEM buffer a
+      jf ^= 1u << a;
+      tc_fence_after();
+      if (!(ablate & 2)) {
+        const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + a * 64);
+        for (int c = 0; c < nchunks; ++c) {
+          const unsigned char* src = QPWC_ABUF(a) + c * Cfg::A_BYTES;
+          const float4 v0 = *reinterpret_cast<const float4*>(src + swz32((uint32_t)(m * 32)));
+          const float4 v1 = *reinterpret_cast<const float4*>(src + swz32((uint32_t)(m * 32 + 16)));
+          const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { hi[e] = __float_as_uint(x[e]); lo[e] = __float_as_uint(tf32_lo(x[e])); }
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                       ::"r"(taddr + (uint32_t)(c * 16)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                       ::"r"(taddr + (uint32_t)(c * 16 + 8)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&alo[a]);
+      if (lane == 0) { mbar_arrive(&arawfree[a]); mbar_arrive(&alo[a]); }
       for (int hb = (k == 0 ? 0 : 1); hb < 2; ++hb) {
-        const int p = (k + hb) & 1;
-        mbar_wait(&bfull[p], (jb >> p) & 1u);
+        const int p = hb ? bot : top;
+        mbar_wait_parked(&bfull[p], QPWC_PAR(jb, p));
         jb ^= 1u << p;
         if (!(ablate & 2)) split_block(QPWC_BBLK(p), QPWC_BBLK(p) + Cfg::RB_BYTES, nchunks * Cfg::BH_BYTES, st);
         fence_proxy_async();
@@ -440,14 +506,18 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
       }
     }}
   } else {  // --------------------------------------------------------------------------- epilogue
-    const int ew = warp - 6, q = warp & 3, part = ew >> 2;
+    setmaxnreg_inc<Cfg::REG_EPI>();
+    const int ew = warp - Cfg::W_EPI, q = warp & 3, part = ew >> 2;
     const float inv_c = 1.f / (float)C;
-    uint32_t T = 0;
+    uint32_t T = 0, ring = 0;
+    int top = 0, bot = 0;
     QPWC_FOR_UNITS
       tc_epilogue_tile(staging, tmem, tfull, tempty, T, q, part, ew, lane, out, b, i0, j0, H, W, ops, inv_c, slope, ablate);
     }}
+    (void)top; (void)bot;
   }
   tc_teardown(tmem, warp);
+#undef QPWC_PAR
 #undef QPWC_FOR_UNITS
 #undef QPWC_ABUF
 #undef QPWC_BBLK

@@ -47,6 +47,13 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t 
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -56,6 +63,7 @@ __device__ __forceinline__ float rna_tf32(float x) {
 // mode 0: one pass, raw fp32 words      mode 1: one pass, low 13 bits masked off by the kernel
 // mode 2: three passes, hi = raw word (relies on the hardware ignoring the low bits), lo = rna(x - trunc(x))
 // mode 3: three passes, hi = rna(x) written explicitly, lo = rna(x - hi)
+// mode 4: as mode 2 with the A operand (hi and lo) held in TMEM columns 384.. (tcgen05.st), B in shared memory
 __global__ void __launch_bounds__(128, 1)
 tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int mode, int reps,
               long long* cycles) {
@@ -77,7 +85,7 @@ tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* _
     float hi, lo;
     if (mode == 0) { hi = x; lo = 0.f; }
     else if (mode == 1) { hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); lo = 0.f; }
-    else if (mode == 2) { hi = x; lo = rna_tf32(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
+    else if (mode == 2 || mode == 4) { hi = x; lo = rna_tf32(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
     else { hi = rna_tf32(x); lo = rna_tf32(x - hi); }
     const uint32_t off = swz32((uint32_t)(row * 32 + kk * 4));
     unsigned char* ph = (isb ? b_hi + chunk * B_BYTES : a_hi + chunk * A_BYTES) + off;
@@ -98,6 +106,23 @@ tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* _
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  if (mode == 4) {
+    // thread = TMEM lane = row of A: chunk c -> columns 384 + 16c (hi) and 384 + 16c + 8 (lo)
+    const int row = warp * 32 + lane;
+    for (int c = 0; c < NCHUNK; ++c)
+      for (int part = 0; part < 2; ++part) {
+        uint32_t v[8];
+        const unsigned char* src = (part ? a_lo : a_hi) + c * A_BYTES;
+        for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const uint32_t*>(src + swz32((uint32_t)(row * 32 + k * 4)));
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(384 + c * 16 + part * 8);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+      }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
 
   long long t0 = 0, t1 = 0;
   if (tid == 0) {
@@ -110,7 +135,8 @@ tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* _
           for (int p = 0; p < npass; ++p) {
             const unsigned char* ap = (p == 1 ? a_lo : a_hi) + c * A_BYTES;
             const unsigned char* bp = (p == 2 ? b_lo : b_hi) + c * B_BYTES + h * NH * 32;
-            mma_tf32(tmem + h * NH, make_desc(smem_u32(ap)), make_desc(smem_u32(bp)), idesc, (r | c | p) != 0);
+            if (mode == 4) mma_tf32_ts(tmem + h * NH, tmem + 384 + c * 16 + (p == 1 ? 8 : 0), make_desc(smem_u32(bp)), idesc, (r | c | p) != 0);
+            else mma_tf32(tmem + h * NH, make_desc(smem_u32(ap)), make_desc(smem_u32(bp)), idesc, (r | c | p) != 0);
           }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
   }
@@ -174,7 +200,7 @@ int main() {
   cudaFuncSetAttribute(tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   std::vector<float> D0;
   printf("fp32 FFMA (sequential fmaf)        : worst |err| / mean|a.b| = %.3e\n", ffma_worst);
-  for (int mode = 0; mode < 4; ++mode) {
+  for (int mode = 0; mode < 5; ++mode) {
     cudaMemset(dD, 0, D.size() * 4);
     tf32x3_kernel<<<1, 128, smem>>>(dA, dB, dD, mode, 1, dC);
     cudaError_t e = cudaDeviceSynchronize();
@@ -185,8 +211,8 @@ int main() {
       const double err = fabs((double)D[i] / K - ref[i]) / cond[i];
       worst = fmax(worst, err); rms += err * err;
     }
-    const char* names[4] = {"1xTF32 raw fp32 words             ", "1xTF32 low 13 bits masked         ",
-                            "3xTF32 hi=raw word, lo=rna(x-trunc)", "3xTF32 hi=rna(x), lo=rna(x-hi)    "};
+    const char* names[5] = {"1xTF32 raw fp32 words             ", "1xTF32 low 13 bits masked         ",
+                            "3xTF32 hi=raw word, lo=rna(x-trunc)", "3xTF32 hi=rna(x), lo=rna(x-hi)    ", "3xTF32 as [2], A operand in TMEM  "};
     printf("%s: worst |err| / mean|a.b| = %.3e  rms %.3e", names[mode], worst, sqrt(rms / (M * N)));
     if (mode == 0) D0 = D;
     if (mode == 1) {
@@ -198,15 +224,15 @@ int main() {
     printf("\n");
   }
   // rate: many repetitions of the tile's MMA sequence (K = 32)
-  for (int mode = 0; mode <= 2; mode += 2) {
+  for (int mode = 0; mode <= 4; mode += 2) {
     const int reps = 400;
     tf32x3_kernel<<<1, 128, smem>>>(dA, dB, dD, mode, reps, dC);
     cudaDeviceSynchronize();
     long long cyc; cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost);
     const int npass = mode >= 2 ? 3 : 1;
     const double nmma = (double)reps * NCHUNK * 2 * npass;
-    printf("%d-pass tile: %.1f clk per 128x192x8 MMA (floor 96), tile (C=32) = %.0f clk, %.1f dense TF32 TFLOP/s/SM-equivalent x148 = %.0f TFLOP/s at 1.965 GHz\n",
-           npass, cyc / nmma, cyc / (double)reps, 2.0 * 128 * 192 * 8 / (cyc / nmma) * 1.965e9 / 1e12,
+    printf("mode %d, %d-pass tile: %.1f clk per 128x192x8 MMA (floor 96), tile (C=32) = %.0f clk, %.1f dense TF32 TFLOP/s/SM-equivalent x148 = %.0f TFLOP/s at 1.965 GHz\n",
+           mode, npass, cyc / nmma, cyc / (double)reps, 2.0 * 128 * 192 * 8 / (cyc / nmma) * 1.965e9 / 1e12,
            2.0 * 128 * 192 * 8 / (cyc / nmma) * 1.965e9 / 1e12 * 148);
   }
   printf("band utilisation 81/384 = %.3f; fp32-equivalent useful rate of the 3-pass tile = dense rate x 0.211 / 3\n", 81.0 / 384);
