@@ -19,9 +19,13 @@ __host__ __device__ __forceinline__ uint32_t swz32(uint32_t byte_off) {
 __host__ __device__ __forceinline__ uint32_t swz64(uint32_t byte_off) {
   return byte_off ^ (((byte_off >> 7) & 3u) << 4);
 }
-// swizzle matching a pixel stride of PXB bytes (32 -> SWIZZLE_32B, 64 -> SWIZZLE_64B)
+// TMA SWIZZLE_128B: bits [4:6] ^= bits [7:9] (period 1024 B)
+__host__ __device__ __forceinline__ uint32_t swz128(uint32_t byte_off) {
+  return byte_off ^ (((byte_off >> 7) & 7u) << 4);
+}
+// swizzle matching a pixel stride of PXB bytes (32 -> SWIZZLE_32B, 64 -> SWIZZLE_64B, 128 -> SWIZZLE_128B)
 template <int PXB> __host__ __device__ __forceinline__ uint32_t swz(uint32_t byte_off) {
-  return PXB == 32 ? swz32(byte_off) : swz64(byte_off);
+  return PXB == 32 ? swz32(byte_off) : (PXB == 64 ? swz64(byte_off) : swz128(byte_off));
 }
 
 #ifndef QPWC_EMU
@@ -80,6 +84,11 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const TensorMap* tm,
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// L2 prefetch of a 4-D tile (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const TensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 // generic-proxy writes (st.shared) -> async-proxy reads (bulk store): order them
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -162,6 +171,7 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 inline void mbar_wait_parked(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 inline void tma_prefetch_desc(const TensorMap*) {}
+inline void tma_prefetch_l2_4d(const TensorMap*, int, int, int, int) {}
 inline void tma_load_4d(void* smem_dst, const TensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   const int co[4] = {c0, c1, c2, c3};
   unsigned char* dst = static_cast<unsigned char*>(smem_dst);
@@ -200,7 +210,7 @@ inline bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W
   tm->dim[0] = C; tm->dim[1] = W; tm->dim[2] = H; tm->dim[3] = B;
   tm->stride[0] = 1; tm->stride[1] = C; tm->stride[2] = (long long)W * C; tm->stride[3] = (long long)H * W * C;
   tm->box[0] = boxC; tm->box[1] = boxW; tm->box[2] = boxH; tm->box[3] = 1;
-  tm->swizzle = boxC * 4 == 32 ? 1 : 3;
+  tm->swizzle = boxC * 4 == 32 ? 1 : (boxC * 4 == 64 ? 3 : 7);
   return true;
 }
 inline bool make_tmap_nchw(TensorMap* tm, const float* base, int B, int C, int H, int W, int boxW, int boxH, int boxC) {

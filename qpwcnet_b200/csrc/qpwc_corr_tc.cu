@@ -16,16 +16,20 @@
 // (profiles/r02_tf32x3_ubench.txt).
 //
 // Structure: one persistent CTA per SM, warp-specialised.
-//   warp 0    TMA producer: per 8-channel K chunk, 4 boxes of A (4 rows x 8 cols each, so that TMEM
-//             lane quadrant q holds a 4x8 pixel block) + 1 box of B (16 x 24, zero fill == ZeroPadding2D),
-//             SWIZZLE_32B = the canonical K-major UMMA layout (pixel rows 32 B apart).
-//   warp 1    MMA issuer (one thread): 6 MMAs (2 halves of N x 3 passes) per chunk into 384 TMEM
-//             columns; tcgen05.commit releases the stage / publishes the accumulator.
-//   warps 2-5 operand split: lo = rna(x - trunc(x)) for the 16 KB of a stage, elementwise.
-//   warps 6-9 epilogue: warp = TMEM lane quadrant = 4x8 pixel block; reads its 12 x 16 window of the
-//             accumulator (tcgen05.ld 32x32b.x16), scales, leaky-relu, and scatters each lane's 9x9 band
-//             into a bank-conflict-free staging buffer (82-float pixel pitch); then copies the staged
-//             rows to global memory as contiguous 16 x 324-byte runs.
+//   warp 0      TMA producer: boxes of 8 x 8 first-frame pixels (so that TMEM lane quadrant q holds a 4x8
+//               pixel block) and 24 x 8 second-frame pixels (half tiles; zero fill == ZeroPadding2D), with
+//               64- or 128-byte channel rows (SWIZZLE_64B / SWIZZLE_128B = the canonical K-major UMMA
+//               layouts): the TMA engine retires about one row per 2 clk whatever its width, and with
+//               32-byte rows it, not the tensor core, set the pace (profiles/README.md).
+//   warp 1      MMA issuer (one thread): per 8-channel K step and half of N the three passes of the
+//               split product; tcgen05.commit releases operands / publishes the accumulator.
+//   warps 4-7   operand split: the first-frame operand goes through TMEM (warp = lane quadrant, lane =
+//               pixel: hi and lo written with tcgen05.st into spare columns), the second-frame lo
+//               is computed elementwise in shared memory.
+//   warps 8-19  epilogue: warp = TMEM lane quadrant = 4x8 pixel block; the three warps of a quadrant
+//               read four rows each of its 12 x 16 accumulator window (tcgen05.ld 32x32b.x16), shift the
+//               lane's 9 columns into place, scale, leaky-relu and store them into the tile's NHWC
+//               staging image; the 8 staged rows leave as TMA bulk stores (16 x 324 contiguous bytes).
 #include <stdlib.h>
 
 #include "qpwc_async.cuh"
@@ -37,8 +41,6 @@ namespace qpwc {
 struct TcCfg {
   static constexpr int NDISP = 81;
   static constexpr int TH = 8, TW = 16, NROW = 16, NCOL = 24, NHALF = 192;
-  static constexpr int KC = 8, PXB = 32;
-  static constexpr int A_BYTES = TH * TW * PXB, B_BYTES = NROW * NCOL * PXB, BH_BYTES = B_BYTES / 2;  // 4096, 12288, 6144
   static constexpr int ROW_FLOATS = TW * NDISP;           // staging: the tile's NHWC output image, 8 rows of 16 x 81
   static constexpr int STAGING_BYTES = TH * ROW_FLOATS * 4;
   static constexpr int NEPI = 12;                         // epilogue warps: 3 per TMEM lane quadrant
@@ -49,59 +51,55 @@ struct TcCfg {
   static constexpr int NTHREADS = (W_EPI + NEPI) * 32;
   static constexpr int REG_CTRL = 40, REG_SPLIT = 56, REG_EPI = 128;  // launch: 96 each; the decs free exactly what the incs take
   static_assert(128 * REG_CTRL + 128 * REG_SPLIT + NEPI * 32 * REG_EPI <= 96 * NTHREADS, "register budget (the pool is the launch allocation)");
-  // ---- streaming kernel (any C % 8 == 0): NST stages of one 8-channel chunk, [A raw | B raw | A lo | B lo]
-  static constexpr int RAW_BYTES = A_BYTES + B_BYTES, STAGE_BYTES = 2 * RAW_BYTES;
-  static constexpr int NST = 5;
-  static constexpr int S_OFF_STAGING = NST * STAGE_BYTES;
-  static constexpr int S_OFF_BARS = S_OFF_STAGING + STAGING_BYTES;
-  static constexpr int S_SMEM_BYTES = S_OFF_BARS + (3 * NST + 4) * 8 + 16;
-  // ---- resident kernel (C <= 32: all K chunks of a tile stay in shared memory): two A buffers and two
-  // half-tile B blocks (8 second-frame rows each), raw + lo, MAXCH chunks each
-  static constexpr int MAXCH = 4;
-  static constexpr int RA_BYTES = MAXCH * A_BYTES, RB_BYTES = MAXCH * BH_BYTES;   // 16 KB (raw), 24 KB (raw; lo follows)
-  static constexpr int NBLK = 3;                                                  // ring of half-tile B blocks
+  // TMEM columns: accumulator 0..383 (two halves of N); first-frame operand (hi, lo) from column 384:
+  // 16 columns per 8-channel K step (8 hi + 8 lo)
+  static constexpr int TM_A = 384;
+  // ---- resident kernel (C <= 32): 128-byte channel rows.  Two landing buffers for A (128 px), a ring of
+  // three half-tile B blocks (192 px, raw + lo)
+  static constexpr int R_PXB = 128;
+  static constexpr int RA_BYTES = 128 * R_PXB, RB_BYTES = NHALF * R_PXB;          // 16 KB, 24 KB (raw; lo follows)
+  static constexpr int NBLK = 3;
   static constexpr int R_OFF_A = 0, R_OFF_B = 2 * RA_BYTES;                       // A: 32 KB, B: 144 KB
   static constexpr int R_OFF_STAGING = R_OFF_B + NBLK * 2 * RB_BYTES;
   static constexpr int R_OFF_BARS = R_OFF_STAGING + STAGING_BYTES;
   static constexpr int R_SMEM_BYTES = R_OFF_BARS + 24 * 8 + 16;
-  // TMEM columns: accumulator 0..383; A operand (hi, lo) of buffer a, chunk c at 384 + 64*a + 16*c (+8 for lo)
-  static constexpr int TM_A = 384;
+  // ---- streaming kernel (any C % 8 == 0): stages of 16 channels, 64-byte rows; per stage both B half
+  // tiles (raw + lo) and an A landing buffer
+  static constexpr int S_PXB = 64, S_KC = 16, NST = 3;
+  static constexpr int SB_BYTES = 2 * NHALF * S_PXB, SA_BYTES = 128 * S_PXB;      // 24 KB (raw; lo follows), 8 KB
+  static constexpr int S_OFF_A = NST * 2 * SB_BYTES;
+  static constexpr int S_OFF_STAGING = S_OFF_A + NST * SA_BYTES;
+  static constexpr int S_OFF_BARS = S_OFF_STAGING + STAGING_BYTES;
+  static constexpr int S_SMEM_BYTES = S_OFF_BARS + (3 * NST + 4) * 8 + 16;
   static_assert(S_SMEM_BYTES <= 232448 && R_SMEM_BYTES <= 232448, "shared memory budget");
-  static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0 && BH_BYTES % 256 == 0, "swizzle phase of every operand block");
+  static_assert(TM_A + 2 * 64 <= 512 && TM_A + NST * 32 <= 512, "TMEM columns");
 };
 
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
-  // cute::UMMA::SmemDescriptor, K-major SWIZZLE_32B: start address, LBO (unused), SBO = 8 rows x 32 B,
-  // version 1, layout type 6
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+// cute::UMMA::SmemDescriptor, K-major, swizzle = PXB bytes (pixel rows PXB bytes apart, 8-row core
+// groups contiguous): start address, LBO (unused for swizzled K-major), SBO = 8 rows, version 1,
+// layout type (SWIZZLE_32B 6, SWIZZLE_64B 4, SWIZZLE_128B 2).  A K step of 8 tf32 inside a wider row is
+// addressed by advancing the start address by 32 bytes.
+template <int PXB> __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  constexpr uint64_t layout = PXB == 32 ? 6 : (PXB == 64 ? 4 : 2);
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((8 * PXB) >> 4) << 32) |
+         ((uint64_t)1 << 46) | (layout << 61);
 }
 // kind::tf32, fp32 accumulator, A and B K-major, M = 128, N = 192
 static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TcCfg::NHALF >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(da), "l"(db), "r"(kIdesc), "r"(acc) : "memory");
-}
-// the three passes of the split product for one K chunk and one half of N: hi.hi + lo.hi + hi.lo
-__device__ __forceinline__ void umma_x3(uint32_t d, uint32_t a_raw, uint32_t a_lo, uint32_t b_raw, uint32_t b_lo, uint32_t acc) {
-  umma_tf32(d, umma_desc_sw32(a_raw), umma_desc_sw32(b_raw), acc);
-  umma_tf32(d, umma_desc_sw32(a_lo), umma_desc_sw32(b_raw), 1u);
-  umma_tf32(d, umma_desc_sw32(a_raw), umma_desc_sw32(b_lo), 1u);
-}
-// A operand from tensor memory (lane = pixel, one column per channel of the chunk), B from shared memory
+// A operand from tensor memory (lane = pixel, one column per channel of the K step), B from shared memory
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(kIdesc), "r"(acc) : "memory");
 }
+// the three passes of the split product for one K step and one half of N: hi.hi + lo.hi + hi.lo
+template <int PXB>
 __device__ __forceinline__ void umma_x3_ts(uint32_t d, uint32_t a_tm, uint32_t b_raw, uint32_t b_lo, uint32_t acc) {
-  umma_tf32_ts(d, a_tm, umma_desc_sw32(b_raw), acc);       // hi.hi
-  umma_tf32_ts(d, a_tm + 8, umma_desc_sw32(b_raw), 1u);    // lo.hi
-  umma_tf32_ts(d, a_tm, umma_desc_sw32(b_lo), 1u);         // hi.lo
+  umma_tf32_ts(d, a_tm, umma_desc<PXB>(b_raw), acc);
+  umma_tf32_ts(d, a_tm + 8, umma_desc<PXB>(b_raw), 1u);
+  umma_tf32_ts(d, a_tm, umma_desc<PXB>(b_lo), 1u);
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -115,12 +113,33 @@ __device__ __forceinline__ float tf32_lo(float x) {
   const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   return __uint_as_float(__float_as_uint(r) + 0x1000u);
 }
-// lo = rna(x - trunc(x)) for `bytes` of a raw operand block, elementwise (any swizzle: same offsets)
+// lo for `bytes` of a raw operand block, elementwise (any swizzle: same offsets)
 __device__ __forceinline__ void split_block(const unsigned char* src, unsigned char* dst, int bytes, int st) {
   for (int off = st * 16; off < bytes; off += 128 * 16) {
     const float4 v = *reinterpret_cast<const float4*>(src + off);
     *reinterpret_cast<float4*>(dst + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
   }
+}
+// First-frame operand -> TMEM: this thread's pixel (row m of the landing buffer, PXB-byte rows), NKS K
+// steps of 8 channels: hi (the fp32 words) to columns col0 + 16*ks, lo to col0 + 16*ks + 8 of the
+// thread's TMEM lane.  `taddr` = TMEM address of (this warp's lane quadrant, col0).
+template <int PXB, int NKS>
+__device__ __forceinline__ void a_to_tmem(const unsigned char* landing, int m, uint32_t taddr, int nks) {
+#pragma unroll
+  for (int ks = 0; ks < NKS; ++ks) {
+    if (ks >= nks) break;
+    const float4 v0 = *reinterpret_cast<const float4*>(landing + swz<PXB>((uint32_t)(m * PXB + ks * 32)));
+    const float4 v1 = *reinterpret_cast<const float4*>(landing + swz<PXB>((uint32_t)(m * PXB + ks * 32 + 16)));
+    const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { hi[e] = __float_as_uint(x[e]); lo[e] = __float_as_uint(tf32_lo(x[e])); }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr + (uint32_t)(ks * 16)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr + (uint32_t)(ks * 16 + 8)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 #define QPWC_TMEM_LD16(v, taddr)                                                                          \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
@@ -245,8 +264,8 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem, int warp) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Streaming kernel: any C % 8 == 0.  K chunks flow through NST stages; the six MMAs of a chunk cover
-// both halves of N, so the accumulator is published once per tile.
+// Streaming kernel: any C % 8 == 0.  Stages of 16 channels flow through NST buffers; the MMAs of a
+// stage cover both halves of N, so the accumulator is published once per tile.
 __global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
 corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
                           float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
@@ -254,6 +273,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
   // ablate (dev, QPWC_ABLATE): bit0 no accumulator drain, bit1 no operand split, bit2 no MMAs, bit3 no loads,
   // bit4 no copy-out
   using Cfg = TcCfg;
+  constexpr int PXB = Cfg::S_PXB;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::S_OFF_BARS);
   uint64_t* raw_full = bars;                      // count 1 (+tx)
@@ -264,8 +284,10 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* staging = reinterpret_cast<float*>(smem + Cfg::S_OFF_STAGING);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nchunks = C / Cfg::KC;
+  const int nstages = (C + Cfg::S_KC - 1) / Cfg::S_KC;  // per tile; the last one may hold a single K step
   const uint32_t tmem = tc_prologue(bars, 2 * Cfg::NST + 2, Cfg::NST, 2, tmem_slot, smem, tid, warp);
+#define QPWC_SB(s) (smem + (s) * 2 * Cfg::SB_BYTES)
+#define QPWC_SA(s) (smem + Cfg::S_OFF_A + (s) * Cfg::SA_BYTES)
 
   if (warp < Cfg::W_SPLIT) {
    setmaxnreg_dec<Cfg::REG_CTRL>();
@@ -273,41 +295,65 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
     if (lane == 0) {  // ------------------------------------------------------------- TMA producer
       tma_prefetch_desc(&tmP);
       tma_prefetch_desc(&tmN);
-      uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tx = tile % tiles_x, rest = tile / tiles_x, ty = rest % tiles_y, b = rest / tiles_y;
-        const int i0 = ty * Cfg::TH, j0 = tx * Cfg::TW;
-        for (int c = 0; c < nchunks; ++c, ++g) {
+      // linear walk over (tile, stage) items; the item PF stages ahead is prefetched into L2 so that the
+      // load proper finds it there (the NST stages in flight cover an L2 hit, not an HBM round trip)
+      constexpr int PF = 2 * Cfg::NST;
+      const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const int nitems = my_tiles * nstages;
+      auto coords = [&](int n, int& c, int& i0, int& j0, int& b) {
+        const int tl = n / nstages;
+        c = n - tl * nstages;
+        const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+        const int tx = tile % tiles_x, rest = tile / tiles_x, ty = rest % tiles_y;
+        b = rest / tiles_y; i0 = ty * Cfg::TH; j0 = tx * Cfg::TW;
+      };
+      auto prefetch = [&](int n) {
+        if (n >= nitems || (ablate & 8)) return;
+        int c, i0, j0, b;
+        coords(n, c, i0, j0, b);
+        tma_prefetch_l2_4d(&tmP, c * Cfg::S_KC, j0, i0, b);
+        tma_prefetch_l2_4d(&tmP, c * Cfg::S_KC, j0 + 8, i0, b);
+        tma_prefetch_l2_4d(&tmN, c * Cfg::S_KC, j0 - 4, i0 - 4, b);
+        tma_prefetch_l2_4d(&tmN, c * Cfg::S_KC, j0 - 4, i0 + 4, b);
+      };
+      for (int n = 0; n < PF; ++n) prefetch(n);
+      for (int n = 0; n < nitems; ++n) {
+        const uint32_t g = (uint32_t)n;
+        int c, i0, j0, b;
+        coords(n, c, i0, j0, b);
+        {
           const int s = (int)(g % Cfg::NST);
           mbar_wait(&stage_free[s], ((g / Cfg::NST) & 1u) ^ 1u);
-          unsigned char* sb = smem + s * Cfg::STAGE_BYTES;
+          prefetch(n + PF);
           if (ablate & 8) { mbar_arrive(&raw_full[s]); continue; }
-          mbar_arrive_expect_tx(&raw_full[s], Cfg::RAW_BYTES);
+          mbar_arrive_expect_tx(&raw_full[s], Cfg::SA_BYTES + Cfg::SB_BYTES);
           // A: two boxes of 8 cols x 8 rows; TMEM lane quadrant q = 2*cb + rb is the block rows 4*rb.., cols 8*cb..
-          tma_load_4d(sb, &tmP, &raw_full[s], c * Cfg::KC, j0, i0, b);
-          tma_load_4d(sb + 2048, &tmP, &raw_full[s], c * Cfg::KC, j0 + 8, i0, b);
-          tma_load_4d(sb + Cfg::A_BYTES, &tmN, &raw_full[s], c * Cfg::KC, j0 - 4, i0 - 4, b);
-          tma_load_4d(sb + Cfg::A_BYTES + Cfg::BH_BYTES, &tmN, &raw_full[s], c * Cfg::KC, j0 - 4, i0 + 4, b);
+          tma_load_4d(QPWC_SA(s), &tmP, &raw_full[s], c * Cfg::S_KC, j0, i0, b);
+          tma_load_4d(QPWC_SA(s) + Cfg::SA_BYTES / 2, &tmP, &raw_full[s], c * Cfg::S_KC, j0 + 8, i0, b);
+          tma_load_4d(QPWC_SB(s), &tmN, &raw_full[s], c * Cfg::S_KC, j0 - 4, i0 - 4, b);
+          tma_load_4d(QPWC_SB(s) + Cfg::SB_BYTES / 2, &tmN, &raw_full[s], c * Cfg::S_KC, j0 - 4, i0 + 4, b);
         }
       }
     }
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     if (lane == 0) {  // --------------------------------------------------------------- MMA issuer
       uint32_t g = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
         mbar_wait(&tempty[0], (tcount & 1u) ^ 1u);  // the epilogue has drained both halves
         mbar_wait(&tempty[1], (tcount & 1u) ^ 1u);
-        tc_fence_after();
-        for (int c = 0; c < nchunks; ++c, ++g) {
+        for (int c = 0; c < nstages; ++c, ++g) {
           const int s = (int)(g % Cfg::NST);
           mbar_wait(&lo_full[s], (g / Cfg::NST) & 1u);
           tc_fence_after();
-          const uint32_t a_raw = smem_u32(smem + s * Cfg::STAGE_BYTES), b_raw = a_raw + Cfg::A_BYTES;
+          const uint32_t b_raw = smem_u32(QPWC_SB(s)), b_lo = b_raw + Cfg::SB_BYTES;
+          const uint32_t a_tm = tmem + (uint32_t)(Cfg::TM_A + s * 32);
+          const int nks = min(2, (C - c * Cfg::S_KC) / 8);
           if (!(ablate & 4))
+            for (int ks = 0; ks < nks; ++ks)
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            umma_x3(tmem + (uint32_t)(h * Cfg::NHALF), a_raw, a_raw + Cfg::RAW_BYTES, b_raw + h * Cfg::BH_BYTES,
-                    b_raw + Cfg::RAW_BYTES + h * Cfg::BH_BYTES, c > 0 ? 1u : 0u);
+              for (int h = 0; h < 2; ++h)
+                umma_x3_ts<PXB>(tmem + (uint32_t)(h * Cfg::NHALF), a_tm + ks * 16, b_raw + h * (Cfg::SB_BYTES / 2) + ks * 32,
+                                b_lo + h * (Cfg::SB_BYTES / 2) + ks * 32, (c | ks) ? 1u : 0u);
           umma_commit(&stage_free[s]);  // stage reusable once these MMAs have read it
         }
         umma_commit(&tfull[0]);
@@ -317,14 +363,19 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
    }
   } else if (warp < Cfg::W_EPI) {  // ------------------------------------------------- operand split
     setmaxnreg_dec<Cfg::REG_SPLIT>();
-    const int st = tid - Cfg::W_SPLIT * 32;
+    const int st = tid - Cfg::W_SPLIT * 32, qd = warp & 3, m = qd * 32 + lane;
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int c = 0; c < nchunks; ++c, ++g) {
+      for (int c = 0; c < nstages; ++c, ++g) {
         const int s = (int)(g % Cfg::NST);
         mbar_wait_parked(&raw_full[s], (g / Cfg::NST) & 1u);
-        if (!(ablate & 2)) split_block(smem + s * Cfg::STAGE_BYTES, smem + s * Cfg::STAGE_BYTES + Cfg::RAW_BYTES, Cfg::RAW_BYTES, st);
+        tc_fence_after();  // (the MMAs that read TMEM buffer s completed before the stage was reloaded)
+        if (!(ablate & 2)) {
+          a_to_tmem<PXB, 2>(QPWC_SA(s), m, tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + s * 32), min(2, (C - c * Cfg::S_KC) / 8));
+          split_block(QPWC_SB(s), QPWC_SB(s) + Cfg::SB_BYTES, Cfg::SB_BYTES, st);
+        }
         fence_proxy_async();  // generic-proxy stores -> tensor-core (async proxy) reads
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&lo_full[s]);
       }
@@ -341,24 +392,26 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
     }
   }
   tc_teardown(tmem, warp);
+#undef QPWC_SA
+#undef QPWC_SB
 }
 
 // ---------------------------------------------------------------------------------------------
-// Resident kernel: C <= 32.  All K chunks of a tile fit on chip, so (1) the MMAs run half-major -- the
+// Resident kernel: C <= 32.  All channels of a tile fit on chip, so (1) the MMAs run half-major -- the
 // first half of N is published (and drained by the epilogue) while the second is being computed, and
 // the next tile's first half while this tile's second drains -- and (2) a CTA walks vertically
 // consecutive tiles of one strip: the lower half-tile of second-frame rows of tile k is the upper
 // half-tile of tile k+1 and stays where it is ("rolling rows"): only 8 new second-frame rows are
 // loaded and split per tile instead of 16.  The half-tile blocks form a ring of three, so the block a
 // tile frees after its first pass is refilled two tile periods before it is needed.  The first-frame
-// operand goes through TMEM: the split warps (warp = TMEM lane quadrant, lane = pixel) read their
-// pixel's channels from the TMA landing buffer and tcgen05.st hi and lo into spare TMEM columns
-// (double-buffered), which halves A's shared-memory footprint and removes its operand reads.
+// operand goes through TMEM (double-buffered), which halves its shared-memory footprint and removes
+// its operand reads.
 __global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
 corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
                        float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
                        int tiles_x, int tiles_y, int seg, int nseg, int nunits, int ablate) {
   using Cfg = TcCfg;
+  constexpr int PXB = Cfg::R_PXB;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::R_OFF_BARS);
   uint64_t* afull = bars;          // [2] count 1 (+tx): A landed in landing buffer a
@@ -373,9 +426,9 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* staging = reinterpret_cast<float*>(smem + Cfg::R_OFF_STAGING);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nchunks = C / Cfg::KC;
+  const int nks = C / 8;           // K steps (<= 4); channels C..31 of the 128-byte rows are TMA zero fill
   const uint32_t tmem = tc_prologue(bars, 12, 7, 2, tmem_slot, smem, tid, warp);
-  // B block p: raw at R_OFF_B + p*2*RB_BYTES, lo RB_BYTES further, chunk c at c*BH_BYTES
+  // B block p: raw at R_OFF_B + p*2*RB_BYTES, lo RB_BYTES further
 #define QPWC_ABUF(a) (smem + Cfg::R_OFF_A + (a) * Cfg::RA_BYTES)
 #define QPWC_BBLK(p) (smem + Cfg::R_OFF_B + (p) * 2 * Cfg::RB_BYTES)
   // every role walks the same tile sequence; `ring` counts the B blocks allocated so far (block = ring % 3):
@@ -407,11 +460,9 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
         ua ^= 1u << a;
         if (ablate & 8) mbar_arrive(&afull[a]);
         else {
-          mbar_arrive_expect_tx(&afull[a], (uint32_t)(nchunks * Cfg::A_BYTES));
-          for (int c = 0; c < nchunks; ++c) {
-            tma_load_4d(QPWC_ABUF(a) + c * Cfg::A_BYTES, &tmP, &afull[a], c * Cfg::KC, j0, i0, b);
-            tma_load_4d(QPWC_ABUF(a) + c * Cfg::A_BYTES + 2048, &tmP, &afull[a], c * Cfg::KC, j0 + 8, i0, b);
-          }
+          mbar_arrive_expect_tx(&afull[a], Cfg::RA_BYTES);
+          tma_load_4d(QPWC_ABUF(a), &tmP, &afull[a], 0, j0, i0, b);
+          tma_load_4d(QPWC_ABUF(a) + Cfg::RA_BYTES / 2, &tmP, &afull[a], 0, j0 + 8, i0, b);
         }
         // second-frame half-tile blocks: rows i0-4..i0+3 (top) and i0+4..i0+11 (bot); only the first
         // tile of a segment loads its top
@@ -420,13 +471,12 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
           mbar_wait(&bfree[p], QPWC_PAR(ub, p) ^ 1u);
           ub ^= 1u << p;
           if (ablate & 8) { mbar_arrive(&bfull[p]); continue; }
-          mbar_arrive_expect_tx(&bfull[p], (uint32_t)(nchunks * Cfg::BH_BYTES));
-          for (int c = 0; c < nchunks; ++c)
-            tma_load_4d(QPWC_BBLK(p) + c * Cfg::BH_BYTES, &tmN, &bfull[p], c * Cfg::KC, j0 - 4, i0 - 4 + hb * 8, b);
+          mbar_arrive_expect_tx(&bfull[p], Cfg::RB_BYTES);
+          tma_load_4d(QPWC_BBLK(p), &tmN, &bfull[p], 0, j0 - 4, i0 - 4 + hb * 8, b);
         }
       }}
     }
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     if (lane == 0) {  // --------------------------------------------------------------- MMA issuer
       uint32_t T = 0, ring = 0, ma = 0, mb = 0;
       int top = 0, bot = 0;
@@ -441,8 +491,8 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
         {
           const uint32_t b_raw = smem_u32(QPWC_BBLK(top)), b_lo = b_raw + Cfg::RB_BYTES;
           if (!(ablate & 4))
-            for (int c = 0; c < nchunks; ++c)
-              umma_x3_ts(tmem, a_tm + c * 16, b_raw + c * Cfg::BH_BYTES, b_lo + c * Cfg::BH_BYTES, c > 0 ? 1u : 0u);
+            for (int ks = 0; ks < nks; ++ks)
+              umma_x3_ts<PXB>(tmem, a_tm + ks * 16, b_raw + ks * 32, b_lo + ks * 32, ks > 0 ? 1u : 0u);
           umma_commit(&tfull[0]);
           umma_commit(&bfree[top]);  // the upper block is dead once these MMAs have read it
         }
@@ -453,8 +503,8 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
         {
           const uint32_t b_raw = smem_u32(QPWC_BBLK(bot)), b_lo = b_raw + Cfg::RB_BYTES;
           if (!(ablate & 4))
-            for (int c = 0; c < nchunks; ++c)
-              umma_x3_ts(tmem + Cfg::NHALF, a_tm + c * 16, b_raw + c * Cfg::BH_BYTES, b_lo + c * Cfg::BH_BYTES, c > 0 ? 1u : 0u);
+            for (int ks = 0; ks < nks; ++ks)
+              umma_x3_ts<PXB>(tmem + Cfg::NHALF, a_tm + ks * 16, b_raw + ks * 32, b_lo + ks * 32, ks > 0 ? 1u : 0u);
           umma_commit(&tfull[1]);
           umma_commit(&afree[a]);
           if (k == nt - 1) umma_commit(&bfree[bot]);  // end of the segment: nobody inherits the lower block
@@ -465,7 +515,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
   } else if (warp < Cfg::W_EPI) {  // ------------------------------------------------- operand split
     setmaxnreg_dec<Cfg::REG_SPLIT>();
     const int st = tid - Cfg::W_SPLIT * 32, qd = warp & 3;  // qd: the TMEM lane quadrant this warp may write
-    const int m = qd * 32 + lane;            // its pixel = row of A = TMEM lane
+    const int m = qd * 32 + lane;                           // its pixel = row of A = TMEM lane
     uint32_t T = 0, ring = 0, ja = 0, jf = 0, jb = 0;
     int top = 0, bot = 0;
     QPWC_FOR_UNITS
@@ -475,23 +525,8 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
       mbar_wait_parked(&afree[a], QPWC_PAR(jf, a) ^ 1u);  // the MMAs of two tiles ago have finished reading TMEM buffer a
       jf ^= 1u << a;
       tc_fence_after();
-      if (!(ablate & 2)) {
-        const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + a * 64);
-        for (int c = 0; c < nchunks; ++c) {
-          const unsigned char* src = QPWC_ABUF(a) + c * Cfg::A_BYTES;
-          const float4 v0 = *reinterpret_cast<const float4*>(src + swz32((uint32_t)(m * 32)));
-          const float4 v1 = *reinterpret_cast<const float4*>(src + swz32((uint32_t)(m * 32 + 16)));
-          const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { hi[e] = __float_as_uint(x[e]); lo[e] = __float_as_uint(tf32_lo(x[e])); }
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                       ::"r"(taddr + (uint32_t)(c * 16)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                       ::"r"(taddr + (uint32_t)(c * 16 + 8)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      }
+      if (!(ablate & 2))
+        a_to_tmem<PXB, 4>(QPWC_ABUF(a), m, tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + a * 64), nks);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&arawfree[a]); mbar_arrive(&alo[a]); }
@@ -499,7 +534,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
         const int p = hb ? bot : top;
         mbar_wait_parked(&bfull[p], QPWC_PAR(jb, p));
         jb ^= 1u << p;
-        if (!(ablate & 2)) split_block(QPWC_BBLK(p), QPWC_BBLK(p) + Cfg::RB_BYTES, nchunks * Cfg::BH_BYTES, st);
+        if (!(ablate & 2)) split_block(QPWC_BBLK(p), QPWC_BBLK(p) + Cfg::RB_BYTES, Cfg::RB_BYTES, st);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&blo[p]);
@@ -531,16 +566,16 @@ int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, in
   if (d != 4 || (C & 7) || C < 8) return QPWC_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15)) return QPWC_ERR_UNSUPPORTED;
   using Cfg = TcCfg;
-  TensorMap tmP, tmN;
-  if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::KC, 8, 8)) return QPWC_ERR_CUDA;           // A: 8 cols x 8 rows
-  if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, Cfg::KC, Cfg::NCOL, 8)) return QPWC_ERR_CUDA;   // B: 24 cols x 8 rows (half tile)
   const int tiles_x = cdiv(W, Cfg::TW), tiles_y = cdiv(H, Cfg::TH);
   const long long nt = (long long)tiles_x * tiles_y * B;
   if (nt >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
   static int ablate = -1;
   if (ablate < 0) { const char* ev = getenv("QPWC_ABLATE"); ablate = ev ? atoi(ev) : 0; }
   const int sms = sm_count_cached();
-  if (C <= Cfg::MAXCH * Cfg::KC && !(ablate & 32)) {
+  TensorMap tmP, tmN;
+  if (C <= 32 && !(ablate & 32)) {
+    if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, 32, 8, 8)) return QPWC_ERR_CUDA;           // A: 8 cols x 8 rows x 128 B
+    if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, 32, Cfg::NCOL, 8)) return QPWC_ERR_CUDA;   // B: 24 cols x 8 rows (half tile)
     // segments of vertically consecutive tiles; short enough that every SM gets several
     int seg = tiles_y;
     while (seg > 2 && (long long)tiles_x * B * cdiv(tiles_y, seg) < 4LL * sms) seg = cdiv(seg, 2);
@@ -552,6 +587,8 @@ int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, in
         tmP, tmN, out, B, H, W, C, slope, ops, tiles_x, tiles_y, seg, nseg, nunits, ablate);
     return check_launch("corr_fwd_tc_res");
   }
+  if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::S_KC, 8, 8)) return QPWC_ERR_CUDA;
+  if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, Cfg::S_KC, Cfg::NCOL, 8)) return QPWC_ERR_CUDA;
   const int ntiles = (int)nt;
   const cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::S_SMEM_BYTES);
   if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_fwd_tc: smem attribute (%d B): %s", Cfg::S_SMEM_BYTES, cudaGetErrorString(e));

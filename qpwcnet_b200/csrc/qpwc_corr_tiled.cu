@@ -516,7 +516,7 @@ bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C
   const cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, boxC * 4 == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, boxC * 4 == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (boxC * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return false; }
   return true;
