@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libqpwc.so")
-SOURCES = ["qpwc_api.cu", "qpwc_warp.cu", "qpwc_corr_direct.cu", "qpwc_corr_tiled.cu", "qpwc_corr_rowpair.cu", "qpwc_upsample.cu", "qpwc_occlusion.cu", "qpwc_corr_nchw.cu", "qpwc_corr_bwd_nchw.cu", "qpwc_corr_bwd_tiled.cu", "qpwc_corr_tc.cu"]
+SOURCES = ["qpwc_api.cu", "qpwc_warp.cu", "qpwc_corr_direct.cu", "qpwc_corr_tiled.cu", "qpwc_upsample.cu", "qpwc_occlusion.cu", "qpwc_corr_nchw.cu", "qpwc_corr_bwd_nchw.cu", "qpwc_corr_bwd_tiled.cu", "qpwc_corr_tc.cu"]
 HEADERS = ["qpwc_common.cuh", "qpwc_async.cuh", "qpwc_upsample.cuh", os.path.join("..", "..", "include", "qpwc.h")]
 
 NVCC_FLAGS = [

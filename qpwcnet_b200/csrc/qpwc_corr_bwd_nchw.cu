@@ -16,6 +16,7 @@
 // tile, delivered by TMA, zero-filled outside the image), 162 FFMAs, and one 8-byte store of the two
 // finished gradients -- a warp writes 256 contiguous bytes of one NCHW row.  No atomics, no
 // zero-initialisation, no transposes; each output element is written exactly once.
+#include <atomic>
 #include "qpwc_async.cuh"
 
 namespace qpwc {
@@ -197,13 +198,13 @@ static int run_bwd_nchw(const float* x, const float* out, const float* g_out, fl
   const int grid = ntiles < sm_count_cached() ? ntiles : sm_count_cached();
   auto k = corr_bwd_nchw_kernel<WHICH, Cfg>;
 #ifndef QPWC_EMU
-  static unsigned attr_done = 0;  // per instantiation, one bit per device
+  static std::atomic<unsigned> attr_done{0};  // per instantiation, one bit per device
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!(attr_done >> (dev & 31) & 1u)) {
+  if (!(attr_done.load(std::memory_order_acquire) >> (dev & 31) & 1u)) {
     const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_bwd_nchw: smem attribute (%d B): %s", SMEM_BYTES, cudaGetErrorString(e));
-    attr_done |= 1u << (dev & 31);
+    attr_done.fetch_or(1u << (dev & 31), std::memory_order_release);
   }
 #endif
   QPWC_LAUNCH(k, grid, Cfg::NTHREADS, SMEM_BYTES, stream, tmX, out, g_out, g, B, H, W, C, slope, tiles_x, tiles_y, ntiles);

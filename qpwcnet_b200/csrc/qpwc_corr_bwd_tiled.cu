@@ -23,6 +23,7 @@
 // Two 128-thread CTAs share an SM (three fit with a 4-byte table and 168 registers but run slower, 1130 vs
 // 700 us at the finest level: only ~14 KB of L1 would remain for the gradient sectors shared by consecutive steps).  No atomics: every gradient element is written once, in a fixed
 // summation order.
+#include <atomic>
 #include <stdlib.h>
 
 #include "qpwc_common.cuh"
@@ -263,14 +264,14 @@ int launch_corr_bwd_tiled(const float* prv, const float* nxt, const float* out, 
   if (ncb > 65535 || B > 65535) return QPWC_ERR_UNSUPPORTED;
   if (((long long)(TH - 1) * W + XW) * ops + Q >= (1LL << GOFF_BITS)) return QPWC_ERR_UNSUPPORTED;  // table entry range
 #ifndef QPWC_EMU
-  static unsigned attr_done = 0;  // one bit per device (the attribute is per device)
+  static std::atomic<unsigned> attr_done{0};  // one bit per device (the attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!(attr_done >> (dev & 31) & 1u)) {
+  if (!(attr_done.load(std::memory_order_acquire) >> (dev & 31) & 1u)) {
     cudaError_t e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_bwd_tiled: smem attribute (%d B): %s", SMEM_BYTES, cudaGetErrorString(e));
-    attr_done |= 1u << (dev & 31);
+    attr_done.fetch_or(1u << (dev & 31), std::memory_order_release);
   }
   const dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)ncb, (unsigned)B);
   corr_bwd_tiled_kernel<0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(prv, nxt, out, g_out, g_prv, g_nxt, H, W, C, slope, ops, tiles_x, ncb);

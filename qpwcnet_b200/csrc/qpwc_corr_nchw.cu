@@ -17,6 +17,7 @@
 // swizzle (a warp's 8-byte loads are 256 contiguous bytes), 120 of 128 columns valid.
 // The output is NCHW too: plane (m,k) receives two adjacent pixels from every thread, i.e. a warp
 // writes 256 contiguous bytes per store -- straight from registers, no staging, no store agents.
+#include <atomic>
 #include <stdlib.h>
 
 #include "qpwc_async.cuh"
@@ -200,13 +201,13 @@ static int run_nchw(const float* prv, const float* nxt, float* out, int B, int C
   const int grid = ntiles < sm_count_cached() ? ntiles : sm_count_cached();
   auto k = corr_fwd_nchw_kernel<Cfg>;
 #ifndef QPWC_EMU
-  static unsigned attr_done = 0;  // per instantiation, one bit per device (the attribute is per device)
+  static std::atomic<unsigned> attr_done{0};  // per instantiation, one bit per device (the attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!(attr_done >> (dev & 31) & 1u)) {
+  if (!(attr_done.load(std::memory_order_acquire) >> (dev & 31) & 1u)) {
     const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_fwd_nchw: smem attribute (%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-    attr_done |= 1u << (dev & 31);
+    attr_done.fetch_or(1u << (dev & 31), std::memory_order_release);
   }
 #endif
   QPWC_LAUNCH(k, grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream, tmP, tmN, out, B, H, W, C, slope, tiles_x, tiles_y, ntiles);

@@ -25,23 +25,20 @@
 //     memory, half a row (28 px) at a time (transposes the per-thread 9x9 blocks into the NHWC
 //     81-vector) -> one asynchronous TMA bulk store per contiguous 28 x 324-byte run.
 #include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
 
 #include "qpwc_async.cuh"
 #include "qpwc_upsample.cuh"
 
 namespace qpwc {
 
-template <int TH_, int WARP_, int MODE_, int PACKED_ = 0, int OCC_ = 1>
+template <int TH_, int WARP_, int MODE_>
 struct TiledCfg {
-  // OCC: CTAs per SM.  2 (TH = 2): two independent CTAs share an SM, so one CTA's tile prologue and
-  // epilogue overlap the other's FFMA loop instead of all eight consumer warps marching in lock-step
-  static constexpr int OCC = OCC_;
-  // PACKED: accumulate with packed fp32 FMAs (FFMA2, sm_100): even-/odd-channel partial sums kept
-  // as register pairs (162 accumulator registers).  Measured on B200 (tools/ubench): FFMA2 issues
-  // every 2.2-2.3 clk/SMSP, a scalar 3-register FFMA every 1.22 clk, and with its shared-memory
-  // loads the scalar 81-accumulator loop sustains 0.70 FMA/lane/clk against 0.60 for this packed
-  // loop -- the scalar consumer (PACKED = 0) is the default, the packed one is kept for A/B runs.
-  static constexpr int PACKED = PACKED_;
+  // (round 2: a 2-CTA-per-SM variant -- two 2-row CTAs per SM so that one's tile prologue/epilogue
+  // overlaps the other's FFMA loop -- measured identical to this one at every level and was dropped:
+  // the kernel is throughput-, not lock-step-bound.)
   static constexpr int D = 4, Q = 2 * D + 1, NDISP = Q * Q;
   static constexpr int TH = TH_, TWT = 64, TW = TWT - 2 * D;  // 56 pixel columns per tile
   static constexpr int WARP = WARP_, MODE = MODE_;
@@ -50,7 +47,7 @@ struct TiledCfg {
   // (measured ~2 clk each), so wider per-pixel reads halve the producer's L1 time
   static constexpr int KC = WARP_ ? 16 : 8, PXB = KC * 4, NQ = KC / 4;
   static constexpr int NROW = TH + 2 * D, NCOL = TWT, PCOL = TW;         // P tile: the 56 valid columns only
-  static constexpr int NST = WARP_ ? 2 : (OCC_ == 2 ? 3 : ((PACKED_ || TH_ <= 4) ? 4 : 3));
+  static constexpr int NST = WARP_ ? 2 : (TH_ <= 4 ? 4 : 3);
   static constexpr int P_BYTES = TH * PCOL * PXB, N_BYTES = NROW * NCOL * PXB;
   static constexpr int STAGE_BYTES = P_BYTES + N_BYTES;
   // producers (128-thread warpgroups, the unit of setmaxnreg): plain = 1 TMA thread + 3 store-agent
@@ -69,18 +66,16 @@ struct TiledCfg {
   static constexpr int OFF_TAPS = OFF_STAGING + TH * NSLOT * SLOT_BYTES;
   static constexpr int OFF_BARS = OFF_TAPS + TAPS_BYTES;
   static constexpr int SMEM_BYTES = OFF_BARS + 2 * NST * 8 + 2 * TH * 8;
-  static_assert(SMEM_BYTES <= (OCC_ == 2 ? 115712 : 232448), "shared memory budget (227 KB per SM, 1 KB reserved per CTA)");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
   static constexpr int FULL_COUNT = 1 + (WARP ? NPROD / 32 : 0);
   static constexpr int EMPTY_COUNT = NCONS / 32;
-  // register split (setmaxnreg), sum <= 65536:  scalar TH=4 plain: 256*200 + 128*56;  scalar TH=6:
-  // 384*152 + 128*56;  packed TH=4 plain:
-  // 256*232 + 128*32;  fused (scalar consumers, TH=4): 256*176 + 256*80
-  static constexpr int REG_CONS = PACKED_ ? 232 : (WARP_ ? 176 : (TH_ <= 4 ? 200 : 152));
-  static constexpr int REG_PROD = WARP_ ? 80 : (PACKED_ ? 32 : 56);
+  // register split (setmaxnreg), sum <= 65536:  plain TH=4: 256*200 + 128*56;  fused TH=4: 256*176 + 256*80
+  static constexpr int REG_CONS = WARP_ ? 176 : 200;
+  static constexpr int REG_PROD = WARP_ ? 80 : 56;
   static constexpr int UB = 2;  // fused producer: units in flight per thread (8 independent 16-byte gathers)
-  static_assert(!(WARP_ && (PACKED_ || TH_ > 4)), "fused variant: scalar consumers, TH <= 4");
+  static_assert(TH_ <= 4, "4-row tiles at most (register budget of the consumers)");
   static_assert(TW % 8 == 0 && P_BYTES % 512 == 0 && N_BYTES % 512 == 0 && TH <= 14, "tile shape");
-  static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536 / OCC_, "register budget");
+  static_assert(NCONS * REG_CONS + NPROD * REG_PROD <= 65536, "register budget");
 };
 
 struct TapsEntry { int o00, o01, o10, o11; float w00, w01, w10, w11; };  // 32 bytes
@@ -107,7 +102,7 @@ struct TapsEntry { int o00, o01, o10, o11; float w00, w01, w10, w11; };  // 32 b
 
 // ---------------------------------------------------------------------------------------------
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::OCC)
+__global__ void __launch_bounds__(Cfg::NTHREADS, 1)
 corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CONSTANT TensorMap tmN,
                       const float* __restrict__ nxt, const float* __restrict__ flow,
                       float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
@@ -297,7 +292,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
     // column part of the second-frame operand offset (the swizzle depends on the column only: the
     // row pitch is a multiple of the swizzle period); the row part is brow[m], per tile
     const uint32_t nb_off = Cfg::P_BYTES + swz<Cfg::PXB>((uint32_t)(((Cfg::WARP ? 0 : ti) * NCOL + tc) * Cfg::PXB));
-    uint32_t a_off[Q];  // scalar path only (the packed path recomputes them)
+    uint32_t a_off[Q];
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
       // first-frame pixel column of acc[.][k] is lp = tc - k; columns outside the tile belong to
@@ -319,12 +314,11 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
         brow[m] = Cfg::WARP ? (uint32_t)(((tseg * TH) % NROW + ti + m) % NROW) * (NCOL * Cfg::PXB)
                             : (uint32_t)(m * (NCOL * Cfg::PXB));   // compile-time: folds into the load
 
-      float acc[Q][Q];              // scalar path
-      float2 acc2[Q][Q];            // packed path: (even-channel sum, odd-channel sum) per output
+      float acc[Q][Q];
 #pragma unroll
       for (int m = 0; m < Q; ++m)
 #pragma unroll
-        for (int k = 0; k < Q; ++k) { acc[m][k] = 0.f; acc2[m][k] = make_float2(0.f, 0.f); }
+        for (int k = 0; k < Q; ++k) acc[m][k] = 0.f;
 
       // pixel columns of this warp's accumulators: lp = tc - k in [(tc & ~31) - 8, (tc | 31)]
       const bool dead_warp = (tc & ~31) - (Q - 1) >= min(TW, W - j0);
@@ -338,46 +332,18 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
 #pragma unroll
         for (int qd = 0; qd < Cfg::NQ; ++qd) {
           const unsigned char* nbp = sb + (nb_off ^ (uint32_t)(qd << 4));
-          if (Cfg::PACKED) {
-            // packed fp32 FMAs on the natural channel pairs (c0,c1) / (c2,c3) of the 16-byte
-            // operands; scheduling is left to ptxas (pinning the order with asm volatile was
-            // measured 30 % slower: it can no longer interleave the operand loads)
-            float4 bq[Q];
+          float4 bv[Q];
 #pragma unroll
-            for (int m = 0; m < Q; ++m) bq[m] = *reinterpret_cast<const float4*>(nbp + brow[m]);
-            // software-skewed: the (c2,c3) update of column k-1 is issued together with the (c0,c1)
-            // update of column k, so the two FFMA2s on one accumulator pair are >= 9 instructions
-            // apart whatever ptxas does locally (back-to-back they stall on the FMA latency)
-            float2 ahi_prev = make_float2(0.f, 0.f);
+          for (int m = 0; m < Q; ++m) bv[m] = *reinterpret_cast<const float4*>(nbp + brow[m]);
 #pragma unroll
-            for (int k = 0; k <= Q; ++k) {
-              float2 alo = make_float2(0.f, 0.f), ahi = make_float2(0.f, 0.f);
-              if (k < Q) {
-                const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
-                alo = make_float2(a.x, a.y); ahi = make_float2(a.z, a.w);
+          for (int k = 0; k < Q; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
 #pragma unroll
-                for (int m = 0; m < Q; ++m) acc2[m][k] = __ffma2_rn(alo, make_float2(bq[m].x, bq[m].y), acc2[m][k]);
-              }
-              if (k > 0) {
-#pragma unroll
-                for (int m = 0; m < Q; ++m) acc2[m][k - 1] = __ffma2_rn(ahi_prev, make_float2(bq[m].z, bq[m].w), acc2[m][k - 1]);
-              }
-              ahi_prev = ahi;
-            }
-          } else {
-            float4 bv[Q];
-#pragma unroll
-            for (int m = 0; m < Q; ++m) bv[m] = *reinterpret_cast<const float4*>(nbp + brow[m]);
-#pragma unroll
-            for (int k = 0; k < Q; ++k) {
-              const float4 a = *reinterpret_cast<const float4*>(sb + (a_off[k] ^ (uint32_t)(qd << 4)));
-#pragma unroll
-              for (int m = 0; m < Q; ++m) {
-                acc[m][k] = fmaf(a.x, bv[m].x, acc[m][k]);
-                acc[m][k] = fmaf(a.y, bv[m].y, acc[m][k]);
-                acc[m][k] = fmaf(a.z, bv[m].z, acc[m][k]);
-                acc[m][k] = fmaf(a.w, bv[m].w, acc[m][k]);
-              }
+            for (int m = 0; m < Q; ++m) {
+              acc[m][k] = fmaf(a.x, bv[m].x, acc[m][k]);
+              acc[m][k] = fmaf(a.y, bv[m].y, acc[m][k]);
+              acc[m][k] = fmaf(a.z, bv[m].z, acc[m][k]);
+              acc[m][k] = fmaf(a.w, bv[m].w, acc[m][k]);
             }
           }
         }
@@ -392,9 +358,7 @@ corr_fwd_tiled_kernel(const QPWC_GRID_CONSTANT TensorMap tmP, const QPWC_GRID_CO
       // 28 px through private slots and hands each contiguous 28 x 324-byte run to the TMA engine
       // (cp.async.bulk shared->global): no copy loop, rows never wait for each other, and the
       // store drains while the next tile is being computed.
-      // packed path: fold the odd-channel partial sum into the even one in place (no second
-      // live copy of the 81 results: register pressure)
-#define QPWC_ACC(m, k) (Cfg::PACKED ? (acc2[m][k].x + acc2[m][k].y) : acc[m][k])
+#define QPWC_ACC(m, k) acc[m][k]
       const int twv = min(TW, W - j0);  // valid pixel columns of this tile
       if (Cfg::AGENT) {
         // scale + leaky relu of all 81 outputs as straight-line code (the per-k range checks below
@@ -507,7 +471,27 @@ static void bind_primary_context() {
   (void)cudaFree(nullptr);
 }
 
+// Encoded descriptors are cached per calling thread (keyed by base pointer, shape and box): a layer
+// called in a loop with the same tensors pays the two driver calls once, and there is no shared state.
+struct TmapKey { const void* base; int d[7]; };
+struct TmapEntry { TmapKey key; TensorMap tm; bool valid; };
+static thread_local TmapEntry g_tmap_cache[8];
+static thread_local unsigned g_tmap_next = 0;
+static bool tmap_lookup(const TmapKey& k, TensorMap* tm, int) {
+  for (int e = 0; e < 8; ++e)
+    if (g_tmap_cache[e].valid && memcmp(&g_tmap_cache[e].key, &k, sizeof(k)) == 0) { *tm = g_tmap_cache[e].tm; return true; }
+  return false;
+}
+static void tmap_store(const TmapKey& k, const TensorMap* tm, int) {
+  TmapEntry& slot = g_tmap_cache[g_tmap_next++ & 7u];
+  slot.key = k; slot.tm = *tm; slot.valid = true;
+}
+
 bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C, int boxC, int boxW, int boxH) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.d[0] = B; key.d[1] = H; key.d[2] = W; key.d[3] = C; key.d[4] = boxC; key.d[5] = boxW; key.d[6] = boxH;
+  if (tmap_lookup(key, tm, 0)) return true;
   EncodeTiledFn enc = get_encode_fn();
   bind_primary_context();
   if (!enc) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available"); return false; }
@@ -519,6 +503,7 @@ bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C
                          CU_TENSOR_MAP_INTERLEAVE_NONE, boxC * 4 == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (boxC * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return false; }
+  tmap_store(key, tm, 0);
   return true;
 }
 bool make_tmap_nchw(TensorMap* tm, const float* base, int B, int C, int H, int W, int boxW, int boxH, int boxC) {
@@ -536,13 +521,15 @@ bool make_tmap_nchw(TensorMap* tm, const float* base, int B, int C, int H, int W
   return true;
 }
 static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static std::atomic<int> n[64];  // per device ordinal: a process may drive differently sized parts
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int v = n[dev & 63].load(std::memory_order_relaxed);
+  if (!v) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev & 63].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
 #else
 static int sm_count() { return 3; }  // small persistent grid: exercises the multi-tile loop
@@ -580,25 +567,22 @@ static int run_tiled(const float* prv, const float* nxt, const float* flow, floa
   const long long ns = (long long)tiles_x * B * nwin * segs_per_strip;
   if (ns >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
   const int nsegs = (int)ns;
-  const int grid = nsegs < Cfg::OCC * sm_count() ? nsegs : Cfg::OCC * sm_count();
+  const int grid = nsegs < sm_count() ? nsegs : sm_count();
   auto k = corr_fwd_tiled_kernel<Cfg>;
 #ifndef QPWC_EMU
-  static unsigned attr_done = 0;  // per instantiation, one bit per device (the attribute is per device)
+  static std::atomic<unsigned> attr_done{0};  // per instantiation, one bit per device (the attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!(attr_done >> (dev & 31) & 1u)) {
+  if (!(attr_done.load(std::memory_order_acquire) >> (dev & 31) & 1u)) {
     const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_fwd_tiled: smem attribute (%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-    attr_done |= 1u << (dev & 31);
+    attr_done.fetch_or(1u << (dev & 31), std::memory_order_release);
   }
 #endif
   QPWC_LAUNCH(k, grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream, tmP, tmN, nxt, flow, out, B, H, W, C, slope, ops,
               tiles_x, tiles_y, nsegs, segs_per_strip, seg, ablate_flags(), nwin, dsearch, up_scale);
   return check_launch("corr_fwd_tiled");
 }
-
-int launch_corr_fwd_rowpair(const float*, const float*, float*, int, int, int, int, int, float, long long,
-                            cudaStream_t);  // qpwc_corr_rowpair.cu
 
 int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow, int mode, float* out,
                           int B, int H, int W, int C, int d, float slope, long long ops,
@@ -608,37 +592,18 @@ int launch_corr_fwd_tiled(const float* prv, const float* nxt, const float* flow,
   if ((d != 4 && d != 8) || (C & 3) || C < 4) return QPWC_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15)) return QPWC_ERR_UNSUPPORTED;
   if ((long long)H * W < 64) return QPWC_ERR_UNSUPPORTED;
-  // QPWC_TILED_SCALAR=1 (dev): the scalar-FFMA 6-row variant instead of the packed-FFMA2 4-row one
-  static int scalar = -1;
-  if (scalar < 0) { const char* e = getenv("QPWC_TILED_SCALAR"); scalar = (e && atoi(e)) ? 1 : 0; }
-  if (scalar && !flow && d == 4) return run_tiled<TiledCfg<6, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream);
   if (!flow) {
-    // QPWC_CORR_VARIANT=rowpair selects the row-pair kernel (qpwc_corr_rowpair.cu).  Its inner loop
-    // is faster (scalar-broadcast FFMA2, 0.73 vs 0.60 FMA/lane/clk in isolation) but with two
-    // pipeline stages and a 4-slot epilogue it only ties the 4-row kernel end to end on B200
-    // (195 vs 193 us at 224x512x32, B=8; ablations in profiles/README.md), so it is opt-in.
-    const char* var = getenv("QPWC_CORR_VARIANT");
-    if (var && var[0] == 'r')
-      return launch_corr_fwd_rowpair(prv, nxt, out, B, H, W, C, d, slope, ops, stream);
     // few tiles (coarse pyramid levels): 2-row tiles double the number of busy SMs
     const long long tiles4 = (long long)cdiv(W, 56) * cdiv(H, 4) * B * (d == 8 ? 4 : 1);
-    if (tiles4 * 2 <= sm_count()) {
-      if (var && var[0] == 'p')
-        return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
-      return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
-    }
-    // default: scalar FFMA, 4-row tiles, 200 registers per consumer thread.  Measured on B200
-    // (tools/ab_corr.py): 178 vs 192 us at 224x512x32 B=8 against the packed channel-parity FFMA2
-    // variant (QPWC_CORR_VARIANT=packed) -- a 3-register FFMA sustains ~0.7 FMA/lane/clk with 81
-    // accumulators (tools/ubench/corr_loop_bench.cu), the packed loop 0.60 with 162.
-    if (var && var[0] == 'p')
-      return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 1>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
-    if (var && var[0] == 't')
-      return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF, 0, 2>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
-    return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+    if (tiles4 * 2 <= sm_count())
+      return run_tiled<TiledCfg<2, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
+    // scalar FFMA, 4-row tiles, 200 registers per consumer thread (measured against a packed
+    // channel-parity FFMA2 consumer and a row-pair FFMA2 kernel in round 1: 178 vs 192 / 196 us at
+    // 224x512x32 B=8; both variants were removed, profiles/r01_corr_variants.txt keeps the numbers)
+    return run_tiled<TiledCfg<4, 0, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d);
   }
-  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d, up_scale);
-  return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA, 0>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d, up_scale);
+  if (mode == QPWC_MODE_TF) return run_tiled<TiledCfg<4, 1, QPWC_MODE_TF>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d, up_scale);
+  return run_tiled<TiledCfg<4, 1, QPWC_MODE_TFA>>(prv, nxt, flow, out, B, H, W, C, slope, ops, stream, d, up_scale);
 }
 
 #ifdef QPWC_EMU

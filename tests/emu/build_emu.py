@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "qpwcnet_b200", "csrc")
 SO = os.path.join(HERE, "_build", "libqpwc_emu.so")
-SOURCES = ["qpwc_api.cu", "qpwc_warp.cu", "qpwc_corr_direct.cu", "qpwc_corr_tiled.cu", "qpwc_corr_rowpair.cu", "qpwc_upsample.cu", "qpwc_occlusion.cu", "qpwc_corr_nchw.cu", "qpwc_corr_bwd_nchw.cu", "qpwc_corr_tc.cu"]
+SOURCES = ["qpwc_api.cu", "qpwc_warp.cu", "qpwc_corr_direct.cu", "qpwc_corr_tiled.cu", "qpwc_upsample.cu", "qpwc_occlusion.cu", "qpwc_corr_nchw.cu", "qpwc_corr_bwd_nchw.cu", "qpwc_corr_tc.cu"]
 
 
 def build(force=False):

@@ -45,10 +45,19 @@ def assert_as_accurate(got, ref32, ref64, floor=1e-6, factor=4.0):
     assert err_gpu <= max(floor, factor * err_ref), f"gpu err {err_gpu:.3e} vs fp32-reference err {err_ref:.3e}"
 
 
+@pytest.fixture(autouse=True, params=["auto", "ffma"])
+def engine(request):
+    """Every test runs under both cost-volume engines: 'auto' (tensor cores, 3xTF32 split, where the
+    shape allows) and 'ffma' (plain fp32 FFMA kernels only)."""
+    ops.set_corr_engine(request.param)
+    yield request.param
+    ops.set_corr_engine("auto")
+
+
 def test_native_library_is_the_one_loaded():
     L = _cabi.lib()
     assert os.path.samefile(L._name, os.path.join(os.path.dirname(_cabi.__file__), "lib", "libqpwc.so"))
-    assert ops.library_version() >= 100
+    assert ops.library_version() >= 200
 
 
 CV_SHAPES = [
@@ -72,18 +81,27 @@ def test_cost_volume_forward(B, H, W, C, d):
 
 
 @pytest.mark.parametrize("B,H,W,C,d", [(2, 14, 32, 256, 4), (1, 56, 128, 128, 4), (1, 33, 70, 64, 4), (1, 40, 72, 32, 4),
-                                       (1, 17, 19, 16, 4), (1, 20, 30, 32, 8), (2, 11, 61, 96, 4), (3, 61, 190, 36, 4)])
-def test_cost_volume_forward_rowpair_variant(B, H, W, C, d, monkeypatch):
-    """The opt-in row-pair FFMA2 kernel (qpwc_corr_rowpair.cu, QPWC_CORR_VARIANT=rowpair): odd
-    heights (half-filled row pairs), ragged widths, channel tails, d = 8 windows, strided output."""
-    monkeypatch.setenv("QPWC_CORR_VARIANT", "rowpair")
+                                       (1, 17, 19, 16, 4), (2, 11, 61, 96, 4), (3, 61, 190, 40, 4), (1, 8, 16, 8, 4),
+                                       (2, 9, 17, 24, 4), (1, 100, 36, 72, 4)])
+def test_cost_volume_tensor_core_engine(B, H, W, C, d):
+    """The tensor-core kernels (qpwc_corr_tc.cu) forced on: resident (C <= 32) and streaming paths,
+    ragged tiles (H % 8, W % 16), channel counts with a half-filled last stage (C % 16 = 8), strided
+    output; graded per element against the condition number."""
+    ops.set_corr_engine("tc")
     r = rng(B * 977 + C)
     prv = r.standard_normal((B, H, W, C)).astype(np.float32)
     nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
-    ref = oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), d)
+    p64, n64 = prv.astype(np.float64), nxt.astype(np.float64)
+    ref = oracle.cost_volume(p64, n64, d)
     got = host(ops.cost_volume(dev(prv), dev(nxt), d))
     assert_rel(got, ref)
-    D = (2 * d + 1) ** 2
+    pad = np.zeros((B, H + 2 * d, W + 2 * d, C))
+    pad[:, d:d + H, d:d + W] = np.abs(n64)
+    q = 2 * d + 1
+    cond = np.stack([(np.abs(p64) * pad[:, i0:i0 + H, j0:j0 + W]).mean(-1) for i0 in range(q) for j0 in range(q)], -1)
+    err = np.abs(got - ref)
+    assert np.all(err <= 1e-5 * cond + 1e-30), f"worst err/cond {np.max(err / (cond + 1e-30)):.2e}"
+    D = q * q
     buf = torch.full((B, H, W, D + 6), float("nan"), device=DEV)
     ops.cost_volume_into(buf, dev(prv), dev(nxt), d)
     np.testing.assert_array_equal(host(buf[..., :D]), got)
@@ -182,7 +200,7 @@ def test_fused_warp_cost_volume_forward_backward(mode, B, H, W, C, d):
     assert_rel(host(out), ref)
     # fused == unfused composition of our own two ops (same warped values, same correlation)
     comp = ops.cost_volume(dev(prv), ops.warp(dev(nxt), dev(flo), mode), d)
-    assert_rel(host(out), host(comp).astype(np.float64), rel=2e-6)
+    assert_rel(host(out), host(comp).astype(np.float64), rel=2e-6 if ops.get_corr_engine() == "ffma" else 1e-5)
     g = r.standard_normal(ref.shape).astype(np.float32)
     gp, gn, gf = torch.autograd.grad(out, (tp, tn, tf), dev(g))
     # reference gradients with the leaky mask of the GPU forward
@@ -303,7 +321,8 @@ def test_cost_volume_channels_first_native(B, C, H, W):
     assert tuple(out.shape) == (B, 81, H, W)
     assert_rel(host(out).transpose(0, 2, 3, 1), ref)
     nhwc = ops.cost_volume(tp.detach().permute(0, 2, 3, 1).contiguous(), tn.detach().permute(0, 2, 3, 1).contiguous(), 4)
-    assert float((out.detach().permute(0, 2, 3, 1) - nhwc).abs().max()) <= 2e-6 * float(nhwc.abs().max())
+    tol = 2e-6 if ops.get_corr_engine() == "ffma" else 1e-5      # NCHW kernel is FFMA; the NHWC op may run on tensor cores
+    assert float((out.detach().permute(0, 2, 3, 1) - nhwc).abs().max()) <= tol * float(nhwc.abs().max())
     g = r.standard_normal((B, 81, H, W)).astype(np.float32)
     gp, gn = torch.autograd.grad(out, (tp, tn), dev(g))
     rp, rn = oracle.cost_volume_bwd(prv.transpose(0, 2, 3, 1).astype(np.float64), nxt.transpose(0, 2, 3, 1).astype(np.float64),
@@ -697,3 +716,45 @@ def test_golden_occlusion():
         t = dev(g[f"{name}/flow"])
         np.testing.assert_array_equal(host(ops.occlusion_map(t)), g[f"{name}/map"])
         np.testing.assert_array_equal(host(ops.occlusion_map(t.permute(0, 3, 1, 2).contiguous(), "channels_first")), g[f"{name}/map"])
+
+
+def test_two_threads_two_streams():
+    """include/qpwc.h threading contract: concurrent calls from two host threads on two streams (their
+    own tensors, shared library state limited to per-device atomics and per-thread caches)."""
+    import threading
+    r = rng(4242)
+    jobs = []
+    for k, (B, H, W, C) in enumerate([(2, 40, 72, 32), (1, 33, 70, 64)]):
+        prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+        nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+        flo = (r.standard_normal((B, H, W, 2)) * 2).astype(np.float32)
+        jobs.append((prv, nxt, flo))
+    results, errors = [None, None], []
+
+    def work(k):
+        try:
+            prv, nxt, flo = jobs[k]
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                tp, tn, tf_ = dev(prv), dev(nxt), dev(flo)
+                acc = []
+                for _ in range(20):
+                    acc.append((ops.cost_volume(tp, tn, 4), ops.warp(tn, tf_, "tfa"), ops.warp_cost_volume(tp, tn, tf_, "tfa", 4)))
+                st.synchronize()
+                results[k] = [tuple(host(t) for t in a) for a in (acc[0], acc[-1])]
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    for k, (prv, nxt, flo) in enumerate(jobs):
+        first, last = results[k]
+        for a, b in zip(first, last):
+            np.testing.assert_array_equal(a, b)                  # deterministic under concurrency
+        assert_rel(first[0], oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), 4))
+        np.testing.assert_array_equal(first[1], oracle.warp(nxt, flo, "tfa"))
+        assert_rel(first[2], oracle.warp_cost_volume(*(a.astype(np.float64) for a in (prv, nxt, flo)), "tfa", 4))
