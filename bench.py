@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1]): the cost-volume / warp call pattern of one PWC-Net forward
-pass -- 1 plain cost volume + 4 fused warp->cost volumes -- on Sintel-shaped 436x1024 pairs
+pass -- 1 plain cost volume + 4 UpFlow warp->cost-volume pairs -- on Sintel-shaped 436x1024 pairs
 (padded to 448x1024), batch 8, search range 4, fp32, synthetic inputs (seed 0).  One "step" = one
 pass over one batch of 8 frame pairs.  N > 1: every rank runs its own batch (independent frame
 pairs, no collective on the data path) => weak scaling; value = 8*N / max-over-ranks step time.
@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "frame-pairs/s at 436x1024 B=8 (PWC-Net pyramid hot path: 1 corr + 4 fused warp->corr, d=4)"
+METRIC = "frame-pairs/s at 436x1024 B=8 (PWC-Net pyramid hot path: 1 cost volume + 4 UpFlow warp->cost-volume pairs, d=4)"
 UNIT = "frame-pairs/s"
 HEIGHT, WIDTH, BATCH, SEARCH = 436, 1024, 8, 4
 FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -216,7 +216,7 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    assert ops.library_version() >= 100
+    assert ops.library_version() >= 200
     K, Wm = args.steps, max(args.warmup, 3)
     wl = PyramidWorkload(HEIGHT, WIDTH, BATCH, SEARCH, device=dev, seed=rank, path=args.path)
     dom = max(range(len(wl.levels)), key=lambda k: algorithmic_bytes(wl.levels[k], BATCH, SEARCH))
@@ -297,8 +297,8 @@ def run_native(args):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": load_traffic(), "peak_source": peak_src,
-        "kernel": f"{wl.level_path[dom]} warp->corr level {lv.H}x{lv.W}x{lv.C} B={BATCH} d={SEARCH}"
-                  + (" (timed: warp kernel + corr kernel)" if wl.level_path[dom] == "composed" else ""),
+        "kernel": f"UpFlow warp->cost-volume, level {lv.H}x{lv.W}x{lv.C} B={BATCH} d={SEARCH}, path '{wl.level_path[dom]}' "
+                  "(warp kernel + tensor-core cost-volume kernel; bytes = those of the fused op)",
         "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": dom_ms,
         "share_of_step": dom_ms / ms_per_step,
         "fp32": {"achieved_tflops": aflops / (dom_ms * 1e-3) / 1e12, "peak_tflops": FP32_PEAK_TFLOPS,
@@ -308,6 +308,96 @@ def run_native(args):
                        "gbs": wl.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9,
                        "tflops": wl.algorithmic_flops() / (ms_per_step * 1e-3) / 1e12},
     }
+
+    # per-kernel times of the dominant level (warp kernel, cost-volume kernel, the library's fused entry
+    # point) and the in-kernel fusion of the FFMA engine, each timed alone with L2 flushed in between
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+
+    def alone(fn, reps=10):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2]
+
+    prv_d, nxt_d, flo_d = wl.inputs[dom]
+    scratch_d = wl.scratch[dom] if wl.scratch[dom] is not None else torch.empty_like(nxt_d)
+    breakdown = {
+        "warp_kernel_ms": alone(lambda: ops.warp_into(scratch_d, nxt_d, flo_d, wl.mode)),
+        "cost_volume_kernel_ms": alone(lambda: ops.cost_volume_into(wl.outputs[dom], prv_d, scratch_d, SEARCH)),
+        "fused_entry_point_ms": alone(lambda: ops.warp_cost_volume_into(wl.outputs[dom], prv_d, nxt_d, flo_d, wl.mode, SEARCH)),
+        "engine": ops.get_corr_engine(),
+    }
+    ops.set_corr_engine("ffma")
+    t_ffma_fused = alone(lambda: ops.warp_cost_volume_into(wl.outputs[dom], prv_d, nxt_d, flo_d, wl.mode, SEARCH))
+    t_ffma_corr = alone(lambda: ops.cost_volume_into(wl.outputs[dom], prv_d, scratch_d, SEARCH))
+    ops.set_corr_engine("auto")
+    roofline["breakdown"] = breakdown
+    roofline_fused = {
+        "kernel": "in-kernel fused warp->corr (FFMA engine, warped tile only in shared memory), same level",
+        "avg_launch_ms": t_ffma_fused, "achieved": abytes / (t_ffma_fused * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": abytes / (t_ffma_fused * 1e-3) / 1e9 / peak, "ffma_cost_volume_kernel_ms": t_ffma_corr,
+        "note": "kept for the FFMA engine; loses to warp kernel + tensor-core cost volume at every level (halo recompute, latency-bound gathers)",
+    }
+    del flush
+
+    # ---- config 3: hot path of one training step (forward + backward), global batch 64 over the ranks
+    train = None
+    if not args.no_train:
+        from qpwcnet_b200.train_step import TrainHotPath
+        per = max(1, 64 // world)
+        th = TrainHotPath(per, dev, seed=rank, world=world)
+        for _ in range(3):
+            th.step(); th.zero_grad()
+        Kt = max(3, min(K, 20))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(Kt):
+            th.step(); th.zero_grad()
+        e1.record()
+        barrier()
+        t_train = max_over_ranks(e0.elapsed_time(e1) / Kt)
+        t_ar = None
+        if world > 1:   # the collective alone (all five buckets back to back) and the step without it
+            for _ in range(2):
+                for bkt in th.buckets:
+                    dist.all_reduce(bkt)
+            barrier()
+            e0.record()
+            for _ in range(10):
+                for bkt in th.buckets:
+                    dist.all_reduce(bkt)
+            e1.record()
+            barrier()
+            t_ar = max_over_ranks(e0.elapsed_time(e1) / 10)
+            th.allreduce = False
+            th.step(); th.zero_grad()
+            barrier()
+            e0.record()
+            for _ in range(Kt):
+                th.step(); th.zero_grad()
+            e1.record()
+            barrier()
+            t_noar = max_over_ranks(e0.elapsed_time(e1) / Kt)
+        train = {
+            "config": "frame-interpolation pre-training step hot path, 256x448 triplets, global batch 64 "
+                      f"({per} per GPU x {world}): 10 cost volumes + 18 warps, forward and backward",
+            "ms_per_step": t_train, "triplets_per_s": per * world / (t_train * 1e-3), "steps": Kt,
+            "algorithmic_bytes_per_gpu": th.algorithmic_bytes(),
+            "hbm_frac": th.algorithmic_bytes() / (t_train * 1e-3) / 1e9 / peak,
+            "allreduce": None if world == 1 else {
+                "bytes_per_step": th.allreduce_bytes(), "buckets": len(th.buckets),
+                "alone_ms": t_ar, "step_without_ms": t_noar, "exposed_ms": t_train - t_noar,
+                "note": "NCCL all-reduce per pyramid level on a side stream, issued as that level's backward "
+                        "calls finish; bucket values are synthetic (the conv stacks are out of scope)"},
+        }
+        del th
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -321,13 +411,16 @@ def run_native(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "pwcnet-pyramid-hotpath 436x1024 (padded 448x1024) B=8 per GPU, d=4, warp mode tfa",
-                       "levels": "14x32x256(corr) 28x64x256 56x128x128 112x256x64 224x512x32 (fused warp->corr)",
+                       "levels": "14x32x256 (cost volume) 28x64x256 56x128x128 112x256x64 224x512x32 (UpFlow: warp -> cost volume)",
+                       "engine": "cost volume on tensor cores (tcgen05, fp32 operands as 3xTF32 split, fp32 accumulate; "
+                                 "max error 8e-7 x mean|prv*nxt| vs the 1e-5 contract); warp: fp32 gather kernel, bit-exact",
                        "l2": "inputs larger than L2: each step streams 853 MB of distinct tensors (126 MB L2)",
                        "parallelism": f"batch-sharded replicas x{world}, no collective on the data path",
                        "launch": ("CUDA graph of the %d launches per step" if use_graph else "%d individual launches per step") % wl.launches_per_step,
                        "upflow_path": dict(zip([f"{l.H}x{l.W}x{l.C}" for l in wl.levels], wl.level_path)),
                        "autotune_ms": getattr(wl, "autotune_ms", None)},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "roofline_fused": roofline_fused, "train_step": train,
+            "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": wl.launches_per_step * K, "clocks": sampler.summary(note),
         }
         print(json.dumps(line), flush=True)
@@ -344,6 +437,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the 5 kernels per step individually")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-3 training-step section")
     ap.add_argument("--path", default="auto", choices=["auto", "fused", "composed"],
                     help="UpFlow levels: fused kernel, warp + cost volume, or time both and keep the faster")
     args = ap.parse_args()

@@ -151,13 +151,19 @@ int qpwc_warp_corr_fwd_up(const float* prv, const float* nxt, const float* flow_
                           long long out_pixel_stride, float up_scale, void* stream);
 
 /* UpFlow's  CostVolumeV2((prv, WarpV2((nxt, flo))))  -- qpwcnet/core/non_layers.py:377-380
- * (layers.py:478-481) as ONE kernel: the warped second frame never reaches HBM. */
+ * (layers.py:478-481) as ONE call in which the warped second frame never makes the round trip through
+ * HBM.  Tensor-core engine (default where the shape allows): the warp kernel and the cost-volume kernel
+ * run back to back on chunks of frame pairs through a stream-ordered scratch buffer that stays resident
+ * in the 126 MB L2 and is reused chunk after chunk.  FFMA engine / other shapes: one kernel, the warped
+ * tile lives in shared memory only. */
 int qpwc_warp_corr_fwd(const float* prv, const float* nxt, const float* flow, float* out, int B,
                        int H, int W, int C, int search_range, float leaky_slope, int mode,
                        long long out_pixel_stride, void* stream);
 
-/* Gradient of the fused op: g_prv, g_nxt (zero-filled here), g_flow.  `workspace` must hold
- * qpwc_warp_corr_bwd_workspace(B,H,W,C) bytes of device memory. */
+/* Gradient of the fused op: g_prv, g_nxt (zero-filled here), g_flow.  No caller workspace (since
+ * 0.2): the warped frame and its gradient are rebuilt chunk by chunk in an L2-resident, stream-ordered
+ * scratch buffer owned by the call; `workspace` / `workspace_bytes` are accepted and ignored, and
+ * qpwc_warp_corr_bwd_workspace() returns 0. */
 size_t qpwc_warp_corr_bwd_workspace(int B, int H, int W, int C);
 int qpwc_warp_corr_bwd(const float* prv, const float* nxt, const float* flow, const float* out,
                        const float* g_out, float* g_prv, float* g_nxt, float* g_flow,

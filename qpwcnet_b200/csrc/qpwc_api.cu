@@ -101,6 +101,80 @@ static int corr_bwd_any(const float* prv, const float* nxt, const float* out, co
   return launch_corr_bwd_direct(prv, nxt, out, g_out, g_prv, g_nxt, B, H, W, C, d, slope, ops, st);
 }
 
+
+// ------------------------------------------------------------------ warp -> corr through L2
+// The UpFlow pair with the tensor-core cost volume: the stand-alone warp kernel writes the warped second
+// frame of a chunk of frame pairs into a stream-ordered scratch buffer owned by the call and the
+// cost-volume kernel reads it back; the scratch is reused chunk after chunk.  Every warped pixel is
+// computed once -- the in-kernel fusion (FFMA engine) recomputes the 8-pixel halo of every tile with
+// latency-bound gathers, which is why it loses to this composition at every level although it moves
+// fewer DRAM bytes (profiles/README.md has both byte counts).  What stays in L2 between the two
+// kernels depends on the chunk size against the 126 MB L2: the coarse levels fit, the finest config-2
+// level (117 MB) largely does not.
+// Scratch per chunk.  Measured (profiles/README.md): splitting B = 8 at the finest level into two
+// L2-sized chunks costs more in tile-count imbalance of the persistent kernel (24.2 tiles per SM run as 28)
+// than the L2 hits save, so a chunk is as large as a whole config-2 level; bigger batches are cut here.
+static const size_t kL2ChunkBytes = (size_t)160 << 20;
+
+// Stream-ordered scratch: cudaMallocAsync from the device's default pool.  By default that pool hands
+// its memory back to the OS at every synchronisation (release threshold 0), which turns each call into
+// a driver allocation of ~100 MB; raise the threshold once per device so that the block is recycled.
+static int scratch_alloc(float** p, size_t bytes, cudaStream_t st, const char* fn) {
+  static std::atomic<unsigned> pool_ready{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(pool_ready.load(std::memory_order_acquire) >> (dev & 31) & 1u)) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_ready.fetch_or(1u << (dev & 31), std::memory_order_release);
+  }
+  const cudaError_t e = cudaMallocAsync(p, bytes, st);
+  if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "%s: scratch (%zu B): %s", fn, bytes, cudaGetErrorString(e));
+  return QPWC_OK;
+}
+
+static int chunk_batch(int B, size_t per_item_bytes) {
+  size_t n = per_item_bytes ? kL2ChunkBytes / per_item_bytes : (size_t)B;
+  if (n < 1) n = 1;
+  if (n > (size_t)B) n = (size_t)B;
+  // even chunks: B = 8 with room for 5 items runs as 4 + 4, not 5 + 3
+  const int nchunks = (B + (int)n - 1) / (int)n;
+  return (B + nchunks - 1) / nchunks;
+}
+
+static bool tc_domain(const float* prv, const float* nxt, int C, int d) {
+  return d == 4 && C >= 8 && (C & 7) == 0 && !(reinterpret_cast<uintptr_t>(prv) & 15) && !(reinterpret_cast<uintptr_t>(nxt) & 15);
+}
+
+static int warp_corr_fwd_l2(const float* prv, const float* nxt, const float* flow, int mode, float* out, int B,
+                            int H, int W, int C, int d, float slope, long long ops, cudaStream_t st, float up_scale) {
+  const size_t item = (size_t)H * W * C, fitem = up_scale != 0.f ? (size_t)(H / 2) * (W / 2) * 2 : (size_t)H * W * 2;
+  const int per = chunk_batch(B, item * sizeof(float));
+  float* scratch = nullptr;
+  int rc = scratch_alloc(&scratch, item * per * sizeof(float), st, "warp_corr_fwd");
+  if (rc != QPWC_OK) return rc;
+  cudaError_t e;
+  for (int b0 = 0; b0 < B && rc == QPWC_OK; b0 += per) {
+    const int nb = B - b0 < per ? B - b0 : per;
+    rc = launch_warp_fwd_ex(nxt + item * b0, flow + fitem * b0, nullptr, nullptr, scratch, nb, H, W, C, mode, 1.f, C, st, up_scale);
+    if (rc == QPWC_OK) rc = launch_corr_fwd_tc(prv + item * b0, scratch, out + (size_t)H * W * ops * b0, nb, H, W, C, d, slope, ops, st);
+  }
+  e = cudaFreeAsync(scratch, st);
+  if (rc == QPWC_OK && e != cudaSuccess) rc = set_error(QPWC_ERR_CUDA, "warp_corr_fwd: scratch free: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+static int warp_corr_fwd_any(const float* prv, const float* nxt, const float* flow, int mode, float* out, int B,
+                             int H, int W, int C, int d, float slope, long long ops, cudaStream_t st, float up_scale = 0.f) {
+  const int engine = g_corr_engine.load(std::memory_order_relaxed);
+  if (engine != 1 && tc_domain(prv, nxt, C, d)) return warp_corr_fwd_l2(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);
+  if (engine == 2) return set_error(QPWC_ERR_UNSUPPORTED, "warp_corr_fwd: tensor-core engine needs search_range 4, C %% 8 == 0 and 16-byte aligned inputs");
+  return corr_fwd_any(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);  // in-kernel fusion (FFMA)
+}
+
 // ------------------------------------------------------------------------------- host staging
 // One workspace per device: NSLOT independent (stream, device buffer) slots.  A slot's stream runs
 // H2D -> kernel -> D2H for one batch slice; different slots overlap (both copy engines + SMs).
@@ -153,7 +227,9 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
   HostStage& hs = g_stage[device];
   std::lock_guard<std::mutex> lock(hs.mu);
   int rc = QPWC_OK, slot = hs.next_slot;
-  const size_t slot_floats = pad4(n_a * per) + pad4(n_b * per) + pad4(n_f * per) + pad4(n_o * per);
+  const bool l2pair = kind == 2 && g_corr_engine.load(std::memory_order_relaxed) != 1 && d == 4 && C >= 8 && (C & 7) == 0;
+  const size_t n_w = l2pair ? n_a : 0;  // warped second frame of a slice (tensor-core engine: warp + cost volume)
+  const size_t slot_floats = pad4(n_a * per) + pad4(n_b * per) + pad4(n_f * per) + pad4(n_o * per) + pad4(n_w * per);
   for (int b0 = 0; b0 < B && rc == QPWC_OK; b0 += per, slot = (slot + 1) % HostStage::NSLOT) {
     const int nb = (B - b0 < per) ? (B - b0) : per;
     rc = stage_reserve(hs, slot, slot_floats * sizeof(float));
@@ -163,13 +239,17 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
     float* db = da + pad4(n_a * per);
     float* df = db + pad4(n_b * per);
     float* dout = df + pad4(n_f * per);
+    float* dw = dout + pad4(n_o * per);
     e = cudaMemcpyAsync(da, a + n_a * b0, n_a * nb * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && n_b) e = cudaMemcpyAsync(db, b + n_b * b0, n_b * nb * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && n_f) e = cudaMemcpyAsync(df, f + n_f * b0, n_f * nb * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { rc = set_error(QPWC_ERR_CUDA, "host call: H2D: %s", cudaGetErrorString(e)); break; }
     if (kind == 0) rc = corr_fwd_any(da, db, nullptr, 0, dout, nb, H, W, C, d, slope, (long long)D, st);
     else if (kind == 1) rc = launch_warp_fwd(da, df, dout, nb, H, W, C, mode, st);
-    else rc = corr_fwd_any(da, db, df, mode, dout, nb, H, W, C, d, slope, (long long)D, st);
+    else if (l2pair) {
+      rc = launch_warp_fwd(db, df, dw, nb, H, W, C, mode, st);
+      if (rc == QPWC_OK) rc = launch_corr_fwd_tc(da, dw, dout, nb, H, W, C, d, slope, (long long)D, st);
+    } else rc = corr_fwd_any(da, db, df, mode, dout, nb, H, W, C, d, slope, (long long)D, st);
     if (rc != QPWC_OK) break;
     e = cudaMemcpyAsync(out + n_o * b0, dout, n_o * nb * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) { rc = set_error(QPWC_ERR_CUDA, "host call: D2H: %s", cudaGetErrorString(e)); break; }
@@ -427,8 +507,8 @@ int qpwc_warp_corr_fwd_up(const float* prv, const float* nxt, const float* flow_
   QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt)); QPWC_TRY(check_ptr(fn, "flow_coarse", flow_coarse));
   QPWC_TRY(check_ptr(fn, "out", out));
   if (reinterpret_cast<uintptr_t>(flow_coarse) % 8) return set_error(QPWC_ERR_INVALID, "%s: flow must be 8-byte aligned", fn);
-  return corr_fwd_any(prv, nxt, flow_coarse, mode, out, B, H, W, C, search_range, leaky_slope, out_pixel_stride,
-                      (cudaStream_t)stream, up_scale);
+  return warp_corr_fwd_any(prv, nxt, flow_coarse, mode, out, B, H, W, C, search_range, leaky_slope, out_pixel_stride,
+                           (cudaStream_t)stream, up_scale);
 }
 
 int qpwc_warp_corr_fwd(const float* prv, const float* nxt, const float* flow, float* out, int B,
@@ -443,12 +523,12 @@ int qpwc_warp_corr_fwd(const float* prv, const float* nxt, const float* flow, fl
   QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt));
   QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
   if (reinterpret_cast<uintptr_t>(flow) % 8) return set_error(QPWC_ERR_INVALID, "%s: flow must be 8-byte aligned", fn);
-  return corr_fwd_any(prv, nxt, flow, mode, out, B, H, W, C, search_range, leaky_slope, out_pixel_stride, (cudaStream_t)stream);
+  return warp_corr_fwd_any(prv, nxt, flow, mode, out, B, H, W, C, search_range, leaky_slope, out_pixel_stride, (cudaStream_t)stream);
 }
 
 size_t qpwc_warp_corr_bwd_workspace(int B, int H, int W, int C) {
-  if (B <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
-  return 2 * sizeof(float) * (size_t)B * H * W * C;  // warped second frame + its gradient
+  (void)B; (void)H; (void)W; (void)C;
+  return 0;  // since 0.2: the intermediate lives in a stream-ordered, L2-sized scratch owned by the call
 }
 
 int qpwc_warp_corr_bwd(const float* prv, const float* nxt, const float* flow, const float* out,
@@ -457,25 +537,39 @@ int qpwc_warp_corr_bwd(const float* prv, const float* nxt, const float* flow, co
                        int search_range, float leaky_slope, int mode, long long out_pixel_stride,
                        void* stream) {
   const char* fn = "qpwc_warp_corr_bwd";
+  (void)workspace; (void)workspace_bytes;  // accepted for source compatibility with 0.1, unused
   QPWC_TRY(check_shape(fn, B, H, W, C));
   QPWC_TRY(check_corr_args(fn, search_range, out_pixel_stride));
   if (empty(B, H, W, C)) return QPWC_OK;
   QPWC_TRY(check_mode(fn, mode, H, W));
   QPWC_TRY(check_ptr(fn, "prv", prv)); QPWC_TRY(check_ptr(fn, "nxt", nxt)); QPWC_TRY(check_ptr(fn, "flow", flow));
   QPWC_TRY(check_ptr(fn, "out", out)); QPWC_TRY(check_ptr(fn, "g_out", g_out)); QPWC_TRY(check_ptr(fn, "g_prv", g_prv));
-  QPWC_TRY(check_ptr(fn, "g_nxt", g_nxt)); QPWC_TRY(check_ptr(fn, "g_flow", g_flow)); QPWC_TRY(check_ptr(fn, "workspace", workspace));
+  QPWC_TRY(check_ptr(fn, "g_nxt", g_nxt)); QPWC_TRY(check_ptr(fn, "g_flow", g_flow));
   if (reinterpret_cast<uintptr_t>(flow) % 8 || reinterpret_cast<uintptr_t>(g_flow) % 8)
     return set_error(QPWC_ERR_INVALID, "%s: flow and g_flow must be 8-byte aligned", fn);
-  const size_t need = qpwc_warp_corr_bwd_workspace(B, H, W, C);
-  if (workspace_bytes < need) return set_error(QPWC_ERR_INVALID, "%s: workspace %zu B < required %zu B", fn, workspace_bytes, need);
-  if (reinterpret_cast<uintptr_t>(workspace) % 16) return set_error(QPWC_ERR_INVALID, "%s: workspace must be 16-byte aligned", fn);
   cudaStream_t st = (cudaStream_t)stream;
-  float* nxt_w = static_cast<float*>(workspace);
-  float* g_nxt_w = nxt_w + (size_t)B * H * W * C;
-  // chain rule over the two stages; the warped frame is rebuilt in the workspace, never kept
-  QPWC_TRY(launch_warp_fwd(nxt, flow, nxt_w, B, H, W, C, mode, st));
-  QPWC_TRY(corr_bwd_any(prv, nxt_w, out, g_out, g_prv, g_nxt_w, B, H, W, C, search_range, leaky_slope, out_pixel_stride, st));
-  return launch_warp_bwd(nxt, flow, g_nxt_w, g_nxt, g_flow, B, H, W, C, mode, st);
+  // Chain rule over the two stages, a chunk of frame pairs at a time: the warped frame and its
+  // gradient (2 x chunk x H x W x C floats) are rebuilt in a scratch buffer that is reused chunk after
+  // chunk and sized to stay resident in L2 -- neither tensor is ever materialised in HBM for the
+  // whole batch, and the caller provides no workspace.
+  const size_t item = (size_t)H * W * C;
+  const int per = chunk_batch(B, 2 * item * sizeof(float));
+  float* scratch = nullptr;
+  int rc = scratch_alloc(&scratch, 2 * item * per * sizeof(float), st, fn);
+  if (rc != QPWC_OK) return rc;
+  cudaError_t e;
+  float* nxt_w = scratch;
+  float* g_nxt_w = scratch + item * per;
+  for (int b0 = 0; b0 < B && rc == QPWC_OK; b0 += per) {
+    const int nb = B - b0 < per ? B - b0 : per;
+    const size_t o = item * b0, of = (size_t)H * W * 2 * b0, oo = (size_t)H * W * out_pixel_stride * b0;
+    rc = launch_warp_fwd(nxt + o, flow + of, nxt_w, nb, H, W, C, mode, st);
+    if (rc == QPWC_OK) rc = corr_bwd_any(prv + o, nxt_w, out + oo, g_out + oo, g_prv + o, g_nxt_w, nb, H, W, C, search_range, leaky_slope, out_pixel_stride, st);
+    if (rc == QPWC_OK) rc = launch_warp_bwd(nxt + o, flow + of, g_nxt_w, g_nxt + o, g_flow + of, nb, H, W, C, mode, st);
+  }
+  e = cudaFreeAsync(scratch, st);
+  if (rc == QPWC_OK && e != cudaSuccess) rc = set_error(QPWC_ERR_CUDA, "%s: scratch free: %s", fn, cudaGetErrorString(e));
+  return rc;
 }
 
 int qpwc_corr_fwd_host(const float* prv, const float* nxt, float* out, int B, int H, int W, int C,

@@ -197,12 +197,11 @@ def _warp_corr_bwd(prv, nxt, flow, out, g_out, mode, d, slope):
     B, H, W, C = prv.shape
     ops = out.shape[-1]
     g_prv, g_nxt, g_flow = torch.empty_like(prv), torch.empty_like(nxt), torch.empty_like(flow)
-    nbytes = int(lib().qpwc_warp_corr_bwd_workspace(B, H, W, C))
-    ws = torch.empty((max(nbytes, 16) + 3) // 4, dtype=torch.float32, device=prv.device)
-    vp, vn, vf, vo, vg, vgp, vgn, vgf, vw = _views(prv, nxt, flow, out, g_out, g_prv, g_nxt, g_flow, ws)
+    # no workspace (library >= 0.2): the call owns an L2-resident scratch for the warped frame and its gradient
+    vp, vn, vf, vo, vg, vgp, vgn, vgf = _views(prv, nxt, flow, out, g_out, g_prv, g_nxt, g_flow)
     with _on_device(prv.device):
         check(lib().qpwc_warp_corr_bwd(vp.ptr, vn.ptr, vf.ptr, vo.ptr, vg.ptr, vgp.ptr, vgn.ptr,
-                                       vgf.ptr, vw.ptr, ws.numel() * 4, B, H, W, C, d, slope, mode,
+                                       vgf.ptr, None, 0, B, H, W, C, d, slope, mode,
                                        ops, _stream_ptr(prv.device)))
     return g_prv, g_nxt, g_flow
 

@@ -570,6 +570,23 @@ def test_host_buffer_entry_points_match_device_path():
                        ops.warp_cost_volume(prv.to(DEV), nxt.to(DEV), flo.to(DEV), "tfa", 4).cpu())
 
 
+@pytest.mark.parametrize("B,H,W,C", [(1, 3, 3, 1), (3, 5, 7, 3), (1, 9, 11, 5), (3, 3, 5, 7)])
+def test_host_buffer_path_odd_sizes(B, H, W, C):
+    """Staged host path with odd H*W*C and odd slice sizes: every sub-buffer of a staging slot starts on
+    a 16-byte boundary (the flow is read as float2, the tensors as float4 where C allows)."""
+    r = rng(31 + C)
+    img = torch.from_numpy(r.random((B, H, W, C)).astype(np.float32))
+    prv = torch.from_numpy(r.standard_normal((B, H, W, C)).astype(np.float32))
+    flo = torch.from_numpy((r.standard_normal((B, H, W, 2)) * 1.5).astype(np.float32))
+    for mode in ("tf", "tfa"):
+        np.testing.assert_array_equal(ops.warp(img, flo, mode).numpy(), oracle.warp(img.numpy(), flo.numpy(), mode))
+        got = ops.warp_cost_volume(prv, img, flo, mode, 4).numpy()
+        assert_rel(got, oracle.warp_cost_volume(prv.numpy().astype(np.float64), img.numpy().astype(np.float64),
+                                                flo.numpy().astype(np.float64), mode, 4))
+    assert_rel(ops.cost_volume(prv, img, 4).numpy(), oracle.cost_volume(prv.numpy().astype(np.float64), img.numpy().astype(np.float64), 4))
+    torch.cuda.synchronize()
+
+
 def test_non_default_stream_and_noncontiguous_inputs():
     r = rng(29)
     prv = dev(r.standard_normal((2, 12, 14, 16)))

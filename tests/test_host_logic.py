@@ -46,7 +46,8 @@ def test_argument_validation_needs_no_device():
     assert b"2x2" in L.qpwc_last_error()
     assert L.qpwc_warp_fwd(None, None, None, 1, 4, 4, 3, 7, None) == _cabi.QPWC_ERR_INVALID
     assert L.qpwc_corr_fwd(None, None, None, 0, 4, 4, 3, 4, 0.1, 81, None) == _cabi.QPWC_OK   # empty batch
-    assert L.qpwc_warp_corr_bwd_workspace(2, 3, 4, 5) == 2 * 4 * 2 * 3 * 4 * 5
+    assert L.qpwc_warp_corr_bwd_workspace(2, 3, 4, 5) == 0      # since 0.2: no caller workspace
+    assert L.qpwc_set_option(0, 7) == _cabi.QPWC_ERR_INVALID and L.qpwc_set_option(0, 0) == _cabi.QPWC_OK
     with pytest.raises(_cabi.QpwcError, match="NULL"):
         _cabi.check(L.qpwc_warp_bwd(None, None, None, None, None, 1, 4, 4, 3, 0, None))
 
