@@ -131,3 +131,149 @@ def warp_cost_volume(prv_band, nxt_band, flow_band, mode="tfa", search_range=4, 
     prv_h = torch.nn.functional.pad(prv_band, (0, 0, 0, 0, top, bot))
     out = op(prv_h, nxt_h, flow_h, mode, d, leaky_slope)
     return out[:, top:out.shape[1] - bot].contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# Overlapped, allocation-free variant ("interior rows compute while halos are in flight")
+# ---------------------------------------------------------------------------------------------
+class ShardedLevel:
+    """One pyramid level of a row-sharded frame pair on this rank, with every buffer allocated once.
+
+    Layout: the band's rows live in the middle of halo-padded buffers (`R` rows above and below), so
+    the neighbours' rows are received straight into their final place -- no cat / pad / crop.  `R` =
+    `d` for the plain cost volume; `d + reach + 1` for the UpFlow pair, `reach` being a fixed budget for
+    the vertical flow (the generic functions above handle larger flows by agreeing on the
+    halo size with a collective).  Bands must be at least `R` rows tall.
+
+    A call enqueues, without any host synchronisation:
+      side stream : send the first / last R band rows to the row neighbours, receive theirs (NCCL p2p)
+      main stream : the rows that need no neighbour data -- cost volume: band rows [d, h-d);
+                    pair: the warp of band rows [reach+1, h-reach-1)
+      main stream, after the exchange: the border strips (cost volume: rows [0,d) and [h-d,h) through a
+                    3d-row scratch; pair: the two warp strips, then ONE cost-volume call over the
+                    halo-padded warped band, whose band rows are all valid).
+    Image-border ranks have no neighbour on one side: their halo rows stay zero (cost volume:
+    ZeroPadding2D semantics).  The warp samples absolute image rows, so the pair hands the warp a view
+    whose row 0 is the image's row 0 only on the first rank; on the others the flow is a displacement
+    and band-local indices differ from absolute ones by a constant, which changes the fp32 rounding
+    of `row + flow` by at most an ulp of the row index (same note as `warp_cost_volume` above).
+    """
+
+    def __init__(self, H, W, C, search_range=4, reach=0, pair=False, mode="tfa", group=None, device=None,
+                 ops_module=None):
+        self.group, self.d, self.pair, self.mode = group, int(search_range), bool(pair), mode
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.r0, self.r1 = band(H, self.rank, self.world)
+        self.h, self.H, self.W, self.C = self.r1 - self.r0, H, W, C
+        self.reach = int(reach)
+        self.R = self.d + (self.reach + 1 if pair else 0)
+        if self.h < self.R and self.world > 1:
+            raise ValueError(f"band of {self.h} rows is thinner than the halo ({self.R} rows): use the generic functions")
+        from . import ops as _ops
+        self.ops = ops_module or _ops
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.dev = torch.device(dev)
+        R, h, D = self.R, self.h, (2 * self.d + 1) ** 2
+        z = lambda *s: torch.zeros(s, device=self.dev)  # noqa: E731
+        self.nxt_h = z(1, h + 2 * R, W, C)
+        self.prv_h = z(1, h + 2 * self.d, W, C)        # halo rows of prv are never read for valid outputs
+        self.out_h = z(1, h + 2 * self.d, W, D)
+        if pair:
+            self.flow_h = z(1, h + 2 * R, W, 2)
+            self.nxtw_h = z(1, h + 2 * self.d, W, C)    # warped band with the d halo rows the cost volume reads
+        else:
+            self.strip = z(1, 3 * self.d, W, D)
+        self.up, self.down = self.rank - 1, self.rank + 1
+        self.side = torch.cuda.Stream(device=self.dev) if self.dev.type == "cuda" else None
+
+    # views
+    @property
+    def nxt(self):
+        return self.nxt_h[:, self.R:self.R + self.h]
+
+    @property
+    def prv(self):
+        return self.prv_h[:, self.d:self.d + self.h]
+
+    @property
+    def flow(self):
+        return self.flow_h[:, self.R:self.R + self.h]
+
+    @property
+    def out(self):
+        return self.out_h[:, self.d:self.d + self.h]
+
+    def _exchange(self, bufs):
+        """Post the halo sends / receives of every (haloed tensor) in `bufs`; returns the requests."""
+        R, h, p2p = self.R, self.h, []
+        for t in bufs:
+            if self.up >= 0:
+                p2p.append(dist.P2POp(dist.isend, t[:, R:2 * R], self.up, self.group))
+                p2p.append(dist.P2POp(dist.irecv, t[:, 0:R], self.up, self.group))
+            if self.down < self.world:
+                p2p.append(dist.P2POp(dist.isend, t[:, h:h + R], self.down, self.group))
+                p2p.append(dist.P2POp(dist.irecv, t[:, h + R:h + 2 * R], self.down, self.group))
+        return dist.batch_isend_irecv(p2p) if p2p else []
+
+    def run(self):
+        """Enqueue one pass over the level; returns the band's cost volume (a view of `out_h`)."""
+        o, d, R, h = self.ops, self.d, self.R, self.h
+        cuda = self.side is not None
+        bufs = [self.nxt_h] + ([self.flow_h] if self.pair else [])
+        if cuda:
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                reqs = self._exchange(bufs)
+                for q in reqs:
+                    q.wait()                      # stream-level wait on the NCCL stream, no host block
+        else:
+            reqs = self._exchange(bufs)
+        if not self.pair:
+            # interior: band-only data is enough for rows [d, h-d) -- the call also writes rows [0,d) and
+            # [h-d,h) (computed against zero padding), which the strips below overwrite
+            o.cost_volume_into(self.out, self.prv, self.nxt, d)
+            if cuda:
+                torch.cuda.current_stream().wait_stream(self.side)
+            else:
+                for q in reqs:
+                    q.wait()
+            if self.world > 1:
+                for top in (True, False):
+                    if (top and self.up < 0) or (not top and self.down >= self.world):
+                        continue              # image border: zero padding is the right answer already
+                    a = 0 if top else h - d   # band rows [a, a+d) from the 3d rows around them
+                    o.cost_volume_into(self.strip, self.prv_h[:, a:a + 3 * d], self.nxt_h[:, a + R - d:a + R + 2 * d], d)
+                    self.out[:, a:a + d].copy_(self.strip[:, d:2 * d])
+            return self.out
+        # ---- UpFlow pair: warp rows [-d, h+d) of the band into nxtw_h, then one cost volume over it
+        k = self.reach + 1
+        lo, hi = (k if self.up >= 0 else 0), (h - k if self.down < self.world else h)
+        hi = max(hi, lo)
+        if hi > lo:   # interior rows: their taps stay inside the band (|flow_y| <= reach)
+            self._warp_rows(lo, hi)
+        if cuda:
+            torch.cuda.current_stream().wait_stream(self.side)
+        else:
+            for q in reqs:
+                q.wait()
+        top_lo = -d if self.up >= 0 else 0
+        bot_hi = h + d if self.down < self.world else h
+        if lo > top_lo:
+            self._warp_rows(top_lo, lo)
+        if bot_hi > hi:
+            self._warp_rows(hi, bot_hi)
+        o.cost_volume_into(self.out_h, self.prv_h, self.nxtw_h, d)
+        return self.out
+
+    def _warp_rows(self, a, b):
+        """Warped band rows [a, b) (band coordinates, may reach d rows into the halo) -> nxtw_h.  The
+        warp is run on the whole haloed view and only rows [a, b) are kept: it must see the same row
+        indexing for every strip, and the taps of row i reach `reach + 1` rows away."""
+        o, d, R, k = self.ops, self.d, self.R, self.reach + 1
+        s0, s1 = max(a + R - k, 0), min(b + R + k, self.h + 2 * R)          # source window in haloed coordinates
+        if self.up < 0:
+            s0 = max(s0, R)          # first rank: rows above the image do not exist (clamp / zero semantics of the warp)
+        if self.down >= self.world:
+            s1 = min(s1, R + self.h)
+        tmp = self.ops.warp(self.nxt_h[:, s0:s1], self.flow_h[:, s0:s1], self.mode)
+        self.nxtw_h[:, d + a:d + b].copy_(tmp[:, a + R - s0:b + R - s0])
