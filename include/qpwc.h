@@ -108,6 +108,14 @@ int qpwc_warp_bwd(const float* img, const float* flow, const float* g_out, float
  * slice; g_flow is the gradient with respect to the UNSCALED flow. */
 int qpwc_warp_fwd_ex(const float* img, const float* flow, float* out, int B, int H, int W, int C,
                      int mode, float flow_scale, long long out_pixel_stride, void* stream);
+/* Row-sharded frames (BASELINE config 5, qpwcnet_b200/sharded.py): `img`, `flow`, `out` are rows
+ * [row_offset, row_offset + H) of tensors `full_height` rows tall.  Sampling coordinates, truncation and
+ * border clamping use the absolute row index -- the reference adds the flow to the absolute pixel index
+ * in fp32 (warp.py:100-111), so the result is bit-identical to the same rows of the unsharded warp for
+ * every output row whose four taps lie inside the view (rows further than max|flow_y| + 1 from a cut). */
+int qpwc_warp_fwd_rows(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                       int mode, int row_offset, int full_height, void* stream);
+
 int qpwc_warp_pair_fwd(const float* img_a, const float* flow_a, const float* img_b,
                        const float* flow_b, float* out, int B, int H, int W, int C, int mode,
                        float flow_scale, long long out_pixel_stride, void* stream);

@@ -55,6 +55,7 @@ def lib() -> ctypes.CDLL:
         "qpwc_warp_fwd": ([fp, fp, fp, i, i, i, i, i, vp], c_int),
         "qpwc_warp_fwd_nchw": ([fp, fp, fp, i, i, i, i, i, f, vp], c_int),
         "qpwc_warp_bwd": ([fp, fp, fp, fp, fp, i, i, i, i, i, vp], c_int),
+        "qpwc_warp_fwd_rows": ([fp, fp, fp, i, i, i, i, i, i, i, vp], c_int),
         "qpwc_warp_fwd_ex": ([fp, fp, fp, i, i, i, i, i, f, ll, vp], c_int),
         "qpwc_warp_pair_fwd": ([fp, fp, fp, fp, fp, i, i, i, i, i, f, ll, vp], c_int),
         "qpwc_warp_bwd_ex": ([fp, fp, fp, fp, fp, i, i, i, i, i, f, ll, vp], c_int),
@@ -86,7 +87,7 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = (
     "qpwc_version", "qpwc_last_error", "qpwc_corr_fwd", "qpwc_corr_fwd_nchw", "qpwc_corr_bwd", "qpwc_warp_fwd",
-    "qpwc_warp_fwd_nchw", "qpwc_warp_bwd", "qpwc_warp_fwd_ex", "qpwc_warp_pair_fwd", "qpwc_warp_bwd_ex", "qpwc_upsample2x_fwd", "qpwc_upsample2x_bwd", "qpwc_occlusion_map", "qpwc_warp_bwd_nchw", "qpwc_corr_bwd_nchw",
+    "qpwc_warp_fwd_nchw", "qpwc_warp_bwd", "qpwc_warp_fwd_rows", "qpwc_warp_fwd_ex", "qpwc_warp_pair_fwd", "qpwc_warp_bwd_ex", "qpwc_upsample2x_fwd", "qpwc_upsample2x_bwd", "qpwc_occlusion_map", "qpwc_warp_bwd_nchw", "qpwc_corr_bwd_nchw",
     "qpwc_warp_fwd_up", "qpwc_warp_corr_fwd_up", "qpwc_warp_corr_fwd", "qpwc_warp_corr_bwd_workspace", "qpwc_warp_corr_bwd",
     "qpwc_corr_fwd_host", "qpwc_warp_fwd_host", "qpwc_warp_corr_fwd_host",
     "qpwc_host_set_deferred", "qpwc_host_sync", "qpwc_set_option", "qpwc_get_option",

@@ -2,6 +2,7 @@
 // argument validation, kernel selection, error plumbing, and the host-buffer (staged) variants.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -15,7 +16,7 @@ namespace qpwc {
 // kernels (qpwc_warp.cu, qpwc_corr_direct.cu, qpwc_corr_tiled.cu)
 int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
-int launch_warp_fwd_ex(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f);
+int launch_warp_fwd_ex(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f, int row_off = 0, int Hfull = 0);
 int launch_upsample2x_fwd(const float*, float*, int, int, int, int, float, cudaStream_t);
 int launch_warp_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_corr_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
@@ -119,6 +120,10 @@ static const size_t kL2ChunkBytes = (size_t)160 << 20;
 // Stream-ordered scratch: cudaMallocAsync from the device's default pool.  By default that pool hands
 // its memory back to the OS at every synchronisation (release threshold 0), which turns each call into
 // a driver allocation of ~100 MB; raise the threshold once per device so that the block is recycled.
+#ifdef QPWC_EMU
+static int scratch_alloc(float** p, size_t bytes, cudaStream_t, const char*) { *p = static_cast<float*>(malloc(bytes)); return QPWC_OK; }
+static cudaError_t scratch_free(float* p, cudaStream_t) { free(p); return cudaSuccess; }
+#else
 static int scratch_alloc(float** p, size_t bytes, cudaStream_t st, const char* fn) {
   static std::atomic<unsigned> pool_ready{0};
   int dev = 0;
@@ -135,6 +140,8 @@ static int scratch_alloc(float** p, size_t bytes, cudaStream_t st, const char* f
   if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "%s: scratch (%zu B): %s", fn, bytes, cudaGetErrorString(e));
   return QPWC_OK;
 }
+static cudaError_t scratch_free(float* p, cudaStream_t st) { return cudaFreeAsync(p, st); }
+#endif
 
 static int chunk_batch(int B, size_t per_item_bytes) {
   size_t n = per_item_bytes ? kL2ChunkBytes / per_item_bytes : (size_t)B;
@@ -162,7 +169,7 @@ static int warp_corr_fwd_l2(const float* prv, const float* nxt, const float* flo
     rc = launch_warp_fwd_ex(nxt + item * b0, flow + fitem * b0, nullptr, nullptr, scratch, nb, H, W, C, mode, 1.f, C, st, up_scale);
     if (rc == QPWC_OK) rc = launch_corr_fwd_tc(prv + item * b0, scratch, out + (size_t)H * W * ops * b0, nb, H, W, C, d, slope, ops, st);
   }
-  e = cudaFreeAsync(scratch, st);
+  e = scratch_free(scratch, st);
   if (rc == QPWC_OK && e != cudaSuccess) rc = set_error(QPWC_ERR_CUDA, "warp_corr_fwd: scratch free: %s", cudaGetErrorString(e));
   return rc;
 }
@@ -362,6 +369,19 @@ int qpwc_warp_fwd_ex(const float* img, const float* flow, float* out, int B, int
   QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
   if (reinterpret_cast<uintptr_t>(flow) % 8) return set_error(QPWC_ERR_INVALID, "%s: flow must be 8-byte aligned", fn);
   return launch_warp_fwd_ex(img, flow, nullptr, nullptr, out, B, H, W, C, mode, flow_scale, out_pixel_stride, (cudaStream_t)stream);
+}
+
+int qpwc_warp_fwd_rows(const float* img, const float* flow, float* out, int B, int H, int W, int C,
+                       int mode, int row_offset, int full_height, void* stream) {
+  const char* fn = "qpwc_warp_fwd_rows";
+  QPWC_TRY(check_shape(fn, B, H, W, C));
+  if (row_offset < 0 || full_height < row_offset + H)
+    return set_error(QPWC_ERR_INVALID, "%s: rows [%d, %d) are not inside an image of %d rows", fn, row_offset, row_offset + H, full_height);
+  if (empty(B, H, W, C)) return QPWC_OK;
+  QPWC_TRY(check_mode(fn, mode, full_height, W));
+  QPWC_TRY(check_ptr(fn, "img", img)); QPWC_TRY(check_ptr(fn, "flow", flow)); QPWC_TRY(check_ptr(fn, "out", out));
+  if (reinterpret_cast<uintptr_t>(flow) % 8) return set_error(QPWC_ERR_INVALID, "%s: flow must be 8-byte aligned", fn);
+  return launch_warp_fwd_ex(img, flow, nullptr, nullptr, out, B, H, W, C, mode, 1.f, C, (cudaStream_t)stream, 0.f, row_offset, full_height);
 }
 
 int qpwc_warp_pair_fwd(const float* img_a, const float* flow_a, const float* img_b, const float* flow_b,
@@ -567,7 +587,7 @@ int qpwc_warp_corr_bwd(const float* prv, const float* nxt, const float* flow, co
     if (rc == QPWC_OK) rc = corr_bwd_any(prv + o, nxt_w, out + oo, g_out + oo, g_prv + o, g_nxt_w, nb, H, W, C, search_range, leaky_slope, out_pixel_stride, st);
     if (rc == QPWC_OK) rc = launch_warp_bwd(nxt + o, flow + of, g_nxt_w, g_nxt + o, g_flow + of, nb, H, W, C, mode, st);
   }
-  e = cudaFreeAsync(scratch, st);
+  e = scratch_free(scratch, st);
   if (rc == QPWC_OK && e != cudaSuccess) rc = set_error(QPWC_ERR_CUDA, "%s: scratch free: %s", fn, cudaGetErrorString(e));
   return rc;
 }

@@ -72,7 +72,11 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ flow2,
                                                        float* __restrict__ out, int H, int W, int C,
                                                        int bsplit, float scale, long long ops,
-                                                       float up_scale) {
+                                                       float up_scale, int row_off, int Hfull) {
+  // row_off / Hfull (row-sharded frames, qpwcnet_b200/sharded.py): `img` is rows [row_off, row_off + H) of
+  // an image Hfull rows tall.  The sampling coordinate, truncation and clamping use the ABSOLUTE row --
+  // the reference adds the flow to the absolute pixel index in fp32, so its rounding depends on it --
+  // and the taps are translated back into the view (the caller keeps only rows whose taps lie inside).
   // up_scale != 0: `flow` is the COARSE flow (B, H/2, W/2, 2); the sampling flow is
   // up_scale * bilinear_x2(flow), interpolated here instead of being read back from HBM
   // (Upsample(scale=2.0) feeding UpFlow's warp, non_layers.py:183-193, pwcnet.py:49-56)
@@ -92,7 +96,12 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
   if (up_scale != 0.f) f = up2_flow(flow + (size_t)b * (H / 2) * (W / 2) * 2, i, j, H / 2, W / 2, up_scale);
   else f = __ldg(reinterpret_cast<const float2*>(flow) + pix);    // ch0 = x, ch1 = y
   f.x = __fmul_rn(scale, f.x); f.y = __fmul_rn(scale, f.y);       // exact for scale == 1
-  const Taps t = make_taps<MODE>(i, j, f.x, f.y, H, W);
+  Taps t = make_taps<MODE>(i + row_off, j, f.x, f.y, Hfull, W);
+  if (row_off != 0 || Hfull != H) {
+    const int lim = (H - 1) * W, sh = row_off * W;
+    t.o00 = min(max(t.o00 - sh, 0), lim + W - 1); t.o01 = min(max(t.o01 - sh, 0), lim + W - 1);
+    t.o10 = min(max(t.o10 - sh, 0), lim + W - 1); t.o11 = min(max(t.o11 - sh, 0), lim + W - 1);
+  }
   // vector n of lane cv is channel vector n*CV + cv: per load/store instruction the CV lanes of a
   // pixel cover CV*V contiguous floats (whole 32-byte sectors), not every other 16 bytes
   const float* base = img + (size_t)b * H * W * C + (size_t)cv * V;
@@ -362,30 +371,30 @@ static int pick_vec(int C, const void* a, const void* b, const void* c = nullptr
 template <int MODE, int V, int NV>
 static void run_warp_fwd_nv(const float* img, const float* flow, const float* img2, const float* flow2,
                             float* out, int B, int H, int W, int C, float scale, long long ops,
-                            float up_scale, cudaStream_t stream);
+                            float up_scale, cudaStream_t stream, int row_off, int Hfull);
 
 template <int MODE, int V>
 static void run_warp_fwd(const float* img, const float* flow, const float* img2, const float* flow2,
                          float* out, int B, int H, int W, int C, float scale, long long ops,
-                         float up_scale, cudaStream_t stream) {
+                         float up_scale, cudaStream_t stream, int row_off, int Hfull) {
   const int block = 256;
   if (V == 4 && C % 8 == 0) {  // two 16-byte vectors per thread
-    run_warp_fwd_nv<MODE, V, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
+    run_warp_fwd_nv<MODE, V, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
     return;
   }
-  run_warp_fwd_nv<MODE, V, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
+  run_warp_fwd_nv<MODE, V, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
 }
 
 template <int MODE, int V, int NV>
 static void run_warp_fwd_nv(const float* img, const float* flow, const float* img2, const float* flow2,
                             float* out, int B, int H, int W, int C, float scale, long long ops,
-                            float up_scale, cudaStream_t stream) {
+                            float up_scale, cudaStream_t stream, int row_off, int Hfull) {
   const int block = 256;
   const int CV = C / (V * NV);
   auto k = warp_fwd_kernel<MODE, V, NV>;
   if (img2) {  // pair: grid.z = 2B (B <= 32767 checked by the caller)
     const dim3 grid((unsigned)cdiv(W * CV, block / WARP_FWD_ROWS), (unsigned)cdiv(H, WARP_FWD_ROWS), (unsigned)(2 * B));
-    QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, img2, flow2, out, H, W, C, B, scale, ops, up_scale);
+    QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, img2, flow2, out, H, W, C, B, scale, ops, up_scale, row_off, Hfull);
     return;
   }
   // gridDim.y/z are limited to 65535: chunk the batch (and refuse absurd heights upstream)
@@ -395,34 +404,35 @@ static void run_warp_fwd_nv(const float* img, const float* flow, const float* im
     const size_t off = (size_t)b0 * H * W;
     const size_t foff = up_scale != 0.f ? (size_t)b0 * (H / 2) * (W / 2) * 2 : off * 2;
     QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + foff, img2, flow2, out + off * ops, H, W, C,
-                nb, scale, ops, up_scale);
+                nb, scale, ops, up_scale, row_off, Hfull);
   }
 }
 
 // img2/flow2 != nullptr: two warps in one launch, the second writing channels [C, 2C) of each pixel
 int launch_warp_fwd_ex(const float* img, const float* flow, const float* img2, const float* flow2,
                        float* out, int B, int H, int W, int C, int mode, float scale, long long ops,
-                       cudaStream_t stream, float up_scale) {
+                       cudaStream_t stream, float up_scale, int row_off, int Hfull) {
+  if (Hfull <= 0) Hfull = H;
   int V = pick_vec(C, img, out, img2);
   while (V > 1 && ops % V) V >>= 1;
   if ((long long)B * H * W * C == 0) return QPWC_OK;
   if (H > 65535 || (long long)W * (C / V) >= (1LL << 31)) return set_error(QPWC_ERR_UNSUPPORTED, "warp_fwd: H > 65535 or W*C too large");
   if (img2 && B > 32767) return set_error(QPWC_ERR_UNSUPPORTED, "warp_pair_fwd: B > 32767");
   if (mode == QPWC_MODE_TF) {
-    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
-    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
-    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
+    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
+    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
   } else {
-    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
-    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
-    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream);
+    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
+    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
   }
   return check_launch("warp_fwd");
 }
 
 int launch_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
                     int mode, cudaStream_t stream) {
-  return launch_warp_fwd_ex(img, flow, nullptr, nullptr, out, B, H, W, C, mode, 1.f, C, stream, 0.f);
+  return launch_warp_fwd_ex(img, flow, nullptr, nullptr, out, B, H, W, C, mode, 1.f, C, stream, 0.f, 0, 0);
 }
 
 template <int MODE, int V>

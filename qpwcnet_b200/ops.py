@@ -692,6 +692,28 @@ def warp_into(out, img, flow, mode="tfa"):
     return _warp_fwd(img, flow, _mode(mode), out=out)
 
 
+def warp_rows_into(out, img, flow, mode, row_offset: int, full_height: int):
+    """Inference-only warp of rows [row_offset, row_offset + H) of a `full_height`-row frame (row-sharded
+    frames): absolute-row arithmetic, bit-identical to the unsharded warp for rows whose taps lie inside
+    the view."""
+    img = _prep(img, "img")
+    flow = _prep(flow, "flow", last=2)
+    if out.shape != img.shape or out.dtype != torch.float32 or out.device != img.device or not out.is_contiguous():
+        raise ValueError("out must be a dense float32 tensor shaped like img on the same device")
+    if not img.is_cuda:
+        raise ValueError("warp_rows_into needs CUDA tensors")
+    m = _mode(mode)
+    if img.shape[:3] != flow.shape[:3] or img.device != flow.device:
+        raise ValueError(f"warp_rows_into: image {tuple(img.shape)} vs flow {tuple(flow.shape)}")
+    _no_grad_into("warp_rows_into", img, flow)
+    B, H, W, C = img.shape
+    vi, vf, vo = _views(img, flow, out)
+    with _on_device(img.device):
+        check(lib().qpwc_warp_fwd_rows(vi.ptr, vf.ptr, vo.ptr, B, H, W, C, m, int(row_offset), int(full_height),
+                                       _stream_ptr(img.device)))
+    return out
+
+
 def _check_out(out, prv):
     if out.dtype != torch.float32 or out.dim() != 4 or out.shape[:3] != prv.shape[:3] \
             or out.device != prv.device or not out.is_contiguous():

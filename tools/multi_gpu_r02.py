@@ -103,10 +103,12 @@ for (H, W, C) in [(68, 120, 256), (136, 240, 256), (272, 480, 128), (544, 960, 6
     out1 = torch.empty_like(ref_cv)
     row["one_gpu_cv_ms"] = timed(lambda: ops.cost_volume_into(out1, full_p, full_n, 4))
     row["one_gpu_pair_ms"] = timed(lambda: ops.warp_cost_volume_into(out1, full_p, full_n, full_f, "tfa", 4))
-    for pair in (False, True):
-        key = "pair" if pair else "cv"
+    for pair, symm in ((False, False), (True, False), (False, True), (True, True)):
+        key = ("pair" if pair else "cv") + ("_nvlink_push" if symm else "_nccl_p2p")
+        if symm and "--no-symm" in sys.argv:
+            continue
         try:
-            lv = sharded.ShardedLevel(H, W, C, 4, reach=reach, pair=pair, group=None)
+            lv = sharded.ShardedLevel(H, W, C, 4, reach=reach, pair=pair, group=None, symmetric=symm)
         except ValueError as e:
             row[key] = {"skipped": str(e)}
             continue
@@ -119,15 +121,23 @@ for (H, W, C) in [(68, 120, 256), (136, 240, 256), (272, 480, 128), (544, 960, 6
         err = float((out - ref).abs().max() / ref.abs().max())
         ident = bool(torch.equal(out, ref))
         t_all = timed(lv.run)
-        t_x = timed(lambda: [q.wait() for q in lv._exchange([lv.nxt_h] + ([lv.flow_h] if pair else []))])
+        t_graph, ident_g = None, None
+        if symm and "--graph" in sys.argv:
+            lv.capture()
+            ident_g = bool(minr(1.0 if torch.equal(lv.replay(), ref) else 0.0) == 1.0)
+            t_graph = timed(lv.replay)
+        if symm:
+            t_x = timed(lv._exchange_symmetric)
+        else:
+            t_x = timed(lambda: [q.wait() for q in lv._exchange([lv.nxt_h] + ([lv.flow_h] if pair else []))])
         # compute alone: the same kernel sequence with the neighbours switched off
         up, down = lv.up, lv.down
         lv.up, lv.down = -1, lv.world
         t_c = timed(lv.run)
         lv.up, lv.down = up, down
-        row[key] = {"sharded_ms": t_all, "exchange_alone_ms": t_x, "compute_alone_ms": t_c,
+        row[key] = {"sharded_ms": t_all, "cuda_graph_ms": t_graph, "cuda_graph_bit_identical": ident_g,  "exchange_alone_ms": t_x, "compute_alone_ms": t_c,
                     "rel_err_worst_rank": maxr(err), "bit_identical_on_every_rank": bool(minr(1.0 if ident else 0.0) == 1.0),
-                    "speedup_vs_one_gpu": row["one_gpu_pair_ms" if pair else "one_gpu_cv_ms"] / t_all}
+                    "speedup_vs_one_gpu": row["one_gpu_pair_ms" if pair else "one_gpu_cv_ms"] / (t_graph or t_all)}
     c5.append(row)
 res["config5_rowsharded_4k"] = c5
 if rank == 0:
