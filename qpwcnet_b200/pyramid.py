@@ -52,8 +52,9 @@ class PyramidWorkload:
     def __init__(self, height=436, width=1024, batch=8, search_range=4, device="cuda", seed=0,
                  flow_sigma=None, warp_mode="tfa", path="auto"):
         """path: how an UpFlow level (warp -> cost volume) is executed --
-        'fused'    one kernel, warped features stay in shared memory (least HBM traffic);
-        'composed' the stand-alone warp kernel followed by the cost-volume kernel;
+        'fused'    the library's fused entry point, one C-ABI call (tensor-core engine: warp kernel + cost-volume
+                   kernel through a scratch buffer owned by the call; FFMA engine: one kernel);
+        'composed' the warp call followed by the cost-volume call (scratch owned by the caller);
         'auto'     time both once per level on the device and keep the faster (device workloads)."""
         self.levels = levels_for(height, width)
         self.B, self.d, self.mode = batch, search_range, warp_mode
@@ -111,7 +112,8 @@ class PyramidWorkload:
         return ops.cost_volume_into(self.outputs[k], prv, nxt, self.d)
 
     def _autotune(self, reps=5):
-        """Per UpFlow level: median device time of the fused kernel vs warp + cost volume."""
+        """Per UpFlow level: median device time of the library's fused entry point (one C-ABI call) vs the
+        warp call followed by the cost-volume call."""
         self.autotune_ms = {}
         for k, lv in enumerate(self.levels):
             if not lv.fused:
@@ -135,7 +137,10 @@ class PyramidWorkload:
 
     @property
     def launches_per_step(self):
-        return sum(2 if p == "composed" else 1 for p in self.level_path)
+        # kernels per level: warp + cost volume for an UpFlow level (the library's fused entry point runs the
+        # same two kernels under the tensor-core engine; the FFMA engine's in-kernel fusion is one launch)
+        two = ops.get_corr_engine() != "ffma"
+        return sum(2 if (p == "composed" or (p == "fused" and two)) else 1 for p in self.level_path)
 
     def step(self):
         """One pass of the hot path over the batch: 1 cost volume + 4 fused warp->cost volumes

@@ -61,6 +61,8 @@ class TrainHotPath:
         self.comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self.allreduce = world > 1
         self.counts = {"cost_volume": 10, "warp": 18}
+        self.bucketing = "per_level"
+        self._graph = None
 
     # ---- algorithmic work of one step (forward + backward), SURVEY 8(d)
     def algorithmic_bytes(self):
@@ -78,9 +80,7 @@ class TrainHotPath:
     def allreduce_bytes(self):
         return 4 * sum(BUCKET_ELEMS)
 
-    def step(self):
-        """Forward + backward of the 10 cost volumes and 18 warps; gradient buckets are all-reduced on
-        the side stream level by level while the remaining backward calls run."""
+    def _forward(self):
         outs, grads = [], []
         for lv in self.flower:
             for k, (p, n, f, g) in enumerate(lv):
@@ -89,20 +89,68 @@ class TrainHotPath:
         for (pa, nb, f01, f10, g) in self.interp:
             outs.append(ops.half_flow_warps(pa, nb, f01, f10, self.mode))
             grads.append(g)
-        # backward, finest level first (the order autograd of the real network produces: the loss sits on
-        # the full-resolution outputs); after each level its gradient bucket goes to the comm stream
+        return outs, grads
+
+    def _backward_level(self, outs, grads, k):
         nl = len(LEVELS)
-        for j, k in enumerate(range(nl - 1, -1, -1)):
-            idx = [k, nl + k, 2 * nl + k]
-            torch.autograd.backward([outs[i] for i in idx], [grads[i] for i in idx])
+        idx = [k, nl + k, 2 * nl + k]
+        torch.autograd.backward([outs[i] for i in idx], [grads[i] for i in idx])
+
+    def _allreduce_bucket(self, j):
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            torch.distributed.all_reduce(self.buckets[j], group=self.pg)
+
+    def step(self):
+        """Forward + backward of the 10 cost volumes and 18 warps, finest level first in the backward pass
+        (the order autograd of the real network produces: the loss sits on the full-resolution outputs).
+        bucketing = 'per_level': the gradient bucket of a level goes to the comm stream as soon as that
+        level's backward calls are enqueued; 'single': one all-reduce of all buckets after the backward
+        pass (fewer host-side NCCL launches: better when the step is launch-bound, i.e. small per-GPU
+        batches).  With a captured graph (capture()) the compute is one cudaGraphLaunch."""
+        nl = len(LEVELS)
+        if self._graph is not None:
+            self._graph.replay()
             if self.allreduce:
-                self.comm.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(self.comm):
-                    torch.distributed.all_reduce(self.buckets[j], group=self.pg)
+                for j in range(nl):
+                    self._allreduce_bucket(j)
+        else:
+            outs, grads = self._forward()
+            for j, k in enumerate(range(nl - 1, -1, -1)):
+                self._backward_level(outs, grads, k)
+                if self.allreduce and self.bucketing == "per_level":
+                    self._allreduce_bucket(j)
+            if self.allreduce and self.bucketing == "single":
+                for j in range(nl):
+                    self._allreduce_bucket(j)
         if self.allreduce:
             torch.cuda.current_stream().wait_stream(self.comm)
 
+    def capture(self):
+        """Record forward + backward into one CUDA graph (gradients are produced into graph-owned
+        buffers; the NCCL all-reduces stay outside the graph and follow the replay)."""
+        self.zero_grad()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                outs, grads = self._forward()
+                for k in range(len(LEVELS) - 1, -1, -1):
+                    self._backward_level(outs, grads, k)
+                self.zero_grad()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs, grads = self._forward()
+            for k in range(len(LEVELS) - 1, -1, -1):
+                self._backward_level(outs, grads, k)
+        self._graph = g
+        return self
+
     def zero_grad(self):
+        if self._graph is not None:
+            return                     # graph-owned gradient buffers are overwritten by every replay
         for lv in self.flower:
             for (p, n, f, _) in lv:
                 for t in (p, n, f):
