@@ -38,6 +38,15 @@ namespace qpwc {
 
 #ifndef QPWC_EMU
 
+// dev instrumentation (tools/tc_trace.py): when set, CTA 0 of the resident kernel stamps clock64() at the
+// hand-over points of its first QPWC_TRACE_TILES tiles: g_tc_trace[tile * 24 + event]
+#define QPWC_TRACE_TILES 40
+__device__ long long* g_tc_trace = nullptr;
+__device__ __forceinline__ void tc_stamp(uint32_t tile, int ev) {
+  long long* t = g_tc_trace;
+  if (t != nullptr && blockIdx.x == 0 && tile < QPWC_TRACE_TILES) t[tile * 24 + ev] = clock64();
+}
+
 struct TcCfg {
   static constexpr int NDISP = 81;
   static constexpr int TH = 8, TW = 16, NROW = 16, NCOL = 24, NHALF = 192;
@@ -62,7 +71,7 @@ struct TcCfg {
   static constexpr int R_OFF_A = 0, R_OFF_B = 2 * RA_BYTES;                       // A: 32 KB, B: 144 KB
   static constexpr int R_OFF_STAGING = R_OFF_B + NBLK * 2 * RB_BYTES;
   static constexpr int R_OFF_BARS = R_OFF_STAGING + STAGING_BYTES;
-  static constexpr int R_SMEM_BYTES = R_OFF_BARS + 24 * 8 + 16;
+  static constexpr int R_SMEM_BYTES = R_OFF_BARS + 25 * 8 + 16;
   // ---- streaming kernel (any C % 8 == 0): stages of 16 channels, 64-byte rows; per stage both B half
   // tiles (raw + lo) and an A landing buffer
   static constexpr int S_PXB = 64, S_KC = 16, NST = 3;
@@ -70,7 +79,7 @@ struct TcCfg {
   static constexpr int S_OFF_A = NST * 2 * SB_BYTES;
   static constexpr int S_OFF_STAGING = S_OFF_A + NST * SA_BYTES;
   static constexpr int S_OFF_BARS = S_OFF_STAGING + STAGING_BYTES;
-  static constexpr int S_SMEM_BYTES = S_OFF_BARS + (3 * NST + 4) * 8 + 16;
+  static constexpr int S_SMEM_BYTES = S_OFF_BARS + (3 * NST + 5) * 8 + 16;
   static_assert(S_SMEM_BYTES <= 232448 && R_SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TM_A + 2 * 64 <= 512 && TM_A + NST * 32 <= 512, "TMEM columns");
 };
@@ -124,13 +133,15 @@ __device__ __forceinline__ void split_block(const unsigned char* src, unsigned c
 // steps of 8 channels: hi (the fp32 words) to columns col0 + 16*ks, lo to col0 + 16*ks + 8 of the
 // thread's TMEM lane.  `taddr` = TMEM address of (this warp's lane quadrant, col0).
 template <int PXB, int NKS>
-__device__ __forceinline__ void a_to_tmem(const unsigned char* landing, int m, uint32_t taddr, int nks) {
+__device__ __forceinline__ void a_to_tmem(const unsigned char* landing, int m, uint32_t taddr, int nks, float a_scale) {
 #pragma unroll
   for (int ks = 0; ks < NKS; ++ks) {
     if (ks >= nks) break;
     const float4 v0 = *reinterpret_cast<const float4*>(landing + swz<PXB>((uint32_t)(m * PXB + ks * 32)));
     const float4 v1 = *reinterpret_cast<const float4*>(landing + swz<PXB>((uint32_t)(m * PXB + ks * 32 + 16)));
-    const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    // a_scale = 1/C when C is a power of two (exact: the mean's division folded into the operand), else 1
+    const float x[8] = {v0.x * a_scale, v0.y * a_scale, v0.z * a_scale, v0.w * a_scale,
+                        v1.x * a_scale, v1.y * a_scale, v1.z * a_scale, v1.w * a_scale};
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { hi[e] = __float_as_uint(x[e]); lo[e] = __float_as_uint(tf32_lo(x[e])); }
@@ -155,7 +166,7 @@ __device__ __forceinline__ void a_to_tmem(const unsigned char* landing, int m, u
 // leaky-relu'd and stored as row (y - r) of the lane's 9x9 band in the NHWC staging image of the tile
 // (compact 81-float pixels: at most 2-way bank conflicts).  After a barrier the 8 staged rows leave
 // as TMA bulk stores (one contiguous 16 x 324-byte run each).
-__device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, uint64_t* tfull, uint64_t* tempty,
+__device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, uint64_t* tfull, uint64_t* tempty, uint64_t* sfree,
                                                  uint32_t tcount, int q, int part, int ew, int lane,
                                                  float* __restrict__ out, int b, int i0, int j0, int H, int W,
                                                  long long ops, float inv_c, float slope, int ablate) {
@@ -164,11 +175,13 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
   const int h = (rb + part) >= 2 ? 1 : 0;
   const int y0 = 4 * part;
   const bool c4 = c & 4, c2 = c & 2, c1 = c & 1;
+  const bool fast = inv_c == 1.f && slope >= 0.f && slope <= 1.f;
   // row (y - r) of the band of pixel (rb*4 + r, cb*8 + c) starts at lane_base[9*y]
   float* lane_base = staging + (rb * 4 + r) * Cfg::ROW_FLOATS + (cb * 8 + c) * Cfg::NDISP - 9 * r;
   const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((rb * 4 + y0) * Cfg::NCOL + cb * 8);
   mbar_wait_parked(&tfull[h], tcount & 1u);
   tc_fence_after();
+  if (ew == 0) tc_stamp(tcount, 10); else if (ew == 8) tc_stamp(tcount, 15);
   // all four rows of this warp's share into registers first: the accumulator half is released as soon
   // as the loads have landed, before the shifting and staging work
   uint32_t u[4][16];
@@ -180,10 +193,14 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(&tempty[h]);        // this half of the accumulator may be overwritten
+  if (ew == 0) tc_stamp(tcount, 11); else if (ew == 8) tc_stamp(tcount, 16);
   // the bulk stores of the previous tile must have finished reading the staging image (waited for
   // here, after the accumulator loads, so that the engine's reads overlap the wait for the MMAs)
-  if (ew < Cfg::TH && lane == 0) bulk_wait_read<0>();
-  named_bar_sync(1, Cfg::NEPI * 32);
+  // (one lane issues and tracks the stores; the others learn through `sfree`, so a warp that has its
+  // rows goes straight on to the shifting/staging work without waiting for the other half's loads)
+  if (ew == 0 && lane == 0) { bulk_wait_read<0>(); mbar_arrive(sfree); }
+  mbar_wait(sfree, tcount & 1u);
+  if (ew == 0) tc_stamp(tcount, 12);
   if (!(ablate & 1)) {
 #pragma unroll
     for (int yy = 0; yy < 4; ++yy) {
@@ -199,22 +216,30 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
       const int y = y0 + yy;
       if ((unsigned)(y - r) <= 8u) {
         float* sp = lane_base + 9 * y;
+        if (fast) {      // scale folded into A, 0 <= slope <= 1: leaky relu = max(v, slope * v)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) sp[k] = lrelu(v[k] * inv_c, slope);
+          for (int k = 0; k < 9; ++k) sp[k] = fmaxf(v[k], v[k] * slope);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) sp[k] = lrelu(v[k] * inv_c, slope);
+        }
       }
     }
   }
   fence_proxy_async();                           // staging stores -> bulk-store (async proxy) reads
+  if (ew == 0) tc_stamp(tcount, 13); else if (ew == 8) tc_stamp(tcount, 17);
   named_bar_sync(2, Cfg::NEPI * 32);             // all pixel blocks staged
+  if (ew == 0) tc_stamp(tcount, 14);
   if (ablate & 16) return;
   const int wv = min(Cfg::TW, W - j0);
   const bool bulk = ops == Cfg::NDISP && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (bulk) {
-    if (ew < Cfg::TH && lane == 0) {
-      const int i = i0 + ew;
-      if (i < H)
-        bulk_store(out + ((size_t)((size_t)b * H + i) * W + j0) * Cfg::NDISP, staging + ew * Cfg::ROW_FLOATS,
-                   (uint32_t)(wv * Cfg::NDISP * 4));
+    if (ew == 0 && lane == 0) {
+#pragma unroll
+      for (int row = 0; row < Cfg::TH; ++row)
+        if (i0 + row < H)
+          bulk_store(out + ((size_t)((size_t)b * H + i0 + row) * W + j0) * Cfg::NDISP, staging + row * Cfg::ROW_FLOATS,
+                     (uint32_t)(wv * Cfg::NDISP * 4));
       bulk_commit();
     }
   } else {
@@ -279,13 +304,14 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
   uint64_t* raw_full = bars;                      // count 1 (+tx)
   uint64_t* stage_free = raw_full + Cfg::NST;     // count 1 (commit)
   uint64_t* tfull = stage_free + Cfg::NST;        // [2] count 1 (commit)
-  uint64_t* lo_full = tfull + 2;                  // count 4
+  uint64_t* sfree = tfull + 2;                    // count 1: staging image read by the previous tile's bulk stores
+  uint64_t* lo_full = sfree + 1;                  // count 4
   uint64_t* tempty = lo_full + Cfg::NST;          // [2] count 6
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* staging = reinterpret_cast<float*>(smem + Cfg::S_OFF_STAGING);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nstages = (C + Cfg::S_KC - 1) / Cfg::S_KC;  // per tile; the last one may hold a single K step
-  const uint32_t tmem = tc_prologue(bars, 2 * Cfg::NST + 2, Cfg::NST, 2, tmem_slot, smem, tid, warp);
+  const uint32_t tmem = tc_prologue(bars, 2 * Cfg::NST + 3, Cfg::NST, 2, tmem_slot, smem, tid, warp);
 #define QPWC_SB(s) (smem + (s) * 2 * Cfg::SB_BYTES)
 #define QPWC_SA(s) (smem + Cfg::S_OFF_A + (s) * Cfg::SA_BYTES)
 
@@ -323,7 +349,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
         coords(n, c, i0, j0, b);
         {
           const int s = (int)(g % Cfg::NST);
-          mbar_wait(&stage_free[s], ((g / Cfg::NST) & 1u) ^ 1u);
+          mbar_wait_parked(&stage_free[s], ((g / Cfg::NST) & 1u) ^ 1u);
           prefetch(n + PF);
           if (ablate & 8) { mbar_arrive(&raw_full[s]); continue; }
           mbar_arrive_expect_tx(&raw_full[s], Cfg::SA_BYTES + Cfg::SB_BYTES);
@@ -364,6 +390,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
   } else if (warp < Cfg::W_EPI) {  // ------------------------------------------------- operand split
     setmaxnreg_dec<Cfg::REG_SPLIT>();
     const int st = tid - Cfg::W_SPLIT * 32, qd = warp & 3, m = qd * 32 + lane;
+    const float a_scale = (C & (C - 1)) == 0 ? 1.f / (float)C : 1.f;
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int c = 0; c < nstages; ++c, ++g) {
@@ -371,7 +398,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
         mbar_wait_parked(&raw_full[s], (g / Cfg::NST) & 1u);
         tc_fence_after();  // (the MMAs that read TMEM buffer s completed before the stage was reloaded)
         if (!(ablate & 2)) {
-          a_to_tmem<PXB, 2>(QPWC_SA(s), m, tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + s * 32), min(2, (C - c * Cfg::S_KC) / 8));
+          a_to_tmem<PXB, 2>(QPWC_SA(s), m, tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + s * 32), min(2, (C - c * Cfg::S_KC) / 8), a_scale);
           split_block(QPWC_SB(s), QPWC_SB(s) + Cfg::SB_BYTES, Cfg::SB_BYTES, st);
         }
         fence_proxy_async();  // generic-proxy stores -> tensor-core (async proxy) reads
@@ -383,11 +410,11 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
   } else {  // --------------------------------------------------------------------------- epilogue
     setmaxnreg_inc<Cfg::REG_EPI>();
     const int ew = warp - Cfg::W_EPI, q = warp & 3, part = ew >> 2;
-    const float inv_c = 1.f / (float)C;
+    const float inv_c = (C & (C - 1)) == 0 ? 1.f : 1.f / (float)C;  // power-of-two C: folded into the first-frame operand
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int tx = tile % tiles_x, rest = tile / tiles_x, ty = rest % tiles_y, b = rest / tiles_y;
-      tc_epilogue_tile(staging, tmem, tfull, tempty, tcount, q, part, ew, lane, out, b, ty * Cfg::TH, tx * Cfg::TW,
+      tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, tcount, q, part, ew, lane, out, b, ty * Cfg::TH, tx * Cfg::TW,
                        H, W, ops, inv_c, slope, ablate);
     }
   }
@@ -419,7 +446,8 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
   uint64_t* afree = bfull + 3;     // [2] count 1 (commit): TMEM A buffer a no longer read
   uint64_t* bfree = afree + 2;     // [3] count 1 (commit): B block p no longer read
   uint64_t* tfull = bfree + 3;     // [2] count 1 (commit)
-  uint64_t* arawfree = tfull + 2;  // [2] count 4: landing buffer a consumed by the split warps
+  uint64_t* sfree = tfull + 2;     // count 1: staging image read by the previous tile's bulk stores
+  uint64_t* arawfree = sfree + 1;  // [2] count 4: landing buffer a consumed by the split warps
   uint64_t* alo = arawfree + 2;    // [2] count 4: TMEM A buffer a written
   uint64_t* blo = alo + 2;         // [3] count 4: B block p split
   uint64_t* tempty = blo + 3;      // [2] count 6
@@ -427,7 +455,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
   float* staging = reinterpret_cast<float*>(smem + Cfg::R_OFF_STAGING);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nks = C / 8;           // K steps (<= 4); channels C..31 of the 128-byte rows are TMA zero fill
-  const uint32_t tmem = tc_prologue(bars, 12, 7, 2, tmem_slot, smem, tid, warp);
+  const uint32_t tmem = tc_prologue(bars, 13, 7, 2, tmem_slot, smem, tid, warp);
   // B block p: raw at R_OFF_B + p*2*RB_BYTES, lo RB_BYTES further
 #define QPWC_ABUF(a) (smem + Cfg::R_OFF_A + (a) * Cfg::RA_BYTES)
 #define QPWC_BBLK(p) (smem + Cfg::R_OFF_B + (p) * 2 * Cfg::RB_BYTES)
@@ -456,8 +484,9 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
       int top = 0, bot = 0;
       QPWC_FOR_UNITS
         const int a = (int)(T & 1u);
-        mbar_wait(&arawfree[a], QPWC_PAR(ua, a) ^ 1u);
+        mbar_wait_parked(&arawfree[a], QPWC_PAR(ua, a) ^ 1u);
         ua ^= 1u << a;
+        tc_stamp(T, 0);
         if (ablate & 8) mbar_arrive(&afull[a]);
         else {
           mbar_arrive_expect_tx(&afull[a], Cfg::RA_BYTES);
@@ -468,8 +497,9 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
         // tile of a segment loads its top
         for (int hb = (k == 0 ? 0 : 1); hb < 2; ++hb) {
           const int p = hb ? bot : top;
-          mbar_wait(&bfree[p], QPWC_PAR(ub, p) ^ 1u);
+          mbar_wait_parked(&bfree[p], QPWC_PAR(ub, p) ^ 1u);
           ub ^= 1u << p;
+          if (hb) tc_stamp(T, 1);
           if (ablate & 8) { mbar_arrive(&bfull[p]); continue; }
           mbar_arrive_expect_tx(&bfull[p], Cfg::RB_BYTES);
           tma_load_4d(QPWC_BBLK(p), &tmN, &bfull[p], 0, j0 - 4, i0 - 4 + hb * 8, b);
@@ -488,6 +518,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
         if (k == 0) { mbar_wait(&blo[top], QPWC_PAR(mb, top)); mb ^= 1u << top; }  // k > 0: waited for as `bot` of tile k-1
         mbar_wait(&tempty[0], (T & 1u) ^ 1u);
         tc_fence_after();
+        tc_stamp(T, 6);
         {
           const uint32_t b_raw = smem_u32(QPWC_BBLK(top)), b_lo = b_raw + Cfg::RB_BYTES;
           if (!(ablate & 4))
@@ -495,11 +526,13 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
               umma_x3_ts<PXB>(tmem, a_tm + ks * 16, b_raw + ks * 32, b_lo + ks * 32, ks > 0 ? 1u : 0u);
           umma_commit(&tfull[0]);
           umma_commit(&bfree[top]);  // the upper block is dead once these MMAs have read it
+          tc_stamp(T, 7);
         }
         mbar_wait(&blo[bot], QPWC_PAR(mb, bot));
         mb ^= 1u << bot;
         mbar_wait(&tempty[1], (T & 1u) ^ 1u);
         tc_fence_after();
+        tc_stamp(T, 8);
         {
           const uint32_t b_raw = smem_u32(QPWC_BBLK(bot)), b_lo = b_raw + Cfg::RB_BYTES;
           if (!(ablate & 4))
@@ -508,6 +541,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
           umma_commit(&tfull[1]);
           umma_commit(&afree[a]);
           if (k == nt - 1) umma_commit(&bfree[bot]);  // end of the segment: nobody inherits the lower block
+          tc_stamp(T, 9);
         }
       }}
     }
@@ -516,38 +550,43 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
     setmaxnreg_dec<Cfg::REG_SPLIT>();
     const int st = tid - Cfg::W_SPLIT * 32, qd = warp & 3;  // qd: the TMEM lane quadrant this warp may write
     const int m = qd * 32 + lane;                           // its pixel = row of A = TMEM lane
+    const float a_scale = (C & (C - 1)) == 0 ? 1.f / (float)C : 1.f;
     uint32_t T = 0, ring = 0, ja = 0, jf = 0, jb = 0;
     int top = 0, bot = 0;
     QPWC_FOR_UNITS
       const int a = (int)(T & 1u);
       mbar_wait_parked(&afull[a], QPWC_PAR(ja, a));
       ja ^= 1u << a;
+      if (warp == Cfg::W_SPLIT) tc_stamp(T, 2);
       mbar_wait_parked(&afree[a], QPWC_PAR(jf, a) ^ 1u);  // the MMAs of two tiles ago have finished reading TMEM buffer a
       jf ^= 1u << a;
       tc_fence_after();
       if (!(ablate & 2))
-        a_to_tmem<PXB, 4>(QPWC_ABUF(a), m, tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + a * 64), nks);
+        a_to_tmem<PXB, 4>(QPWC_ABUF(a), m, tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + a * 64), nks, a_scale);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&arawfree[a]); mbar_arrive(&alo[a]); }
+      if (warp == Cfg::W_SPLIT) tc_stamp(T, 3);
       for (int hb = (k == 0 ? 0 : 1); hb < 2; ++hb) {
         const int p = hb ? bot : top;
         mbar_wait_parked(&bfull[p], QPWC_PAR(jb, p));
         jb ^= 1u << p;
+        if (warp == Cfg::W_SPLIT && hb) tc_stamp(T, 4);
         if (!(ablate & 2)) split_block(QPWC_BBLK(p), QPWC_BBLK(p) + Cfg::RB_BYTES, Cfg::RB_BYTES, st);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&blo[p]);
+        if (warp == Cfg::W_SPLIT && hb) tc_stamp(T, 5);
       }
     }}
   } else {  // --------------------------------------------------------------------------- epilogue
     setmaxnreg_inc<Cfg::REG_EPI>();
     const int ew = warp - Cfg::W_EPI, q = warp & 3, part = ew >> 2;
-    const float inv_c = 1.f / (float)C;
+    const float inv_c = (C & (C - 1)) == 0 ? 1.f : 1.f / (float)C;  // power-of-two C: folded into the first-frame operand
     uint32_t T = 0, ring = 0;
     int top = 0, bot = 0;
     QPWC_FOR_UNITS
-      tc_epilogue_tile(staging, tmem, tfull, tempty, T, q, part, ew, lane, out, b, i0, j0, H, W, ops, inv_c, slope, ablate);
+      tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, T, q, part, ew, lane, out, b, i0, j0, H, W, ops, inv_c, slope, ablate);
     }}
     (void)top; (void)bot;
   }
@@ -559,6 +598,10 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
 }
 
 int sm_count_cached();
+
+extern "C" int qpwc_debug_tc_trace(long long* device_buffer) {   // dev tool, not part of include/qpwc.h
+  return cudaMemcpyToSymbol(g_tc_trace, &device_buffer, sizeof(device_buffer)) == cudaSuccess ? 0 : 3;
+}
 
 int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, int H, int W, int C, int d,
                        float slope, long long ops, cudaStream_t stream) {
