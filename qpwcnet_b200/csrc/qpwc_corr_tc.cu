@@ -259,6 +259,7 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
         if (e >= Cfg::NDISP) { e -= Cfg::NDISP; ++p; }
       }
     }
+    named_bar_sync(1, Cfg::NEPI * 32);           // every warp has read its share before the image is reused
   }
 }
 
