@@ -63,6 +63,10 @@ const char* qpwc_last_error(void);
 #define QPWC_ENGINE_AUTO 0
 #define QPWC_ENGINE_FFMA 1
 #define QPWC_ENGINE_TC 2
+/* QPWC_OPT_WARP_BWD: warp backward kernel -- 0 auto / 1: vector global atomics with coincident taps folded in
+ * registers (the faster one on B200); 2: per-tile pre-aggregation in shared memory before the global
+ * atomics (C % 32 == 0; measured 2.5x slower: shared-memory float atomics retire ~1 lane/clk/SM). */
+#define QPWC_OPT_WARP_BWD 1
 int qpwc_set_option(int key, int value);
 int qpwc_get_option(int key); /* -1 for an unknown key */
 

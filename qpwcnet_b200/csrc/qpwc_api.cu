@@ -80,6 +80,8 @@ static int check_mode(const char* fn, int mode, int H, int W) {
 // qpwc_set_option(QPWC_OPT_CORR_ENGINE, ...): 0 = auto (tensor cores where the shape allows), 1 = FFMA
 // kernels only (plain fp32 arithmetic), 2 = tensor cores (3xTF32 split) or fail
 static std::atomic<int> g_corr_engine{0};
+void set_warp_bwd_variant(int);   // qpwc_warp.cu
+int get_warp_bwd_variant();
 
 static int corr_fwd_any(const float* prv, const float* nxt, const float* flow, int mode, float* out,
                         int B, int H, int W, int C, int d, float slope, long long ops, cudaStream_t st,
@@ -296,9 +298,10 @@ extern "C" {
 int qpwc_version(void) { return 200; /* 0.2.0 */ }
 int qpwc_set_option(int key, int value) {
   if (key == QPWC_OPT_CORR_ENGINE && value >= 0 && value <= 2) { g_corr_engine.store(value); return QPWC_OK; }
+  if (key == QPWC_OPT_WARP_BWD && value >= 0 && value <= 2) { set_warp_bwd_variant(value); return QPWC_OK; }
   return set_error(QPWC_ERR_INVALID, "qpwc_set_option: unknown key %d or value %d", key, value);
 }
-int qpwc_get_option(int key) { return key == QPWC_OPT_CORR_ENGINE ? g_corr_engine.load() : -1; }
+int qpwc_get_option(int key) { return key == QPWC_OPT_CORR_ENGINE ? g_corr_engine.load() : (key == QPWC_OPT_WARP_BWD ? get_warp_bwd_variant() : -1); }
 int qpwc_host_set_deferred(int on) { g_host_deferred = on != 0; return QPWC_OK; }
 int qpwc_host_sync(int device) { return host_sync(device); }
 const char* qpwc_last_error(void) { return g_err; }

@@ -9,6 +9,8 @@
 // Backward: sub-warp groups of G lanes own one pixel at a time (G = pow2 >= C/V, <= 32); each lane
 //           scatter-adds its channel vector into the four taps (vector red.global.add) and the
 //           flow gradient is reduced across the group with xor-shuffles in a fixed order.
+#include <atomic>
+
 #include "qpwc_upsample.cuh"
 
 namespace qpwc {
@@ -357,6 +359,152 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__
     reinterpret_cast<float2*>(g_flow)[pix] = make_float2(px ? __fmul_rn(scale, gx) : 0.f, py ? __fmul_rn(scale, gy) : 0.f);
 }
 
+
+// ----------------------------------------------------------------- bwd, shared-memory pre-aggregation
+// Scatter-add with per-tile accumulation in shared memory before the global atomics (north_star:
+// "shared-memory pre-aggregation before global atomics").  A CTA owns a tile of TBH x TBW output pixels
+// and one chunk of 32 channels; the image gradient of the tile and a margin of TBM pixels around it is
+// accumulated with shared-memory atomics (flows of a few pixels land inside the window; anything further
+// goes straight to global memory), then the window is flushed with one vector `red.global.add.v4.f32`
+// per 16 bytes that received anything -- about (TBH+2M)(TBW+2M)/(4*TBH*TBW) of the direct kernel's
+// global atomics.  Per-element arithmetic is that of warp_bwd_kernel; the flow gradient is reduced over
+// the 8 lanes of a pixel in a fixed order and (C > 32) across channel chunks by atomics on a pre-zeroed
+// g_flow.
+// MEASURED (tools/ab_warp_bwd.py, B200, B=8): 400 us vs 158 us for the direct kernel at 224x512x32, 2.5-3x
+// slower at every level, smooth and noisy flows alike: shared-memory float atomics retire about one lane
+// per clock per SM (117 M lane-atomics / 148 SMs = 0.79 M clk = 400 us), while `red.global.add.v4.f32`
+// is executed 16 bytes at a time by the L2 slices.  Pre-aggregation in shared memory is therefore NOT
+// the default on this part; the kernel stays selectable (QPWC_OPT_WARP_BWD = 2) as the measured
+// alternative and is parity-tested.
+#ifndef QPWC_EMU   // (the CPU emulation build keeps the direct kernel)
+#define TBH 16
+#define TBW 32
+#define TBM 3
+#define TBCK 32
+#define TB_WH (TBH + 2 * TBM)
+#define TB_WW (TBW + 2 * TBM)
+template <int MODE>
+__global__ void __launch_bounds__(256) warp_bwd_tile_kernel(const float* __restrict__ img, const float* __restrict__ flow,
+                                                           const float* __restrict__ g_out, float* __restrict__ g_img,
+                                                           float* __restrict__ g_flow, int H, int W, int C, int nchunks,
+                                                           float scale, long long gops) {
+  extern __shared__ __align__(16) float acc[];   // [TB_WH][TB_WW][TBCK]
+  const int tid = threadIdx.x;
+  const int b = (int)blockIdx.z / nchunks, ck = (int)blockIdx.z - b * nchunks;
+  const int i0 = (int)blockIdx.y * TBH, j0 = (int)blockIdx.x * TBW;
+  const int wi0 = i0 - TBM, wj0 = j0 - TBM;                 // window origin (may be negative)
+  for (int e = tid; e < TB_WH * TB_WW * TBCK / 4; e += 256) reinterpret_cast<float4*>(acc)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int cq = tid & 7;                                    // channel quad inside the chunk
+  const size_t boff = (size_t)b * H * W * C;
+  const int c0 = ck * TBCK + cq * 4;
+  for (int pp = tid >> 3; pp < TBH * TBW; pp += 32) {
+    const int i = i0 + pp / TBW, j = j0 + pp % TBW;
+    const bool live = i < H && j < W;                        // the 8 lanes of a pixel agree
+    float gx = 0.f, gy = 0.f;
+    bool px = true, py = true;
+    size_t pix = 0;
+    if (live) {
+      pix = ((size_t)b * H + i) * W + j;
+      float2 f = __ldg(reinterpret_cast<const float2*>(flow) + pix);
+      f.x = __fmul_rn(scale, f.x); f.y = __fmul_rn(scale, f.y);
+      Taps t;
+      if (MODE == QPWC_MODE_TF) t = taps_tf(i, j, f.x, f.y, H, W);
+      else t = taps_tfa(i, j, f.x, f.y, H, W, &px, &py);
+      float ax1 = 0.f, ax0 = 0.f, ay1 = 0.f, ay0 = 0.f;
+      if (MODE == QPWC_MODE_TF) {
+        const float x = __fadd_rn((float)j, f.x), y = __fadd_rn((float)i, f.y);
+        const int y0 = t.o00 / W, x0 = t.o00 - y0 * W, y1 = t.o11 / W, x1 = t.o11 - y1 * W;
+        ax1 = __fsub_rn((float)x1, x); ax0 = __fsub_rn(x, (float)x0);
+        ay1 = __fsub_rn((float)y1, y); ay0 = __fsub_rn(y, (float)y0);
+      }
+      const bool dupx = (MODE == QPWC_MODE_TF) && (t.o00 == t.o01);
+      const bool dupy = (MODE == QPWC_MODE_TF) && (t.o00 == t.o10);
+      float v00[4], v01[4], v10[4], v11[4], g[4], a00[4], a01[4], a10[4], a11[4];
+      vload<4>(img + boff + (size_t)t.o00 * C + c0, v00);
+      vload<4>(img + boff + (size_t)t.o01 * C + c0, v01);
+      vload<4>(img + boff + (size_t)t.o10 * C + c0, v10);
+      vload<4>(img + boff + (size_t)t.o11 * C + c0, v11);
+      vload<4>(g_out + pix * (size_t)gops + c0, g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (MODE == QPWC_MODE_TF) {
+          a00[k] = __fmul_rn(t.w00, g[k]); a10[k] = __fmul_rn(t.w10, g[k]);
+          a01[k] = __fmul_rn(t.w01, g[k]); a11[k] = __fmul_rn(t.w11, g[k]);
+          const float sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-ay1, v00[k]), __fmul_rn(-ay0, v10[k])),
+                                               __fmul_rn(ay1, v01[k])), __fmul_rn(ay0, v11[k]));
+          const float sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-ax1, v00[k]), __fmul_rn(ax1, v10[k])),
+                                               __fmul_rn(-ax0, v01[k])), __fmul_rn(ax0, v11[k]));
+          gx = __fadd_rn(gx, __fmul_rn(g[k], sx));
+          gy = __fadd_rn(gy, __fmul_rn(g[k], sy));
+        } else {
+          const float ax = t.w00, ay = t.w01;
+          const float top = __fadd_rn(__fmul_rn(ax, __fsub_rn(v01[k], v00[k])), v00[k]);
+          const float bot = __fadd_rn(__fmul_rn(ax, __fsub_rn(v11[k], v10[k])), v10[k]);
+          gy = __fadd_rn(gy, __fmul_rn(g[k], __fsub_rn(bot, top)));
+          const float g_bot = __fmul_rn(ay, g[k]);
+          const float g_top = __fsub_rn(g[k], g_bot);
+          gx = __fadd_rn(gx, __fadd_rn(__fmul_rn(g_top, __fsub_rn(v01[k], v00[k])),
+                                       __fmul_rn(g_bot, __fsub_rn(v11[k], v10[k]))));
+          const float g_tr = __fmul_rn(ax, g_top), g_br = __fmul_rn(ax, g_bot);
+          a01[k] = g_tr; a00[k] = __fsub_rn(g_top, g_tr); a11[k] = g_br; a10[k] = __fsub_rn(g_bot, g_br);
+        }
+      }
+      if (dupx) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a00[k] = __fadd_rn(a00[k], a01[k]); a10[k] = __fadd_rn(a10[k], a11[k]); }
+      }
+      if (dupy) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a00[k] = __fadd_rn(a00[k], a10[k]); a01[k] = __fadd_rn(a01[k], a11[k]); }
+      }
+      // scatter: into the shared window when the tap lies inside it, else straight to global memory
+      auto scatter = [&](int o, const float (&a)[4]) {
+        const int ty = o / W, tx = o - ty * W, wy = ty - wi0, wx = tx - wj0;
+        if ((unsigned)wy < (unsigned)TB_WH && (unsigned)wx < (unsigned)TB_WW) {
+          float* d = acc + ((wy * TB_WW + wx) * TBCK + cq * 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) atomicAdd(d + k, a[k]);
+        } else {
+          vatomic_add<4>(g_img + boff + (size_t)o * C + c0, a);
+        }
+      };
+      scatter(t.o00, a00);
+      if (!dupx) scatter(t.o01, a01);
+      if (!dupy) scatter(t.o10, a10);
+      if (!dupx && !dupy) scatter(t.o11, a11);
+    }
+    // flow gradient: fixed-order butterfly over the 8 lanes of the pixel (lanes 8k..8k+7 of a warp)
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      gx += __shfl_xor_sync(0xffffffffu, gx, o);
+      gy += __shfl_xor_sync(0xffffffffu, gy, o);
+    }
+    if (live && cq == 0) {
+      const float fx = px ? __fmul_rn(scale, gx) : 0.f, fy = py ? __fmul_rn(scale, gy) : 0.f;
+      if (nchunks == 1) reinterpret_cast<float2*>(g_flow)[pix] = make_float2(fx, fy);
+      else { atomicAdd(g_flow + 2 * pix, fx); atomicAdd(g_flow + 2 * pix + 1, fy); }
+    }
+  }
+  __syncthreads();
+  // flush the window: one vector atomic per 16 bytes that received anything
+  for (int e = tid; e < TB_WH * TB_WW * TBCK / 4; e += 256) {
+    const int q4 = e & 7, cell = e >> 3, wy = cell / TB_WW, wx = cell - wy * TB_WW;
+    const int ty = wi0 + wy, tx = wj0 + wx;
+    if (ty < 0 || ty >= H || tx < 0 || tx >= W) continue;
+    const float4 v = reinterpret_cast<const float4*>(acc)[e];
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+    const float a[4] = {v.x, v.y, v.z, v.w};
+    vatomic_add<4>(g_img + boff + ((size_t)ty * W + tx) * C + ck * TBCK + q4 * 4, a);
+  }
+}
+
+#endif  // !QPWC_EMU
+
+static std::atomic<int> g_warp_bwd_variant{0};   // 0 auto (= direct), 1 direct (register-folded global atomics), 2 shared-memory tiles
+void set_warp_bwd_variant(int v) { g_warp_bwd_variant.store(v); }
+int get_warp_bwd_variant() { return g_warp_bwd_variant.load(); }
+
 // ------------------------------------------------------------------------------------ launchers
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -464,6 +612,29 @@ int launch_warp_bwd_ex(const float* img, const float* flow, const float* g_out, 
   int V = pick_vec(C, img, g_out, g_img);
   while (V > 1 && gops % V) V >>= 1;
   if (H > 65535) return set_error(QPWC_ERR_UNSUPPORTED, "warp_bwd: H > 65535");
+#ifndef QPWC_EMU
+  const int variant = g_warp_bwd_variant.load(std::memory_order_relaxed);
+  if (variant == 2 && V == 4 && C % TBCK == 0 && (long long)B * (C / TBCK) <= 65535 && cdiv(H, TBH) <= 65535) {
+    const int nchunks = C / TBCK;
+    if (nchunks > 1) {
+      e = cudaMemsetAsync(g_flow, 0, sizeof(float) * 2 * (size_t)npix, stream);
+      if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "warp_bwd: memset g_flow: %s", cudaGetErrorString(e));
+    }
+    const int smem = TB_WH * TB_WW * TBCK * 4;
+    static std::atomic<unsigned> attr_done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_done.load(std::memory_order_acquire) >> (dev & 31) & 1u)) {
+      cudaFuncSetAttribute(warp_bwd_tile_kernel<QPWC_MODE_TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(warp_bwd_tile_kernel<QPWC_MODE_TFA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr_done.fetch_or(1u << (dev & 31), std::memory_order_release);
+    }
+    const dim3 grid((unsigned)cdiv(W, TBW), (unsigned)cdiv(H, TBH), (unsigned)(B * nchunks));
+    if (mode == QPWC_MODE_TF) warp_bwd_tile_kernel<QPWC_MODE_TF><<<grid, 256, smem, stream>>>(img, flow, g_out, g_img, g_flow, H, W, C, nchunks, scale, gops);
+    else warp_bwd_tile_kernel<QPWC_MODE_TFA><<<grid, 256, smem, stream>>>(img, flow, g_out, g_img, g_flow, H, W, C, nchunks, scale, gops);
+    return check_launch("warp_bwd_tile");
+  }
+#endif
   if (mode == QPWC_MODE_TF) {
     if (V == 4) run_warp_bwd<QPWC_MODE_TF, 4>(img, flow, g_out, g_img, g_flow, B, H, W, C, scale, gops, stream);
     else if (V == 2) run_warp_bwd<QPWC_MODE_TF, 2>(img, flow, g_out, g_img, g_flow, B, H, W, C, scale, gops, stream);

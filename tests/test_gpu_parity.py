@@ -775,3 +775,25 @@ def test_two_threads_two_streams():
         assert_rel(first[0], oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), 4))
         np.testing.assert_array_equal(first[1], oracle.warp(nxt, flo, "tfa"))
         assert_rel(first[2], oracle.warp_cost_volume(*(a.astype(np.float64) for a in (prv, nxt, flo)), "tfa", 4))
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+@pytest.mark.parametrize("B,H,W,C,sigma", [(2, 40, 70, 32, 2.0), (1, 33, 47, 64, 6.0), (1, 17, 32, 256, 1.0)])
+def test_warp_backward_shared_memory_preaggregation(mode, B, H, W, C, sigma):
+    """QPWC_OPT_WARP_BWD = 2: the tile kernel that accumulates in shared memory before the global
+    atomics (kept as the measured alternative) against the oracle and the default kernel."""
+    from qpwcnet_b200 import _cabi
+    r = rng(900 + C)
+    img = r.random((B, H, W, C)).astype(np.float32)
+    flo = (r.standard_normal((B, H, W, 2)) * sigma).astype(np.float32)
+    g = r.standard_normal((B, H, W, C)).astype(np.float32)
+    gi64, gf64 = oracle.warp_bwd(img.astype(np.float64), flo.astype(np.float64), g.astype(np.float64), mode)
+    gi32, gf32 = oracle.warp_bwd(img, flo, g, mode)
+    L = _cabi.lib()
+    try:
+        assert L.qpwc_set_option(1, 2) == 0
+        gi, gf = ops._warp_bwd(dev(img), dev(flo), dev(g), 0 if mode == "tf" else 1)
+    finally:
+        L.qpwc_set_option(1, 0)
+    assert_as_accurate(host(gi), gi32, gi64)
+    assert_as_accurate(host(gf), gf32, gf64, floor=1e-6 * max(1.0, C / 8))
