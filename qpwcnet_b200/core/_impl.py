@@ -52,10 +52,17 @@ def warp_cost_volume(inputs, mode, search_range, fmt, leaky_slope=0.1):
 
 def half_flow_warps(inputs, mode, fmt, flow_scale=0.5):
     prv, nxt, flo_01, flo_10 = inputs
+    if fmt == "channels_first" and prv.is_cuda and prv.dim() == 4:
+        # native NCHW warps with the flow scale fused; the concat along C is a plane-wise copy, no transposes
+        return torch.cat([ops.warp_nchw(prv, flo_10, mode, flow_scale), ops.warp_nchw(nxt, flo_01, mode, flow_scale)], dim=1)
     out = ops.half_flow_warps(to_nhwc(prv, fmt), to_nhwc(nxt, fmt), to_nhwc(flo_01, fmt),
                               to_nhwc(flo_10, fmt), mode, flow_scale)
     return from_nhwc(out, fmt)
 
 
 def upsample(x, scale, fmt):
+    if fmt == "channels_first" and x.dim() == 4:
+        # every (batch, channel) plane is a one-channel NHWC image: same kernel, same arithmetic, no transposes
+        B, C, H, W = x.shape
+        return ops.upsample2x(x.contiguous().view(B * C, H, W, 1), scale).view(B, C, 2 * H, 2 * W)
     return from_nhwc(ops.upsample2x(to_nhwc(x, fmt), scale), fmt)

@@ -282,15 +282,15 @@ class _WarpNCHW(torch.autograd.Function):
     """channels_first warp: native NCHW forward and backward kernels."""
 
     @staticmethod
-    def forward(ctx, img, flow, mode):
+    def forward(ctx, img, flow, mode, scale=1.0):
         B, C, H, W = img.shape
         out = torch.empty_like(img)
         vi, vf = _views(img, flow)
         with _on_device(img.device):
-            check(lib().qpwc_warp_fwd_nchw(vi.ptr, vf.ptr, out.data_ptr(), B, C, H, W, mode, 1.0,
+            check(lib().qpwc_warp_fwd_nchw(vi.ptr, vf.ptr, out.data_ptr(), B, C, H, W, mode, float(scale),
                                            _stream_ptr(img.device)))
         ctx.save_for_backward(img, flow)
-        ctx.mode = mode
+        ctx.mode, ctx.scale = mode, float(scale)
         return out
 
     @staticmethod
@@ -301,8 +301,8 @@ class _WarpNCHW(torch.autograd.Function):
         g_img, g_flow = torch.empty_like(img), torch.empty_like(flow)
         with _on_device(img.device):
             check(lib().qpwc_warp_bwd_nchw(img.data_ptr(), flow.data_ptr(), g_out.data_ptr(), g_img.data_ptr(),
-                                           g_flow.data_ptr(), B, C, H, W, ctx.mode, 1.0, _stream_ptr(img.device)))
-        return g_img, g_flow, None
+                                           g_flow.data_ptr(), B, C, H, W, ctx.mode, ctx.scale, _stream_ptr(img.device)))
+        return g_img, g_flow, None, None
 
 
 class _Warp(torch.autograd.Function):
@@ -489,9 +489,9 @@ def cost_volume_nchw(prv, nxt, search_range: int = 4, leaky_slope: float = 0.1):
     return _CostVolumeNCHW.apply(prv.contiguous(), nxt.contiguous(), int(search_range), float(leaky_slope))
 
 
-def warp_nchw(img, flow, mode="tfa"):
+def warp_nchw(img, flow, mode="tfa", flow_scale: float = 1.0):
     """``warp`` for channels_first tensors: img (B,C,H,W), flow (B,2,H,W) (plane 0 = x) -> (B,C,H,W),
-    through the native NCHW kernel."""
+    through the native NCHW kernel; ``flow_scale`` fuses FrameInterpolate's ``0.5 * flo``."""
     if img.dim() != 4 or flow.dim() != 4 or flow.shape[1] != 2 or img.shape[0] != flow.shape[0] \
             or img.shape[2:] != flow.shape[2:] or img.device != flow.device:
         raise ValueError(f"warp_nchw: img {tuple(img.shape)}@{img.device} vs flow {tuple(flow.shape)}@{flow.device}")
@@ -502,7 +502,7 @@ def warp_nchw(img, flow, mode="tfa"):
     m = _mode(mode)
     if m == 1 and (img.shape[2] < 2 or img.shape[3] < 2):
         raise ValueError("Grid must be at least 2x2 (tfa interpolate_bilinear)")
-    return _WarpNCHW.apply(img.contiguous(), flow.contiguous(), m)
+    return _WarpNCHW.apply(img.contiguous(), flow.contiguous(), m, float(flow_scale))
 
 
 def warp(img, flow, mode="tfa", flow_scale: float = 1.0):

@@ -797,3 +797,36 @@ def test_warp_backward_shared_memory_preaggregation(mode, B, H, W, C, sigma):
         L.qpwc_set_option(1, 0)
     assert_as_accurate(host(gi), gi32, gi64)
     assert_as_accurate(host(gf), gf32, gf64, floor=1e-6 * max(1.0, C / 8))
+
+
+@pytest.mark.parametrize("mode", ["tf", "tfa"])
+def test_channels_first_half_flow_warps_and_upsample_are_native(mode, monkeypatch):
+    """FrameInterpolate's pair and Upsample under channels_first (the reference's training layout,
+    pre_train.py:34): bit-identical to the channels_last layers, gradients included, and no
+    permute().contiguous() on the way (torch.Tensor.permute is made to fail during the calls)."""
+    from qpwcnet_b200.core import non_layers
+    r = rng(77)
+    B, C, H, W = 2, 8, 12, 20
+    prv, nxt = r.random((B, H, W, C)).astype(np.float32), r.random((B, H, W, C)).astype(np.float32)
+    f01, f10 = (r.standard_normal((B, H, W, 2)) * 3).astype(np.float32), (r.standard_normal((B, H, W, 2)) * 3).astype(np.float32)
+    g = r.standard_normal((B, H, W, 2 * C)).astype(np.float32)
+    nhwc = [dev(a).requires_grad_() for a in (prv, nxt, f01, f10)]
+    nchw = [dev(a).permute(0, 3, 1, 2).contiguous().requires_grad_() for a in (prv, nxt, f01, f10)]
+    ref = non_layers.HalfFlowWarps(warp_mode=mode, data_format="channels_last")(tuple(nhwc))
+    gref = torch.autograd.grad(ref, nhwc, dev(g))
+    g_cf = dev(g).permute(0, 3, 1, 2).contiguous()
+    fc = dev(r.standard_normal((B, H // 2, W // 2, 2)).astype(np.float32))
+    up_ref = non_layers.Upsample(scale=2.0, data_format="channels_last")(fc)
+    fc_cf = fc.permute(0, 3, 1, 2).contiguous()
+
+    def boom(*a, **k):
+        raise AssertionError("permute() reached under channels_first")
+    monkeypatch.setattr(torch.Tensor, "permute", boom)
+    out = non_layers.HalfFlowWarps(warp_mode=mode, data_format="channels_first")(tuple(nchw))
+    gout = torch.autograd.grad(out, nchw, g_cf)
+    up = non_layers.Upsample(scale=2.0, data_format="channels_first")(fc_cf)
+    monkeypatch.undo()
+    np.testing.assert_array_equal(host(out).transpose(0, 2, 3, 1), host(ref))
+    np.testing.assert_array_equal(host(up).transpose(0, 2, 3, 1), host(up_ref))
+    for a, b in zip(gout, gref):
+        np.testing.assert_allclose(host(a).transpose(0, 2, 3, 1), host(b), rtol=0, atol=2e-5)
