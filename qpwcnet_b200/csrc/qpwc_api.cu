@@ -83,14 +83,24 @@ static std::atomic<int> g_corr_engine{0};
 void set_warp_bwd_variant(int);   // qpwc_warp.cu
 int get_warp_bwd_variant();
 
+// Engine policy.  AUTO takes the tensor-core kernels for search range 4 only: range 8 runs there as four
+// 9x9 windows whose results leave through a strided scalar copy (36-byte runs at a 1156-byte pixel pitch admit
+// neither bulk stores nor a tensor-map store: the 68-byte displacement-row pitch is not a multiple of 16),
+// measured 1192 vs 978 us at 8x218x512x16 (profiles/r02_tc_d8.txt).  Forcing the engine still selects them.
+#ifdef QPWC_EMU
+static bool tc_wanted(int, int) { return false; }   // the emulation harness has no tensor-core stand-in
+#else
+static bool tc_wanted(int engine, int d) { return engine == 2 || (engine == 0 && d == 4); }
+#endif
+
 static int corr_fwd_any(const float* prv, const float* nxt, const float* flow, int mode, float* out,
                         int B, int H, int W, int C, int d, float slope, long long ops, cudaStream_t st,
                         float up_scale = 0.f) {
   const int engine = g_corr_engine.load(std::memory_order_relaxed);
-  if (!flow && engine != 1) {
+  if (!flow && tc_wanted(engine, d)) {
     const int rt = launch_corr_fwd_tc(prv, nxt, out, B, H, W, C, d, slope, ops, st);
     if (rt != QPWC_ERR_UNSUPPORTED) return rt;
-    if (engine == 2) return set_error(QPWC_ERR_UNSUPPORTED, "corr_fwd: tensor-core engine needs search_range 4, C %% 8 == 0 and 16-byte aligned inputs");
+    if (engine == 2) return set_error(QPWC_ERR_UNSUPPORTED, "corr_fwd: tensor-core engine needs search_range 4 or 8, C %% 8 == 0 and 16-byte aligned inputs");
   }
   const int rc = launch_corr_fwd_tiled(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);
   if (rc != QPWC_ERR_UNSUPPORTED) return rc;
@@ -155,7 +165,7 @@ static int chunk_batch(int B, size_t per_item_bytes) {
 }
 
 static bool tc_domain(const float* prv, const float* nxt, int C, int d) {
-  return d == 4 && C >= 8 && (C & 7) == 0 && !(reinterpret_cast<uintptr_t>(prv) & 15) && !(reinterpret_cast<uintptr_t>(nxt) & 15);
+  return (d == 4 || d == 8) && C >= 8 && (C & 7) == 0 && !(reinterpret_cast<uintptr_t>(prv) & 15) && !(reinterpret_cast<uintptr_t>(nxt) & 15);
 }
 
 static int warp_corr_fwd_l2(const float* prv, const float* nxt, const float* flow, int mode, float* out, int B,
@@ -179,8 +189,8 @@ static int warp_corr_fwd_l2(const float* prv, const float* nxt, const float* flo
 static int warp_corr_fwd_any(const float* prv, const float* nxt, const float* flow, int mode, float* out, int B,
                              int H, int W, int C, int d, float slope, long long ops, cudaStream_t st, float up_scale = 0.f) {
   const int engine = g_corr_engine.load(std::memory_order_relaxed);
-  if (engine != 1 && tc_domain(prv, nxt, C, d)) return warp_corr_fwd_l2(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);
-  if (engine == 2) return set_error(QPWC_ERR_UNSUPPORTED, "warp_corr_fwd: tensor-core engine needs search_range 4, C %% 8 == 0 and 16-byte aligned inputs");
+  if (tc_wanted(engine, d) && tc_domain(prv, nxt, C, d)) return warp_corr_fwd_l2(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);
+  if (engine == 2) return set_error(QPWC_ERR_UNSUPPORTED, "warp_corr_fwd: tensor-core engine needs search_range 4 or 8, C %% 8 == 0 and 16-byte aligned inputs");
   return corr_fwd_any(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);  // in-kernel fusion (FFMA)
 }
 
@@ -236,7 +246,7 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
   HostStage& hs = g_stage[device];
   std::lock_guard<std::mutex> lock(hs.mu);
   int rc = QPWC_OK, slot = hs.next_slot;
-  const bool l2pair = kind == 2 && g_corr_engine.load(std::memory_order_relaxed) != 1 && d == 4 && C >= 8 && (C & 7) == 0;
+  const bool l2pair = kind == 2 && tc_wanted(g_corr_engine.load(std::memory_order_relaxed), d) && (d == 4 || d == 8) && C >= 8 && (C & 7) == 0;
   const size_t n_w = l2pair ? n_a : 0;  // warped second frame of a slice (tensor-core engine: warp + cost volume)
   const size_t slot_floats = pad4(n_a * per) + pad4(n_b * per) + pad4(n_f * per) + pad4(n_o * per) + pad4(n_w * per);
   for (int b0 = 0; b0 < B && rc == QPWC_OK; b0 += per, slot = (slot + 1) % HostStage::NSLOT) {

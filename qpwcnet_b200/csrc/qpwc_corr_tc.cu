@@ -103,12 +103,15 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(kIdesc), "r"(acc) : "memory");
 }
-// the three passes of the split product for one K step and one half of N: hi.hi + lo.hi + hi.lo
-template <int PXB>
-__device__ __forceinline__ void umma_x3_ts(uint32_t d, uint32_t a_tm, uint32_t b_raw, uint32_t b_lo, uint32_t acc) {
-  umma_tf32_ts(d, a_tm, umma_desc<PXB>(b_raw), acc);
-  umma_tf32_ts(d, a_tm + 8, umma_desc<PXB>(b_raw), 1u);
-  umma_tf32_ts(d, a_tm, umma_desc<PXB>(b_lo), 1u);
+// the three passes of the split product for one K step and one half of N: hi.hi + lo.hi + hi.lo.
+// `d_raw` / `d_lo` are the shared-memory descriptors of the raw / lo B operand; the issuing thread's own
+// instruction stream is on the critical path (tools/ubench/tf32x3_tile.cu: 96 clk per MMA with
+// descriptors prepared, ~130 with the address arithmetic in the loop), so descriptors are built once
+// per block and advanced by adding to the start-address field (16-byte units, no carry: < 2^14).
+__device__ __forceinline__ void umma_x3_ts(uint32_t d, uint32_t a_tm, uint64_t d_raw, uint64_t d_lo, uint32_t acc) {
+  umma_tf32_ts(d, a_tm, d_raw, acc);
+  umma_tf32_ts(d, a_tm + 8, d_raw, 1u);
+  umma_tf32_ts(d, a_tm, d_lo, 1u);
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -169,7 +172,10 @@ __device__ __forceinline__ void a_to_tmem(const unsigned char* landing, int m, u
 __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, uint64_t* tfull, uint64_t* tempty, uint64_t* sfree,
                                                  uint32_t tcount, int q, int part, int ew, int lane,
                                                  float* __restrict__ out, int b, int i0, int j0, int H, int W,
-                                                 long long ops, float inv_c, float slope, int ablate) {
+                                                 long long ops, float inv_c, float slope, int ablate, int chb, int qo) {
+  // chb / qo: first output channel and channel pitch of a displacement row.  d = 4: (0, 9), the 81
+  // results of a pixel are contiguous.  d = 8 runs as four 9x9 windows of the 17x17 range: qo = 17,
+  // chb = (oi + 4) * 17 + (oj + 4) for the window offset (oi, oj) in {-4, +4}^2.
   using Cfg = TcCfg;
   const int rb = q & 1, cb = q >> 1, r = lane >> 3, c = lane & 7;
   const int h = (rb + part) >= 2 ? 1 : 0;
@@ -232,7 +238,7 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
   if (ew == 0) tc_stamp(tcount, 14);
   if (ablate & 16) return;
   const int wv = min(Cfg::TW, W - j0);
-  const bool bulk = ops == Cfg::NDISP && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const bool bulk = ops == Cfg::NDISP && qo == 9 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (bulk) {
     if (ew == 0 && lane == 0) {
 #pragma unroll
@@ -254,7 +260,8 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
       const int g0 = third * 432 + lane, gend = min(n, (third + 1) * 432);
       int p = g0 / Cfg::NDISP, e = g0 - p * Cfg::NDISP;  // element e of pixel p
       for (int g = g0; g < gend; g += 32) {
-        dst[(size_t)p * ops + e] = src[g];
+        const int m = e / 9;
+        dst[(size_t)p * ops + chb + m * qo + (e - m * 9)] = src[g];
         e += 32;
         if (e >= Cfg::NDISP) { e -= Cfg::NDISP; ++p; }
       }
@@ -295,7 +302,8 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem, int warp) {
 __global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
 corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
                           float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
-                          int tiles_x, int tiles_y, int ntiles, int ablate) {
+                          int tiles_x, int tiles_y, int ntiles, int ablate, int oi, int oj, int chb, int qo) {
+  // (oi, oj): window offset of the second-frame tile (0 for d = 4; +-4 for the four windows of d = 8)
   // ablate (dev, QPWC_ABLATE): bit0 no accumulator drain, bit1 no operand split, bit2 no MMAs, bit3 no loads,
   // bit4 no copy-out
   using Cfg = TcCfg;
@@ -340,8 +348,8 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
         coords(n, c, i0, j0, b);
         tma_prefetch_l2_4d(&tmP, c * Cfg::S_KC, j0, i0, b);
         tma_prefetch_l2_4d(&tmP, c * Cfg::S_KC, j0 + 8, i0, b);
-        tma_prefetch_l2_4d(&tmN, c * Cfg::S_KC, j0 - 4, i0 - 4, b);
-        tma_prefetch_l2_4d(&tmN, c * Cfg::S_KC, j0 - 4, i0 + 4, b);
+        tma_prefetch_l2_4d(&tmN, c * Cfg::S_KC, j0 - 4 + oj, i0 - 4 + oi, b);
+        tma_prefetch_l2_4d(&tmN, c * Cfg::S_KC, j0 - 4 + oj, i0 + 4 + oi, b);
       };
       for (int n = 0; n < PF; ++n) prefetch(n);
       for (int n = 0; n < nitems; ++n) {
@@ -357,8 +365,8 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
           // A: two boxes of 8 cols x 8 rows; TMEM lane quadrant q = 2*cb + rb is the block rows 4*rb.., cols 8*cb..
           tma_load_4d(QPWC_SA(s), &tmP, &raw_full[s], c * Cfg::S_KC, j0, i0, b);
           tma_load_4d(QPWC_SA(s) + Cfg::SA_BYTES / 2, &tmP, &raw_full[s], c * Cfg::S_KC, j0 + 8, i0, b);
-          tma_load_4d(QPWC_SB(s), &tmN, &raw_full[s], c * Cfg::S_KC, j0 - 4, i0 - 4, b);
-          tma_load_4d(QPWC_SB(s) + Cfg::SB_BYTES / 2, &tmN, &raw_full[s], c * Cfg::S_KC, j0 - 4, i0 + 4, b);
+          tma_load_4d(QPWC_SB(s), &tmN, &raw_full[s], c * Cfg::S_KC, j0 - 4 + oj, i0 - 4 + oi, b);
+          tma_load_4d(QPWC_SB(s) + Cfg::SB_BYTES / 2, &tmN, &raw_full[s], c * Cfg::S_KC, j0 - 4 + oj, i0 + 4 + oi, b);
         }
       }
     }
@@ -372,15 +380,16 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
           const int s = (int)(g % Cfg::NST);
           mbar_wait(&lo_full[s], (g / Cfg::NST) & 1u);
           tc_fence_after();
-          const uint32_t b_raw = smem_u32(QPWC_SB(s)), b_lo = b_raw + Cfg::SB_BYTES;
+          const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_SB(s))), d_lo = d_raw + (uint64_t)(Cfg::SB_BYTES >> 4);
           const uint32_t a_tm = tmem + (uint32_t)(Cfg::TM_A + s * 32);
           const int nks = min(2, (C - c * Cfg::S_KC) / 8);
           if (!(ablate & 4))
             for (int ks = 0; ks < nks; ++ks)
 #pragma unroll
-              for (int h = 0; h < 2; ++h)
-                umma_x3_ts<PXB>(tmem + (uint32_t)(h * Cfg::NHALF), a_tm + ks * 16, b_raw + h * (Cfg::SB_BYTES / 2) + ks * 32,
-                                b_lo + h * (Cfg::SB_BYTES / 2) + ks * 32, (c | ks) ? 1u : 0u);
+              for (int h = 0; h < 2; ++h) {
+                const uint64_t off = (uint64_t)((h * (Cfg::SB_BYTES / 2) + ks * 32) >> 4);
+                umma_x3_ts(tmem + (uint32_t)(h * Cfg::NHALF), a_tm + ks * 16, d_raw + off, d_lo + off, (c | ks) ? 1u : 0u);
+              }
           umma_commit(&stage_free[s]);  // stage reusable once these MMAs have read it
         }
         umma_commit(&tfull[0]);
@@ -416,7 +425,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int tx = tile % tiles_x, rest = tile / tiles_x, ty = rest % tiles_y, b = rest / tiles_y;
       tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, tcount, q, part, ew, lane, out, b, ty * Cfg::TH, tx * Cfg::TW,
-                       H, W, ops, inv_c, slope, ablate);
+                       H, W, ops, inv_c, slope, ablate, chb, qo);
     }
   }
   tc_teardown(tmem, warp);
@@ -437,7 +446,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
 __global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
 corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
                        float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
-                       int tiles_x, int tiles_y, int seg, int nseg, int nunits, int ablate) {
+                       int tiles_x, int tiles_y, int seg, int nseg, int nunits, int ablate, int oi, int oj, int chb, int qo) {
   using Cfg = TcCfg;
   constexpr int PXB = Cfg::R_PXB;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -503,7 +512,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
           if (hb) tc_stamp(T, 1);
           if (ablate & 8) { mbar_arrive(&bfull[p]); continue; }
           mbar_arrive_expect_tx(&bfull[p], Cfg::RB_BYTES);
-          tma_load_4d(QPWC_BBLK(p), &tmN, &bfull[p], 0, j0 - 4, i0 - 4 + hb * 8, b);
+          tma_load_4d(QPWC_BBLK(p), &tmN, &bfull[p], 0, j0 - 4 + oj, i0 - 4 + oi + hb * 8, b);
         }
       }}
     }
@@ -521,10 +530,10 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
         tc_fence_after();
         tc_stamp(T, 6);
         {
-          const uint32_t b_raw = smem_u32(QPWC_BBLK(top)), b_lo = b_raw + Cfg::RB_BYTES;
+          const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_BBLK(top))), d_lo = d_raw + (uint64_t)(Cfg::RB_BYTES >> 4);
           if (!(ablate & 4))
             for (int ks = 0; ks < nks; ++ks)
-              umma_x3_ts<PXB>(tmem, a_tm + ks * 16, b_raw + ks * 32, b_lo + ks * 32, ks > 0 ? 1u : 0u);
+              umma_x3_ts(tmem, a_tm + ks * 16, d_raw + (uint64_t)(2 * ks), d_lo + (uint64_t)(2 * ks), ks > 0 ? 1u : 0u);
           umma_commit(&tfull[0]);
           umma_commit(&bfree[top]);  // the upper block is dead once these MMAs have read it
           tc_stamp(T, 7);
@@ -535,10 +544,10 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
         tc_fence_after();
         tc_stamp(T, 8);
         {
-          const uint32_t b_raw = smem_u32(QPWC_BBLK(bot)), b_lo = b_raw + Cfg::RB_BYTES;
+          const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_BBLK(bot))), d_lo = d_raw + (uint64_t)(Cfg::RB_BYTES >> 4);
           if (!(ablate & 4))
             for (int ks = 0; ks < nks; ++ks)
-              umma_x3_ts<PXB>(tmem + Cfg::NHALF, a_tm + ks * 16, b_raw + ks * 32, b_lo + ks * 32, ks > 0 ? 1u : 0u);
+              umma_x3_ts(tmem + Cfg::NHALF, a_tm + ks * 16, d_raw + (uint64_t)(2 * ks), d_lo + (uint64_t)(2 * ks), ks > 0 ? 1u : 0u);
           umma_commit(&tfull[1]);
           umma_commit(&afree[a]);
           if (k == nt - 1) umma_commit(&bfree[bot]);  // end of the segment: nobody inherits the lower block
@@ -587,7 +596,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
     uint32_t T = 0, ring = 0;
     int top = 0, bot = 0;
     QPWC_FOR_UNITS
-      tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, T, q, part, ew, lane, out, b, i0, j0, H, W, ops, inv_c, slope, ablate);
+      tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, T, q, part, ew, lane, out, b, i0, j0, H, W, ops, inv_c, slope, ablate, chb, qo);
     }}
     (void)top; (void)bot;
   }
@@ -606,8 +615,9 @@ extern "C" int qpwc_debug_tc_trace(long long* device_buffer) {   // dev tool, no
 
 int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, int H, int W, int C, int d,
                        float slope, long long ops, cudaStream_t stream) {
-  // domain: d == 4, C a multiple of 8, 16-byte aligned inputs (TMA)
-  if (d != 4 || (C & 7) || C < 8) return QPWC_ERR_UNSUPPORTED;
+  // domain: d == 4 (one 9x9 window) or d == 8 (four 9x9 windows of the 17x17 range, one launch each; the
+  // shared lines di = 0 / dj = 0 are written twice, bit-identically), C a multiple of 8, 16-byte aligned inputs
+  if ((d != 4 && d != 8) || (C & 7) || C < 8) return QPWC_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15)) return QPWC_ERR_UNSUPPORTED;
   using Cfg = TcCfg;
   const int tiles_x = cdiv(W, Cfg::TW), tiles_y = cdiv(H, Cfg::TH);
@@ -616,29 +626,39 @@ int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, in
   static int ablate = -1;
   if (ablate < 0) { const char* ev = getenv("QPWC_ABLATE"); ablate = ev ? atoi(ev) : 0; }
   const int sms = sm_count_cached();
+  const bool resident = C <= 32 && !(ablate & 32);
   TensorMap tmP, tmN;
-  if (C <= 32 && !(ablate & 32)) {
+  if (resident) {
     if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, 32, 8, 8)) return QPWC_ERR_CUDA;           // A: 8 cols x 8 rows x 128 B
     if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, 32, Cfg::NCOL, 8)) return QPWC_ERR_CUDA;   // B: 24 cols x 8 rows (half tile)
-    // segments of vertically consecutive tiles; short enough that every SM gets several
-    int seg = tiles_y;
-    while (seg > 2 && (long long)tiles_x * B * cdiv(tiles_y, seg) < 4LL * sms) seg = cdiv(seg, 2);
-    const int nseg = cdiv(tiles_y, seg);
-    const int nunits = tiles_x * B * nseg;
-    const cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::R_SMEM_BYTES);
-    if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_fwd_tc: smem attribute (%d B): %s", Cfg::R_SMEM_BYTES, cudaGetErrorString(e));
-    corr_fwd_tc_res_kernel<<<nunits < sms ? nunits : sms, Cfg::NTHREADS, Cfg::R_SMEM_BYTES, stream>>>(
-        tmP, tmN, out, B, H, W, C, slope, ops, tiles_x, tiles_y, seg, nseg, nunits, ablate);
-    return check_launch("corr_fwd_tc_res");
+  } else {
+    if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::S_KC, 8, 8)) return QPWC_ERR_CUDA;
+    if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, Cfg::S_KC, Cfg::NCOL, 8)) return QPWC_ERR_CUDA;
   }
-  if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::S_KC, 8, 8)) return QPWC_ERR_CUDA;
-  if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, Cfg::S_KC, Cfg::NCOL, 8)) return QPWC_ERR_CUDA;
-  const int ntiles = (int)nt;
-  const cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::S_SMEM_BYTES);
-  if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_fwd_tc: smem attribute (%d B): %s", Cfg::S_SMEM_BYTES, cudaGetErrorString(e));
-  corr_fwd_tc_stream_kernel<<<ntiles < sms ? ntiles : sms, Cfg::NTHREADS, Cfg::S_SMEM_BYTES, stream>>>(
-      tmP, tmN, out, B, H, W, C, slope, ops, tiles_x, tiles_y, ntiles, ablate);
-  return check_launch("corr_fwd_tc_stream");
+  const int smem = resident ? Cfg::R_SMEM_BYTES : Cfg::S_SMEM_BYTES;
+  const cudaError_t e = resident
+      ? cudaFuncSetAttribute(corr_fwd_tc_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+      : cudaFuncSetAttribute(corr_fwd_tc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "corr_fwd_tc: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
+  // segments of vertically consecutive tiles (resident kernel); short enough that every SM gets several
+  int seg = tiles_y;
+  while (seg > 2 && (long long)tiles_x * B * cdiv(tiles_y, seg) < 4LL * sms) seg = cdiv(seg, 2);
+  const int nseg = cdiv(tiles_y, seg);
+  const int nunits = tiles_x * B * nseg, ntiles = (int)nt;
+  const int nwin = d == 8 ? 4 : 1, qo = 2 * d + 1;
+  for (int win = 0; win < nwin; ++win) {
+    const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4);
+    const int chb = nwin == 1 ? 0 : (oi + 4) * qo + (oj + 4);
+    if (resident)
+      corr_fwd_tc_res_kernel<<<nunits < sms ? nunits : sms, Cfg::NTHREADS, smem, stream>>>(
+          tmP, tmN, out, B, H, W, C, slope, ops, tiles_x, tiles_y, seg, nseg, nunits, ablate, oi, oj, chb, qo);
+    else
+      corr_fwd_tc_stream_kernel<<<ntiles < sms ? ntiles : sms, Cfg::NTHREADS, smem, stream>>>(
+          tmP, tmN, out, B, H, W, C, slope, ops, tiles_x, tiles_y, ntiles, ablate, oi, oj, chb, qo);
+    const int rc = check_launch(resident ? "corr_fwd_tc_res" : "corr_fwd_tc_stream");
+    if (rc != QPWC_OK) return rc;
+  }
+  return QPWC_OK;
 }
 
 #else  // CPU emulation build: the tensor-core kernel has no stand-in; callers fall back to the FFMA kernels

@@ -82,7 +82,9 @@ def test_cost_volume_forward(B, H, W, C, d):
 
 @pytest.mark.parametrize("B,H,W,C,d", [(2, 14, 32, 256, 4), (1, 56, 128, 128, 4), (1, 33, 70, 64, 4), (1, 40, 72, 32, 4),
                                        (1, 17, 19, 16, 4), (2, 11, 61, 96, 4), (3, 61, 190, 40, 4), (1, 8, 16, 8, 4),
-                                       (2, 9, 17, 24, 4), (1, 100, 36, 72, 4)])
+                                       (2, 9, 17, 24, 4), (1, 100, 36, 72, 4),
+                                       # search range 8: four 9x9 windows of the 17x17 range (config 4)
+                                       (1, 20, 30, 32, 8), (2, 27, 50, 16, 8), (1, 19, 33, 72, 8)])
 def test_cost_volume_tensor_core_engine(B, H, W, C, d):
     """The tensor-core kernels (qpwc_corr_tc.cu) forced on: resident (C <= 32) and streaming paths,
     ragged tiles (H % 8, W % 16), channel counts with a half-filled last stage (C % 16 = 8), strided

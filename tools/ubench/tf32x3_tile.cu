@@ -128,16 +128,33 @@ tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* _
   if (tid == 0) {
     const uint32_t idesc = make_idesc(M, NH);
     const int npass = mode >= 2 ? 3 : 1;
+    // descriptors are built before the timed loop: the issuing thread's own instruction stream must not
+    // be what is measured (with the address arithmetic inside the loop the rate drops to ~130 clk/MMA)
+    uint64_t da[NCHUNK][3], db[NCHUNK][2][3];
+    uint32_t ta[NCHUNK][3];
+    for (int c = 0; c < NCHUNK; ++c)
+      for (int p = 0; p < 3; ++p) {
+        da[c][p] = make_desc(smem_u32((p == 1 ? a_lo : a_hi) + c * A_BYTES));
+        ta[c][p] = tmem + 384 + c * 16 + (p == 1 ? 8 : 0);
+        for (int h = 0; h < 2; ++h) db[c][h][p] = make_desc(smem_u32((p == 2 ? b_lo : b_hi) + c * B_BYTES + h * NH * 32));
+      }
     t0 = clock64();
-    for (int r = 0; r < reps; ++r)
-      for (int c = 0; c < NCHUNK; ++c)
-        for (int h = 0; h < 2; ++h)
-          for (int p = 0; p < npass; ++p) {
-            const unsigned char* ap = (p == 1 ? a_lo : a_hi) + c * A_BYTES;
-            const unsigned char* bp = (p == 2 ? b_lo : b_hi) + c * B_BYTES + h * NH * 32;
-            if (mode == 4) mma_tf32_ts(tmem + h * NH, tmem + 384 + c * 16 + (p == 1 ? 8 : 0), make_desc(smem_u32(bp)), idesc, (r | c | p) != 0);
-            else mma_tf32(tmem + h * NH, make_desc(smem_u32(ap)), make_desc(smem_u32(bp)), idesc, (r | c | p) != 0);
-          }
+    if (mode == 4) {
+      for (int r = 0; r < reps; ++r)
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int p = 0; p < 3; ++p) mma_tf32_ts(tmem + h * NH, ta[c][p], db[c][h][p], idesc, (r | c | p) != 0);
+    } else {
+      for (int r = 0; r < reps; ++r)
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            for (int p = 0; p < npass; ++p) mma_tf32(tmem + h * NH, da[c][p], db[c][h][p], idesc, (r | c | p) != 0);
+    }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
   }
   // everybody waits for the MMAs
