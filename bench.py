@@ -224,8 +224,23 @@ def run_native(args):
     # The step (5 launches) is recorded once into a CUDA graph and replayed: same kernels, same
     # stream order, no per-call host overhead on the launch-bound coarse levels.
     use_graph = not args.no_graph
-    if use_graph:
+    serial_ms = None
+    if use_graph and not args.serial_levels:
+        # the same step with the five levels in stream order (round-1/2a layout), for comparison
         wl.capture()
+        for _ in range(Wm):
+            wl.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Ks = min(K, 100)
+        e0.record()
+        for _ in range(Ks):
+            wl.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        serial_ms = e0.elapsed_time(e1) / Ks
+    if use_graph:
+        wl.capture(concurrent=not args.serial_levels)
     run_step = wl.replay if use_graph else wl.step
     for _ in range(Wm):
         run_step()
@@ -456,7 +471,11 @@ def run_native(args):
                                  "max error 8e-7 x mean|prv*nxt| vs the 1e-5 contract); warp: fp32 gather kernel, bit-exact",
                        "l2": "inputs larger than L2: each step streams 853 MB of distinct tensors (126 MB L2)",
                        "parallelism": f"batch-sharded replicas x{world}, no collective on the data path",
-                       "launch": ("CUDA graph of the %d launches per step" if use_graph else "%d individual launches per step") % wl.launches_per_step,
+                       "launch": (("CUDA graph of the %d launches per step" + ("" if args.serial_levels else
+                                   "; the five levels are independent branches of the graph (synthetic levels carry no data "
+                                   "dependence), so coarse levels overlap the tails of fine ones"))
+                                  if use_graph else "%d individual launches per step") % wl.launches_per_step,
+                       "serial_levels_ms_per_step": serial_ms,
                        "upflow_path": dict(zip([f"{l.H}x{l.W}x{l.C}" for l in wl.levels], wl.level_path)),
                        "autotune_ms": getattr(wl, "autotune_ms", None)},
             "roofline": roofline, "roofline_fused": roofline_fused, "train_step": train,
@@ -477,6 +496,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the 5 kernels per step individually")
+    ap.add_argument("--serial-levels", action="store_true", help="graph with the five levels in stream order (no fork/join)")
     ap.add_argument("--no-train", action="store_true", help="skip the config-3 training-step section")
     ap.add_argument("--path", default="auto", choices=["auto", "fused", "composed"],
                     help="UpFlow levels: fused kernel, warp + cost volume, or time both and keep the faster")

@@ -97,6 +97,12 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uin
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
+// asynchronous 4-D tensor store shared -> global (TMA engine): the whole box in one instruction, clipped
+// at the tensor's extent; completion is tracked by the same bulk groups as bulk_store
+__device__ __forceinline__ void tma_store_4d(const TensorMap* tm, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still have to READ their shared-memory source
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
@@ -119,6 +125,9 @@ template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile
 // (boxC, boxW, boxH, 1), SWIZZLE_32B, zero fill out of bounds, 128-B L2 promotion.
 // Returns false (and sets the error) on failure.
 bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C, int boxC, int boxW, int boxH);  // swizzle = boxC*4 bytes
+// dense (B,H,W,81) cost volume seen as (216, W*81/216, H, B): a box (216, 6, th, 1) is the 16-pixel x th-row
+// output tile of the tensor-core kernels (one tensor store per tile).  Needs W % 8 == 0.
+bool make_tmap_cv_tiles(TensorMap* tm, float* out, int B, int H, int W, int th);
 // dense NCHW fp32 tensor, dims (W, H, C, B), box (boxW, boxH, boxC, 1), no swizzle (channel-planar tiles)
 bool make_tmap_nchw(TensorMap* tm, const float* base, int B, int C, int H, int W, int boxW, int boxH, int boxC);
 

@@ -47,6 +47,11 @@ __device__ __forceinline__ void tc_stamp(uint32_t tile, int ev) {
   if (t != nullptr && blockIdx.x == 0 && tile < QPWC_TRACE_TILES) t[tile * 24 + ev] = clock64();
 }
 
+// dev (QPWC_ABLATE bit 9): spin instead of parking on the role hand-over barriers
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, int spin) {
+  if (spin) mbar_wait(bar, parity); else mbar_wait_parked(bar, parity);
+}
+
 struct TcCfg {
   static constexpr int NDISP = 81;
   static constexpr int TH = 8, TW = 16, NROW = 16, NCOL = 24, NHALF = 192;
@@ -63,14 +68,17 @@ struct TcCfg {
   // TMEM columns: accumulator 0..383 (two halves of N); first-frame operand (hi, lo) from column 384:
   // 16 columns per 8-channel K step (8 hi + 8 lo)
   static constexpr int TM_A = 384;
-  // ---- resident kernel (C <= 32): 128-byte channel rows.  Two landing buffers for A (128 px), a ring of
-  // three half-tile B blocks (192 px, raw + lo)
+  // ---- resident kernel (C <= 32): 128-byte channel rows.  One landing buffer for A (128 px; it is moved to
+  // TMEM at once), a ring of three raw half-tile B blocks (192 px; a block is loaded two tile periods
+  // before it is needed), a ring of TWO lo blocks (the lo of a block is written after the block two
+  // allocations earlier has died -- one tile period of slack, no HBM latency on that path), and TWO staging
+  // images: the TMA store of tile T drains (~2000 clk for 41 KB) while tile T+1 is being staged.
   static constexpr int R_PXB = 128;
-  static constexpr int RA_BYTES = 128 * R_PXB, RB_BYTES = NHALF * R_PXB;          // 16 KB, 24 KB (raw; lo follows)
-  static constexpr int NBLK = 3;
-  static constexpr int R_OFF_A = 0, R_OFF_B = 2 * RA_BYTES;                       // A: 32 KB, B: 144 KB
-  static constexpr int R_OFF_STAGING = R_OFF_B + NBLK * 2 * RB_BYTES;
-  static constexpr int R_OFF_BARS = R_OFF_STAGING + STAGING_BYTES;
+  static constexpr int RA_BYTES = 128 * R_PXB, RB_BYTES = NHALF * R_PXB;          // 16 KB, 24 KB
+  static constexpr int NBLK = 3, NLO = 2, NSTG = 2;
+  static constexpr int R_OFF_A = 0, R_OFF_B = RA_BYTES, R_OFF_BLO = R_OFF_B + NBLK * RB_BYTES;
+  static constexpr int R_OFF_STAGING = R_OFF_BLO + NLO * RB_BYTES;
+  static constexpr int R_OFF_BARS = R_OFF_STAGING + NSTG * STAGING_BYTES;
   static constexpr int R_SMEM_BYTES = R_OFF_BARS + 25 * 8 + 16;
   // ---- streaming kernel (any C % 8 == 0): stages of 16 channels, 64-byte rows; per stage both B half
   // tiles (raw + lo) and an A landing buffer
@@ -79,7 +87,7 @@ struct TcCfg {
   static constexpr int S_OFF_A = NST * 2 * SB_BYTES;
   static constexpr int S_OFF_STAGING = S_OFF_A + NST * SA_BYTES;
   static constexpr int S_OFF_BARS = S_OFF_STAGING + STAGING_BYTES;
-  static constexpr int S_SMEM_BYTES = S_OFF_BARS + (3 * NST + 5) * 8 + 16;
+  static constexpr int S_SMEM_BYTES = S_OFF_BARS + (4 * NST + 5) * 8 + 16;
   static_assert(S_SMEM_BYTES <= 232448 && R_SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TM_A + 2 * 64 <= 512 && TM_A + NST * 32 <= 512, "TMEM columns");
 };
@@ -172,20 +180,24 @@ __device__ __forceinline__ void a_to_tmem(const unsigned char* landing, int m, u
 __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, uint64_t* tfull, uint64_t* tempty, uint64_t* sfree,
                                                  uint32_t tcount, int q, int part, int ew, int lane,
                                                  float* __restrict__ out, int b, int i0, int j0, int H, int W,
-                                                 long long ops, float inv_c, float slope, int ablate, int chb, int qo) {
+                                                 long long ops, float inv_c, float slope, int ablate, int chb, int qo,
+                                                 const TensorMap* tmO, int nstg) {
   // chb / qo: first output channel and channel pitch of a displacement row.  d = 4: (0, 9), the 81
   // results of a pixel are contiguous.  d = 8 runs as four 9x9 windows of the 17x17 range: qo = 17,
   // chb = (oi + 4) * 17 + (oj + 4) for the window offset (oi, oj) in {-4, +4}^2.
   using Cfg = TcCfg;
+  // nstg staging images (1 or 2): tile T uses image T % nstg, free once the store of tile T - nstg has read it
+  staging += (tcount & (uint32_t)(nstg - 1)) * (Cfg::STAGING_BYTES / 4);
   const int rb = q & 1, cb = q >> 1, r = lane >> 3, c = lane & 7;
   const int h = (rb + part) >= 2 ? 1 : 0;
   const int y0 = 4 * part;
   const bool c4 = c & 4, c2 = c & 2, c1 = c & 1;
   const bool fast = inv_c == 1.f && slope >= 0.f && slope <= 1.f;
+  const int spin = (ablate >> 9) & 1;
   // row (y - r) of the band of pixel (rb*4 + r, cb*8 + c) starts at lane_base[9*y]
   float* lane_base = staging + (rb * 4 + r) * Cfg::ROW_FLOATS + (cb * 8 + c) * Cfg::NDISP - 9 * r;
   const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((rb * 4 + y0) * Cfg::NCOL + cb * 8);
-  mbar_wait_parked(&tfull[h], tcount & 1u);
+  tc_wait(&tfull[h], tcount & 1u, spin);
   tc_fence_after();
   if (ew == 0) tc_stamp(tcount, 10); else if (ew == 8) tc_stamp(tcount, 15);
   // all four rows of this warp's share into registers first: the accumulator half is released as soon
@@ -204,7 +216,10 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
   // here, after the accumulator loads, so that the engine's reads overlap the wait for the MMAs)
   // (one lane issues and tracks the stores; the others learn through `sfree`, so a warp that has its
   // rows goes straight on to the shifting/staging work without waiting for the other half's loads)
-  if (ew == 0 && lane == 0) { bulk_wait_read<0>(); mbar_arrive(sfree); }
+  if (ew == 0 && lane == 0) {
+    if (nstg == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+    mbar_arrive(sfree);
+  }
   mbar_wait(sfree, tcount & 1u);
   if (ew == 0) tc_stamp(tcount, 12);
   if (!(ablate & 1)) {
@@ -239,7 +254,15 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
   if (ablate & 16) return;
   const int wv = min(Cfg::TW, W - j0);
   const bool bulk = ops == Cfg::NDISP && qo == 9 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-  if (bulk) {
+  if (tmO != nullptr) {
+    // W % 8 == 0: the tile is one box of the (216, W*81/216, H, B) view of the cost volume -- a single
+    // tensor store, clipped at the image edge (eight per-row bulk copies cost the issuing lane ~1100 clk
+    // per tile, on the critical chain stores -> staging free -> next tile staged: profiles/r02_tc_trace.txt)
+    if (ew == 0 && lane == 0) {
+      tma_store_4d(tmO, staging, 0, (j0 >> 4) * 6, i0, b);
+      bulk_commit();
+    }
+  } else if (bulk) {
     if (ew == 0 && lane == 0) {
 #pragma unroll
       for (int row = 0; row < Cfg::TH; ++row)
@@ -301,11 +324,11 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem, int warp) {
 // stage cover both halves of N, so the accumulator is published once per tile.
 __global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
 corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
-                          float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
+                          const __grid_constant__ TensorMap tmO, int tstore, float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
                           int tiles_x, int tiles_y, int ntiles, int ablate, int oi, int oj, int chb, int qo) {
   // (oi, oj): window offset of the second-frame tile (0 for d = 4; +-4 for the four windows of d = 8)
   // ablate (dev, QPWC_ABLATE): bit0 no accumulator drain, bit1 no operand split, bit2 no MMAs, bit3 no loads,
-  // bit4 no copy-out
+  // bit4 no copy-out, bit5 force the streaming kernel, bit6 per-row bulk copies instead of the tensor store, bit7 no L2 prefetch
   using Cfg = TcCfg;
   constexpr int PXB = Cfg::S_PXB;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -314,13 +337,14 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
   uint64_t* stage_free = raw_full + Cfg::NST;     // count 1 (commit)
   uint64_t* tfull = stage_free + Cfg::NST;        // [2] count 1 (commit)
   uint64_t* sfree = tfull + 2;                    // count 1: staging image read by the previous tile's bulk stores
-  uint64_t* lo_full = sfree + 1;                  // count 4
-  uint64_t* tempty = lo_full + Cfg::NST;          // [2] count 6
+  uint64_t* lo_full = sfree + 1;                  // count 4: second-frame lo of the stage written
+  uint64_t* a_full = lo_full + Cfg::NST;          // count 4: first-frame operand of the stage in TMEM
+  uint64_t* tempty = a_full + Cfg::NST;           // [2] count 6
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* staging = reinterpret_cast<float*>(smem + Cfg::S_OFF_STAGING);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, spin = (ablate >> 9) & 1;
   const int nstages = (C + Cfg::S_KC - 1) / Cfg::S_KC;  // per tile; the last one may hold a single K step
-  const uint32_t tmem = tc_prologue(bars, 2 * Cfg::NST + 3, Cfg::NST, 2, tmem_slot, smem, tid, warp);
+  const uint32_t tmem = tc_prologue(bars, 2 * Cfg::NST + 3, 2 * Cfg::NST, 2, tmem_slot, smem, tid, warp);
 #define QPWC_SB(s) (smem + (s) * 2 * Cfg::SB_BYTES)
 #define QPWC_SA(s) (smem + Cfg::S_OFF_A + (s) * Cfg::SA_BYTES)
 
@@ -343,7 +367,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
         b = rest / tiles_y; i0 = ty * Cfg::TH; j0 = tx * Cfg::TW;
       };
       auto prefetch = [&](int n) {
-        if (n >= nitems || (ablate & 8)) return;
+        if (n >= nitems || (ablate & (8 | 128))) return;
         int c, i0, j0, b;
         coords(n, c, i0, j0, b);
         tma_prefetch_l2_4d(&tmP, c * Cfg::S_KC, j0, i0, b);
@@ -358,7 +382,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
         coords(n, c, i0, j0, b);
         {
           const int s = (int)(g % Cfg::NST);
-          mbar_wait_parked(&stage_free[s], ((g / Cfg::NST) & 1u) ^ 1u);
+          tc_wait(&stage_free[s], ((g / Cfg::NST) & 1u) ^ 1u, spin);
           prefetch(n + PF);
           if (ablate & 8) { mbar_arrive(&raw_full[s]); continue; }
           mbar_arrive_expect_tx(&raw_full[s], Cfg::SA_BYTES + Cfg::SB_BYTES);
@@ -378,7 +402,13 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
         mbar_wait(&tempty[1], (tcount & 1u) ^ 1u);
         for (int c = 0; c < nstages; ++c, ++g) {
           const int s = (int)(g % Cfg::NST);
-          mbar_wait(&lo_full[s], (g / Cfg::NST) & 1u);
+          // the passes that read only the raw second-frame words (hi.hi, lo.hi) go out as soon as the
+          // first-frame operand is in TMEM; the elementwise lo of the 24 KB second-frame block is
+          // computed by the split warps meanwhile, and the hi.lo pass follows.  (Measured and dropped:
+          // half-major order inside a stage, to publish half 0 early and overlap the accumulator drain,
+          // is 3-5 us SLOWER at every streaming level.)
+          mbar_wait(&raw_full[s], (g / Cfg::NST) & 1u);
+          mbar_wait(&a_full[s], (g / Cfg::NST) & 1u);
           tc_fence_after();
           const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_SB(s))), d_lo = d_raw + (uint64_t)(Cfg::SB_BYTES >> 4);
           const uint32_t a_tm = tmem + (uint32_t)(Cfg::TM_A + s * 32);
@@ -388,7 +418,17 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const uint64_t off = (uint64_t)((h * (Cfg::SB_BYTES / 2) + ks * 32) >> 4);
-                umma_x3_ts(tmem + (uint32_t)(h * Cfg::NHALF), a_tm + ks * 16, d_raw + off, d_lo + off, (c | ks) ? 1u : 0u);
+                umma_tf32_ts(tmem + (uint32_t)(h * Cfg::NHALF), a_tm + ks * 16, d_raw + off, (c | ks) ? 1u : 0u);
+                umma_tf32_ts(tmem + (uint32_t)(h * Cfg::NHALF), a_tm + ks * 16 + 8, d_raw + off, 1u);
+              }
+          mbar_wait(&lo_full[s], (g / Cfg::NST) & 1u);
+          tc_fence_after();
+          if (!(ablate & 4))
+            for (int ks = 0; ks < nks; ++ks)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint64_t off = (uint64_t)((h * (Cfg::SB_BYTES / 2) + ks * 32) >> 4);
+                umma_tf32_ts(tmem + (uint32_t)(h * Cfg::NHALF), a_tm + ks * 16, d_lo + off, 1u);
               }
           umma_commit(&stage_free[s]);  // stage reusable once these MMAs have read it
         }
@@ -405,12 +445,14 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int c = 0; c < nstages; ++c, ++g) {
         const int s = (int)(g % Cfg::NST);
-        mbar_wait_parked(&raw_full[s], (g / Cfg::NST) & 1u);
+        tc_wait(&raw_full[s], (g / Cfg::NST) & 1u, spin);
         tc_fence_after();  // (the MMAs that read TMEM buffer s completed before the stage was reloaded)
-        if (!(ablate & 2)) {
+        if (!(ablate & 2))
           a_to_tmem<PXB, 2>(QPWC_SA(s), m, tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + s * 32), min(2, (C - c * Cfg::S_KC) / 8), a_scale);
-          split_block(QPWC_SB(s), QPWC_SB(s) + Cfg::SB_BYTES, Cfg::SB_BYTES, st);
-        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[s]);
+        if (!(ablate & 2)) split_block(QPWC_SB(s), QPWC_SB(s) + Cfg::SB_BYTES, Cfg::SB_BYTES, st);
         fence_proxy_async();  // generic-proxy stores -> tensor-core (async proxy) reads
         tc_fence_before();
         __syncwarp();
@@ -422,10 +464,11 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
     const int ew = warp - Cfg::W_EPI, q = warp & 3, part = ew >> 2;
     const float inv_c = (C & (C - 1)) == 0 ? 1.f : 1.f / (float)C;  // power-of-two C: folded into the first-frame operand
     uint32_t tcount = 0;
+    if (tstore && ew == 0 && lane == 0) tma_prefetch_desc(&tmO);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int tx = tile % tiles_x, rest = tile / tiles_x, ty = rest % tiles_y, b = rest / tiles_y;
       tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, tcount, q, part, ew, lane, out, b, ty * Cfg::TH, tx * Cfg::TW,
-                       H, W, ops, inv_c, slope, ablate, chb, qo);
+                       H, W, ops, inv_c, slope, ablate, chb, qo, tstore ? &tmO : nullptr, 1);
     }
   }
   tc_teardown(tmem, warp);
@@ -439,39 +482,43 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
 // the next tile's first half while this tile's second drains -- and (2) a CTA walks vertically
 // consecutive tiles of one strip: the lower half-tile of second-frame rows of tile k is the upper
 // half-tile of tile k+1 and stays where it is ("rolling rows"): only 8 new second-frame rows are
-// loaded and split per tile instead of 16.  The half-tile blocks form a ring of three, so the block a
-// tile frees after its first pass is refilled two tile periods before it is needed.  The first-frame
-// operand goes through TMEM (double-buffered), which halves its shared-memory footprint and removes
-// its operand reads.
+// loaded and split per tile instead of 16.  The raw half-tile blocks form a ring of three, so the block a
+// tile frees after its first pass is refilled two tile periods before it is needed; their lo parts
+// live in a ring of two (block n reuses the lo slot of block n-2, which dies one tile period before
+// block n's lo is read).  The first-frame operand goes through TMEM (double-buffered there, one landing
+// buffer in shared memory).  The shared memory this frees holds a second staging image, so the TMA
+// store of a tile drains while the next tile is staged (profiles/r02_tc_trace.txt: with one image the
+// epilogue warps waited ~1300 of 3900 clk per tile for the previous store to finish reading it).
 __global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
 corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
-                       float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
+                       const __grid_constant__ TensorMap tmO, int tstore, float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
                        int tiles_x, int tiles_y, int seg, int nseg, int nunits, int ablate, int oi, int oj, int chb, int qo) {
   using Cfg = TcCfg;
   constexpr int PXB = Cfg::R_PXB;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::R_OFF_BARS);
-  uint64_t* afull = bars;          // [2] count 1 (+tx): A landed in landing buffer a
-  uint64_t* bfull = afull + 2;     // [3] count 1 (+tx): B block p landed
+  uint64_t* afull = bars;          // count 1 (+tx): A landed in the landing buffer
+  uint64_t* bfull = afull + 1;     // [3] count 1 (+tx): raw B block p landed
   uint64_t* afree = bfull + 3;     // [2] count 1 (commit): TMEM A buffer a no longer read
-  uint64_t* bfree = afree + 2;     // [3] count 1 (commit): B block p no longer read
-  uint64_t* tfull = bfree + 3;     // [2] count 1 (commit)
-  uint64_t* sfree = tfull + 2;     // count 1: staging image read by the previous tile's bulk stores
-  uint64_t* arawfree = sfree + 1;  // [2] count 4: landing buffer a consumed by the split warps
-  uint64_t* alo = arawfree + 2;    // [2] count 4: TMEM A buffer a written
-  uint64_t* blo = alo + 2;         // [3] count 4: B block p split
-  uint64_t* tempty = blo + 3;      // [2] count 6
+  uint64_t* bfree = afree + 2;     // [3] count 1 (commit): raw B block p no longer read
+  uint64_t* lofree = bfree + 3;    // [2] count 1 (commit): lo block l no longer read
+  uint64_t* tfull = lofree + 2;    // [2] count 1 (commit)
+  uint64_t* sfree = tfull + 2;     // count 1: staging image of this tile no longer read by the store of two tiles ago
+  uint64_t* arawfree = sfree + 1;  // count 4: landing buffer consumed by the split warps
+  uint64_t* alo = arawfree + 1;    // [2] count 4: TMEM A buffer a written
+  uint64_t* blo = alo + 2;         // [2] count 4: lo block l written
+  uint64_t* tempty = blo + 2;      // [2] count 6
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* staging = reinterpret_cast<float*>(smem + Cfg::R_OFF_STAGING);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, spin = (ablate >> 9) & 1;
   const int nks = C / 8;           // K steps (<= 4); channels C..31 of the 128-byte rows are TMA zero fill
-  const uint32_t tmem = tc_prologue(bars, 13, 7, 2, tmem_slot, smem, tid, warp);
-  // B block p: raw at R_OFF_B + p*2*RB_BYTES, lo RB_BYTES further
-#define QPWC_ABUF(a) (smem + Cfg::R_OFF_A + (a) * Cfg::RA_BYTES)
-#define QPWC_BBLK(p) (smem + Cfg::R_OFF_B + (p) * 2 * Cfg::RB_BYTES)
-  // every role walks the same tile sequence; `ring` counts the B blocks allocated so far (block = ring % 3):
-  // the first tile of a segment takes two fresh blocks (top, bot), every other tile inherits its top
-  // from the previous tile's bot and takes one fresh block
+  const uint32_t tmem = tc_prologue(bars, 14, 5, 2, tmem_slot, smem, tid, warp);
+#define QPWC_ABUF (smem + Cfg::R_OFF_A)
+#define QPWC_BRAW(p) (smem + Cfg::R_OFF_B + (p) * Cfg::RB_BYTES)
+#define QPWC_BLO(l) (smem + Cfg::R_OFF_BLO + (l) * Cfg::RB_BYTES)
+  // every role walks the same tile sequence; `ring` counts the B blocks allocated so far (raw slot = ring % 3,
+  // lo slot = ring % 2): the first tile of a segment takes two fresh blocks (top, bot), every other tile
+  // inherits its top from the previous tile's bot and takes one fresh block
 #define QPWC_FOR_UNITS                                                                           \
   for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {                                \
     const int tx = unit % tiles_x, rest_ = unit / tiles_x, sg = rest_ % nseg, b = rest_ / nseg;  \
@@ -479,9 +526,9 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
     (void)b; (void)j0;                                                                           \
     for (int k = 0; k < nt; ++k, ++T) {                                                          \
       const int i0 = (ty0 + k) * Cfg::TH;                                                        \
-      if (k == 0) { top = (int)(ring % 3u); ++ring; } else top = bot;                            \
-      bot = (int)(ring % 3u); ++ring;                                                            \
-      (void)i0;
+      if (k == 0) { top = (int)(ring % 3u); ltop = (int)(ring & 1u); ++ring; } else { top = bot; ltop = lbot; } \
+      bot = (int)(ring % 3u); lbot = (int)(ring & 1u); ++ring;                                   \
+      (void)i0; (void)ltop; (void)lbot;
 #define QPWC_PAR(mask, idx) (((mask) >> (idx)) & 1u)
 
   if (warp < Cfg::W_SPLIT) {
@@ -490,67 +537,66 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
     if (lane == 0) {  // ------------------------------------------------------------- TMA producer
       tma_prefetch_desc(&tmP);
       tma_prefetch_desc(&tmN);
-      uint32_t T = 0, ring = 0, ua = 0, ub = 0;
-      int top = 0, bot = 0;
+      uint32_t T = 0, ring = 0, ub = 0;
+      int top = 0, bot = 0, ltop = 0, lbot = 0;
       QPWC_FOR_UNITS
-        const int a = (int)(T & 1u);
-        mbar_wait_parked(&arawfree[a], QPWC_PAR(ua, a) ^ 1u);
-        ua ^= 1u << a;
+        tc_wait(arawfree, (T & 1u) ^ 1u, spin);  // the landing buffer has been moved to TMEM
         tc_stamp(T, 0);
-        if (ablate & 8) mbar_arrive(&afull[a]);
+        if (ablate & 8) mbar_arrive(afull);
         else {
-          mbar_arrive_expect_tx(&afull[a], Cfg::RA_BYTES);
-          tma_load_4d(QPWC_ABUF(a), &tmP, &afull[a], 0, j0, i0, b);
-          tma_load_4d(QPWC_ABUF(a) + Cfg::RA_BYTES / 2, &tmP, &afull[a], 0, j0 + 8, i0, b);
+          mbar_arrive_expect_tx(afull, Cfg::RA_BYTES);
+          tma_load_4d(QPWC_ABUF, &tmP, afull, 0, j0, i0, b);
+          tma_load_4d(QPWC_ABUF + Cfg::RA_BYTES / 2, &tmP, afull, 0, j0 + 8, i0, b);
         }
         // second-frame half-tile blocks: rows i0-4..i0+3 (top) and i0+4..i0+11 (bot); only the first
         // tile of a segment loads its top
         for (int hb = (k == 0 ? 0 : 1); hb < 2; ++hb) {
           const int p = hb ? bot : top;
-          mbar_wait_parked(&bfree[p], QPWC_PAR(ub, p) ^ 1u);
+          tc_wait(&bfree[p], QPWC_PAR(ub, p) ^ 1u, spin);
           ub ^= 1u << p;
           if (hb) tc_stamp(T, 1);
           if (ablate & 8) { mbar_arrive(&bfull[p]); continue; }
           mbar_arrive_expect_tx(&bfull[p], Cfg::RB_BYTES);
-          tma_load_4d(QPWC_BBLK(p), &tmN, &bfull[p], 0, j0 - 4 + oj, i0 - 4 + oi + hb * 8, b);
+          tma_load_4d(QPWC_BRAW(p), &tmN, &bfull[p], 0, j0 - 4 + oj, i0 - 4 + oi + hb * 8, b);
         }
       }}
     }
    } else if (warp == 1) {
     if (lane == 0) {  // --------------------------------------------------------------- MMA issuer
       uint32_t T = 0, ring = 0, ma = 0, mb = 0;
-      int top = 0, bot = 0;
+      int top = 0, bot = 0, ltop = 0, lbot = 0;
       QPWC_FOR_UNITS
         const int a = (int)(T & 1u);
         const uint32_t a_tm = tmem + (uint32_t)(Cfg::TM_A + a * 64);
         mbar_wait(&alo[a], QPWC_PAR(ma, a));
         ma ^= 1u << a;
-        if (k == 0) { mbar_wait(&blo[top], QPWC_PAR(mb, top)); mb ^= 1u << top; }  // k > 0: waited for as `bot` of tile k-1
+        if (k == 0) { mbar_wait(&blo[ltop], QPWC_PAR(mb, ltop)); mb ^= 1u << ltop; }  // k > 0: waited for as `bot` of tile k-1
         mbar_wait(&tempty[0], (T & 1u) ^ 1u);
         tc_fence_after();
         tc_stamp(T, 6);
         {
-          const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_BBLK(top))), d_lo = d_raw + (uint64_t)(Cfg::RB_BYTES >> 4);
+          const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_BRAW(top))), d_lo = umma_desc<PXB>(smem_u32(QPWC_BLO(ltop)));
           if (!(ablate & 4))
             for (int ks = 0; ks < nks; ++ks)
               umma_x3_ts(tmem, a_tm + ks * 16, d_raw + (uint64_t)(2 * ks), d_lo + (uint64_t)(2 * ks), ks > 0 ? 1u : 0u);
           umma_commit(&tfull[0]);
-          umma_commit(&bfree[top]);  // the upper block is dead once these MMAs have read it
+          umma_commit(&bfree[top]);     // the upper block is dead once these MMAs have read it
+          umma_commit(&lofree[ltop]);
           tc_stamp(T, 7);
         }
-        mbar_wait(&blo[bot], QPWC_PAR(mb, bot));
-        mb ^= 1u << bot;
+        mbar_wait(&blo[lbot], QPWC_PAR(mb, lbot));
+        mb ^= 1u << lbot;
         mbar_wait(&tempty[1], (T & 1u) ^ 1u);
         tc_fence_after();
         tc_stamp(T, 8);
         {
-          const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_BBLK(bot))), d_lo = d_raw + (uint64_t)(Cfg::RB_BYTES >> 4);
+          const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_BRAW(bot))), d_lo = umma_desc<PXB>(smem_u32(QPWC_BLO(lbot)));
           if (!(ablate & 4))
             for (int ks = 0; ks < nks; ++ks)
               umma_x3_ts(tmem + Cfg::NHALF, a_tm + ks * 16, d_raw + (uint64_t)(2 * ks), d_lo + (uint64_t)(2 * ks), ks > 0 ? 1u : 0u);
           umma_commit(&tfull[1]);
           umma_commit(&afree[a]);
-          if (k == nt - 1) umma_commit(&bfree[bot]);  // end of the segment: nobody inherits the lower block
+          if (k == nt - 1) { umma_commit(&bfree[bot]); umma_commit(&lofree[lbot]); }  // end of the segment: nobody inherits the lower block
           tc_stamp(T, 9);
         }
       }}
@@ -561,31 +607,32 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
     const int st = tid - Cfg::W_SPLIT * 32, qd = warp & 3;  // qd: the TMEM lane quadrant this warp may write
     const int m = qd * 32 + lane;                           // its pixel = row of A = TMEM lane
     const float a_scale = (C & (C - 1)) == 0 ? 1.f / (float)C : 1.f;
-    uint32_t T = 0, ring = 0, ja = 0, jf = 0, jb = 0;
-    int top = 0, bot = 0;
+    uint32_t T = 0, ring = 0, jf = 0, jb = 0, jl = 0;
+    int top = 0, bot = 0, ltop = 0, lbot = 0;
     QPWC_FOR_UNITS
       const int a = (int)(T & 1u);
-      mbar_wait_parked(&afull[a], QPWC_PAR(ja, a));
-      ja ^= 1u << a;
+      tc_wait(afull, T & 1u, spin);
       if (warp == Cfg::W_SPLIT) tc_stamp(T, 2);
-      mbar_wait_parked(&afree[a], QPWC_PAR(jf, a) ^ 1u);  // the MMAs of two tiles ago have finished reading TMEM buffer a
+      tc_wait(&afree[a], QPWC_PAR(jf, a) ^ 1u, spin);  // the MMAs of two tiles ago have finished reading TMEM buffer a
       jf ^= 1u << a;
       tc_fence_after();
       if (!(ablate & 2))
-        a_to_tmem<PXB, 4>(QPWC_ABUF(a), m, tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + a * 64), nks, a_scale);
+        a_to_tmem<PXB, 4>(QPWC_ABUF, m, tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(Cfg::TM_A + a * 64), nks, a_scale);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&arawfree[a]); mbar_arrive(&alo[a]); }
+      if (lane == 0) { mbar_arrive(arawfree); mbar_arrive(&alo[a]); }
       if (warp == Cfg::W_SPLIT) tc_stamp(T, 3);
       for (int hb = (k == 0 ? 0 : 1); hb < 2; ++hb) {
-        const int p = hb ? bot : top;
-        mbar_wait_parked(&bfull[p], QPWC_PAR(jb, p));
+        const int p = hb ? bot : top, l = hb ? lbot : ltop;
+        tc_wait(&bfull[p], QPWC_PAR(jb, p), spin);
         jb ^= 1u << p;
+        tc_wait(&lofree[l], QPWC_PAR(jl, l) ^ 1u, spin);  // the block that held this lo slot (two allocations ago) is dead
+        jl ^= 1u << l;
         if (warp == Cfg::W_SPLIT && hb) tc_stamp(T, 4);
-        if (!(ablate & 2)) split_block(QPWC_BBLK(p), QPWC_BBLK(p) + Cfg::RB_BYTES, Cfg::RB_BYTES, st);
+        if (!(ablate & 2)) split_block(QPWC_BRAW(p), QPWC_BLO(l), Cfg::RB_BYTES, st);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&blo[p]);
+        if (lane == 0) mbar_arrive(&blo[l]);
         if (warp == Cfg::W_SPLIT && hb) tc_stamp(T, 5);
       }
     }}
@@ -594,9 +641,10 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
     const int ew = warp - Cfg::W_EPI, q = warp & 3, part = ew >> 2;
     const float inv_c = (C & (C - 1)) == 0 ? 1.f : 1.f / (float)C;  // power-of-two C: folded into the first-frame operand
     uint32_t T = 0, ring = 0;
-    int top = 0, bot = 0;
+    int top = 0, bot = 0, ltop = 0, lbot = 0;
+    if (tstore && ew == 0 && lane == 0) tma_prefetch_desc(&tmO);
     QPWC_FOR_UNITS
-      tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, T, q, part, ew, lane, out, b, i0, j0, H, W, ops, inv_c, slope, ablate, chb, qo);
+      tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, T, q, part, ew, lane, out, b, i0, j0, H, W, ops, inv_c, slope, ablate, chb, qo, tstore ? &tmO : nullptr, Cfg::NSTG);
     }}
     (void)top; (void)bot;
   }
@@ -604,7 +652,8 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
 #undef QPWC_PAR
 #undef QPWC_FOR_UNITS
 #undef QPWC_ABUF
-#undef QPWC_BBLK
+#undef QPWC_BRAW
+#undef QPWC_BLO
 }
 
 int sm_count_cached();
@@ -635,6 +684,10 @@ int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, in
     if (!make_tmap_nhwc(&tmP, prv, B, H, W, C, Cfg::S_KC, 8, 8)) return QPWC_ERR_CUDA;
     if (!make_tmap_nhwc(&tmN, nxt, B, H, W, C, Cfg::S_KC, Cfg::NCOL, 8)) return QPWC_ERR_CUDA;
   }
+  // output tiles as single tensor stores when the cost volume is dense, d = 4 and W % 8 == 0
+  const int tstore = (d == 4 && ops == Cfg::NDISP && (W & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && !(ablate & 64)) ? 1 : 0;
+  TensorMap tmO = tmP;
+  if (tstore && !make_tmap_cv_tiles(&tmO, out, B, H, W, Cfg::TH)) return QPWC_ERR_CUDA;
   const int smem = resident ? Cfg::R_SMEM_BYTES : Cfg::S_SMEM_BYTES;
   const cudaError_t e = resident
       ? cudaFuncSetAttribute(corr_fwd_tc_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
@@ -651,10 +704,10 @@ int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, in
     const int chb = nwin == 1 ? 0 : (oi + 4) * qo + (oj + 4);
     if (resident)
       corr_fwd_tc_res_kernel<<<nunits < sms ? nunits : sms, Cfg::NTHREADS, smem, stream>>>(
-          tmP, tmN, out, B, H, W, C, slope, ops, tiles_x, tiles_y, seg, nseg, nunits, ablate, oi, oj, chb, qo);
+          tmP, tmN, tmO, tstore, out, B, H, W, C, slope, ops, tiles_x, tiles_y, seg, nseg, nunits, ablate, oi, oj, chb, qo);
     else
       corr_fwd_tc_stream_kernel<<<ntiles < sms ? ntiles : sms, Cfg::NTHREADS, smem, stream>>>(
-          tmP, tmN, out, B, H, W, C, slope, ops, tiles_x, tiles_y, ntiles, ablate, oi, oj, chb, qo);
+          tmP, tmN, tmO, tstore, out, B, H, W, C, slope, ops, tiles_x, tiles_y, ntiles, ablate, oi, oj, chb, qo);
     const int rc = check_launch(resident ? "corr_fwd_tc_res" : "corr_fwd_tc_stream");
     if (rc != QPWC_OK) return rc;
   }
@@ -665,6 +718,7 @@ int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, in
 int launch_corr_fwd_tc(const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t) {
   return QPWC_ERR_UNSUPPORTED;
 }
+
 #endif
 
 }  // namespace qpwc

@@ -506,6 +506,24 @@ bool make_tmap_nhwc(TensorMap* tm, const float* base, int B, int H, int W, int C
   tmap_store(key, tm, 0);
   return true;
 }
+bool make_tmap_cv_tiles(TensorMap* tm, float* out, int B, int H, int W, int th) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = out; key.d[0] = B; key.d[1] = H; key.d[2] = W; key.d[3] = -81; key.d[4] = 216; key.d[5] = 6; key.d[6] = th;
+  if (tmap_lookup(key, tm, 0)) return true;
+  EncodeTiledFn enc = get_encode_fn();
+  bind_primary_context();
+  if (!enc) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available"); return false; }
+  const cuuint64_t gdim[4] = {216, (cuuint64_t)W * 81 / 216, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {216 * 4, (cuuint64_t)W * 81 * 4, (cuuint64_t)H * W * 81 * 4};
+  const cuuint32_t box[4] = {216, 6, (cuuint32_t)th, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error(QPWC_ERR_CUDA, "cuTensorMapEncodeTiled (cost-volume tiles) failed (CUresult %d)", (int)r); return false; }
+  tmap_store(key, tm, 0);
+  return true;
+}
 bool make_tmap_nchw(TensorMap* tm, const float* base, int B, int C, int H, int W, int boxW, int boxH, int boxC) {
   EncodeTiledFn enc = get_encode_fn();
   bind_primary_context();

@@ -154,7 +154,21 @@ class PyramidWorkload:
             self.run_level(k)
         return self.outputs
 
-    def capture(self):
+    def step_concurrent(self, streams):
+        """The same five levels, each on its own stream, forked from and joined back into the current
+        stream: the synthetic levels carry no data dependence on each other, so the launch-bound
+        coarse levels (28 and 112 CTAs) fill SMs the fine levels' tails leave idle.  Finest first."""
+        cur = torch.cuda.current_stream()
+        for k in reversed(range(len(self.levels))):
+            s = streams[k]
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                self.run_level(k)
+        for s in streams:
+            cur.wait_stream(s)
+        return self.outputs
+
+    def capture(self, concurrent=False):
         """Record step() into a CUDA graph (device-resident workloads only): the five launches --
         TMA descriptors included, they are plain kernel parameters -- replay with one
         cudaGraphLaunch, which removes the per-call host overhead from the launch-bound coarse
@@ -169,8 +183,13 @@ class PyramidWorkload:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
+        if concurrent:
+            self._streams = [torch.cuda.Stream() for _ in self.levels]
         with torch.cuda.graph(self._graph):
-            self.step()
+            if concurrent:
+                self.step_concurrent(self._streams)
+            else:
+                self.step()
         return self
 
     def replay(self):

@@ -9,14 +9,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
     ops.set_corr_engine("tc")
     res = []
-    for B, H, W, C in [(8, 224, 512, 32), (8, 224, 512, 16), (8, 112, 256, 64)]:
+    for B, H, W, C in [(8, 224, 512, 32), (8, 112, 256, 64), (8, 28, 64, 256)]:
         prv = torch.randn((B, H, W, C), device="cuda"); nxt = torch.randn((B, H, W, C), device="cuda")
         out = torch.empty((B, H, W, 81), device="cuda")
         res.append(timeit(lambda: ops.cost_volume_into(out, prv, nxt, 4), 10, flush) * 1e6)
     print("  ".join(f"{t:8.1f}" for t in res))
 else:
-    names = {0: "full", 1: "no drain", 16: "no copy-out", 17: "no epilogue", 2: "no split", 4: "no mma", 8: "no loads", 6: "no split+mma",
-             14: "no split+mma+loads", 19: "no epilogue, no split", 23: "only loads", 31: "nothing"}
+    names = {0: "full", 512: "spin waits", 31: "nothing", 31+512: "nothing, spin", 14: "epilogue only", 14+512: "epilogue only, spin", 17: "no epilogue", 17+512: "no epilogue, spin"}
     print(f"{'':28s} 224x512x32  112x256x64  28x64x256  (us)")
     for a, n in names.items():
         env = dict(os.environ, QPWC_ABLATE=str(a))

@@ -4,16 +4,22 @@ import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qpwcnet_b200 import ops, _cabi
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+FUSED = len(sys.argv) > 2 and sys.argv[2] == "fused"
+SIGMA = float(sys.argv[3]) if len(sys.argv) > 3 else 2.0
 prv = torch.randn((8, 224, 512, C), device="cuda"); nxt = torch.randn((8, 224, 512, C), device="cuda")
 out = torch.empty((8, 224, 512, 81), device="cuda")
+flo = torch.randn((8, 224, 512, 2), device="cuda") * SIGMA
+def run():
+    if FUSED: ops.warp_cost_volume_into(out, prv, nxt, flo, "tfa", 4)
+    else: ops.cost_volume_into(out, prv, nxt, 4)
 ops.set_corr_engine("tc")
 for _ in range(3):
-    ops.cost_volume_into(out, prv, nxt, 4)
+    run()
 buf = torch.zeros(40 * 24, dtype=torch.int64, device="cuda")
 L = _cabi.lib()
 L.qpwc_debug_tc_trace.argtypes = [ctypes.c_void_p]
 assert L.qpwc_debug_tc_trace(buf.data_ptr()) == 0
-ops.cost_volume_into(out, prv, nxt, 4)
+run()
 torch.cuda.synchronize()
 L.qpwc_debug_tc_trace(None)
 t = buf.cpu().view(40, 24)
