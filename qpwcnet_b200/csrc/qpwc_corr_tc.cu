@@ -404,23 +404,24 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
           const int s = (int)(g % Cfg::NST);
           // the passes that read only the raw second-frame words (hi.hi, lo.hi) go out as soon as the
           // first-frame operand is in TMEM; the elementwise lo of the 24 KB second-frame block is
-          // computed by the split warps meanwhile, and the hi.lo pass follows.  (Measured and dropped:
-          // half-major order inside a stage, to publish half 0 early and overlap the accumulator drain,
-          // is 3-5 us SLOWER at every streaming level.)
+          // computed by the split warps meanwhile, and the hi.lo pass follows
           mbar_wait(&raw_full[s], (g / Cfg::NST) & 1u);
           mbar_wait(&a_full[s], (g / Cfg::NST) & 1u);
           tc_fence_after();
           const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_SB(s))), d_lo = d_raw + (uint64_t)(Cfg::SB_BYTES >> 4);
           const uint32_t a_tm = tmem + (uint32_t)(Cfg::TM_A + s * 32);
           const int nks = min(2, (C - c * Cfg::S_KC) / 8);
+          // consecutive MMAs alternate between the two accumulator halves (back-to-back MMAs into the same
+          // accumulator serialise on it: half-major order inside a stage measured 3-5 us slower per level)
           if (!(ablate & 4))
             for (int ks = 0; ks < nks; ++ks)
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint64_t off = (uint64_t)((h * (Cfg::SB_BYTES / 2) + ks * 32) >> 4);
-                umma_tf32_ts(tmem + (uint32_t)(h * Cfg::NHALF), a_tm + ks * 16, d_raw + off, (c | ks) ? 1u : 0u);
-                umma_tf32_ts(tmem + (uint32_t)(h * Cfg::NHALF), a_tm + ks * 16 + 8, d_raw + off, 1u);
-              }
+              for (int ps = 0; ps < 2; ++ps)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const uint64_t off = (uint64_t)((h * (Cfg::SB_BYTES / 2) + ks * 32) >> 4);
+                  umma_tf32_ts(tmem + (uint32_t)(h * Cfg::NHALF), a_tm + ks * 16 + ps * 8, d_raw + off, (c | ks | ps) ? 1u : 0u);
+                }
           mbar_wait(&lo_full[s], (g / Cfg::NST) & 1u);
           tc_fence_after();
           if (!(ablate & 4))

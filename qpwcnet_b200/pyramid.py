@@ -147,7 +147,9 @@ class PyramidWorkload:
         (five C-ABI launches on the current stream)."""
         if not self.outputs[0].is_cuda:
             with ops.host_batch():      # host buffers: let the five levels' copies/kernels overlap
-                for k in range(len(self.levels)):
+                # finest level first: the D2H engine can start after ONE slice of input has arrived, and the
+                # slices that are still on the wire when the H2D engine falls idle are the small coarse ones
+                for k in reversed(range(len(self.levels))):
                     self.run_level(k)
             return self.outputs
         for k in range(len(self.levels)):

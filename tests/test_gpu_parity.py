@@ -110,6 +110,34 @@ def test_cost_volume_tensor_core_engine(B, H, W, C, d):
     assert torch.isnan(buf[..., D:]).all()
 
 
+@pytest.mark.parametrize("W", [16, 40, 56, 20, 36, 18, 33])
+@pytest.mark.parametrize("C", [16, 72])
+def test_tensor_core_copy_out_routes(W, C):
+    """The three ways a staged output tile leaves the tensor-core kernels -- one TMA tensor store
+    (W % 8 == 0, incl. a last tile 8 columns wide, clipped by the engine), per-row bulk copies
+    (W % 4 == 0), coalesced scalar copies (any W) -- at ragged heights, several tiles per CTA (two
+    staging images in the resident kernel), against the oracle, with guard rows around the output."""
+    ops.set_corr_engine("tc")
+    B, H = 3, 21
+    r = rng(W * 31 + C)
+    prv = r.standard_normal((B, H, W, C)).astype(np.float32)
+    nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
+    ref = oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), 4)
+    guard = torch.full((B + 2, H, W, 81), float("nan"), device=DEV)
+    ops.cost_volume_into(guard[1:B + 1], dev(prv), dev(nxt), 4)
+    assert_rel(host(guard[1:B + 1]), ref)
+    assert torch.isnan(guard[0]).all() and torch.isnan(guard[B + 1]).all()
+    # a large map: every CTA walks many tiles, so both staging images are recycled
+    B2, H2, W2 = 2, 136, 328 if W % 8 == 0 else (324 if W % 4 == 0 else 323)
+    prv = r.standard_normal((B2, H2, W2, C)).astype(np.float32)
+    nxt = r.standard_normal((B2, H2, W2, C)).astype(np.float32)
+    got = host(ops.cost_volume(dev(prv), dev(nxt), 4))
+    ops.set_corr_engine("ffma")
+    want = host(ops.cost_volume(dev(prv), dev(nxt), 4))
+    ops.set_corr_engine("auto")
+    assert np.abs(got - want).max() <= 4e-6 * np.abs(want).max()
+
+
 @pytest.mark.parametrize("B,H,W,C,d", [(4, 32, 64, 3, 4), (1, 28, 64, 256, 4), (1, 40, 72, 32, 4),
                                        (1, 17, 19, 16, 4), (1, 9, 9, 5, 4), (1, 12, 13, 6, 2),
                                        (1, 20, 30, 32, 8),

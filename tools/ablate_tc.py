@@ -15,7 +15,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         res.append(timeit(lambda: ops.cost_volume_into(out, prv, nxt, 4), 10, flush) * 1e6)
     print("  ".join(f"{t:8.1f}" for t in res))
 else:
-    names = {0: "full", 512: "spin waits", 31: "nothing", 31+512: "nothing, spin", 14: "epilogue only", 14+512: "epilogue only, spin", 17: "no epilogue", 17+512: "no epilogue, spin"}
+    names = {0: "full", 64: "per-row bulk copies instead of the tensor store", 1: "no drain", 16: "no copy-out", 17: "no epilogue", 2: "no split", 4: "no mma", 8: "no loads", 14: "epilogue only", 23: "only loads", 31: "nothing"}
     print(f"{'':28s} 224x512x32  112x256x64  28x64x256  (us)")
     for a, n in names.items():
         env = dict(os.environ, QPWC_ABLATE=str(a))
