@@ -239,8 +239,13 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
   // accesses of the kernels, TMA) whatever the tensor sizes are
   auto pad4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
   const size_t item = (n_a + n_b + n_f + n_o) * sizeof(float);
-  // slice the batch so that one slice moves >= ~8 MiB (amortises per-slice launch/copy latency)
-  int per = (int)((((size_t)8 << 20) + item - 1) / item);
+  // slice the batch so that one slice moves >= ~128 MiB: every copy costs the DMA engines ~10 us of dead time,
+  // and with 8 MiB slices (round 1) the 100 copies of a config-2 step added 1 ms to an 11.8 ms step
+  // (tools/e2e_probe.py, one box: 8 MiB 11.76 ms, 32 MiB 10.84, 70 MiB 10.75, 600 MiB 12.26; another, with the half-sized
+  // first slice: 32 MiB 11.31, 64 MiB 10.88, 96 MiB 10.58, 140 MiB 10.53).  The FIRST slice of a
+  // call is half as large: the D2H engine idles until it has been copied in and computed.
+  static const size_t slice_mb = [] { const char* ev = getenv("QPWC_HOST_SLICE_MB"); const long v = ev ? atol(ev) : 0; return (size_t)(v > 0 ? v : 128); }();
+  int per = (int)(((slice_mb << 20) + item - 1) / item);
   if (per < 1) per = 1;
   if (per > B) per = B;
   HostStage& hs = g_stage[device];
@@ -249,8 +254,9 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
   const bool l2pair = kind == 2 && tc_wanted(g_corr_engine.load(std::memory_order_relaxed), d) && (d == 4 || d == 8) && C >= 8 && (C & 7) == 0;
   const size_t n_w = l2pair ? n_a : 0;  // warped second frame of a slice (tensor-core engine: warp + cost volume)
   const size_t slot_floats = pad4(n_a * per) + pad4(n_b * per) + pad4(n_f * per) + pad4(n_o * per) + pad4(n_w * per);
-  for (int b0 = 0; b0 < B && rc == QPWC_OK; b0 += per, slot = (slot + 1) % HostStage::NSLOT) {
-    const int nb = (B - b0 < per) ? (B - b0) : per;
+  for (int b0 = 0, nb = 0; b0 < B && rc == QPWC_OK; b0 += nb, slot = (slot + 1) % HostStage::NSLOT) {
+    nb = b0 == 0 ? (per + 1) / 2 : per;
+    if (nb > B - b0) nb = B - b0;
     rc = stage_reserve(hs, slot, slot_floats * sizeof(float));
     if (rc != QPWC_OK) break;
     cudaStream_t st = hs.stream[slot];
