@@ -287,6 +287,9 @@ def run_native(args):
     value = BATCH * world / (ms_per_step * 1e-3)
 
     # ---- e2e: public API with pinned host buffers, H2D + kernels + D2H inside the timed region
+    # (the thread is bound to the GPU's NUMA node while the pinned buffers are allocated and driven:
+    # staging pages on the other socket cost a factor 2-3 in copy rate; undone for the CPU baseline leg)
+    old_affinity = ops.bind_host_thread_near(dev)
     wl_h = PyramidWorkload(HEIGHT, WIDTH, BATCH, SEARCH, device="cpu", seed=rank)
     Ke = max(3, min(K, 20))
     for _ in range(2):
@@ -328,7 +331,9 @@ def run_native(args):
                     "note": "floor = the larger of the step's H2D / D2H bytes at the full-duplex rate of the FASTEST rank, "
                             "measured in this run with every rank copying at once"},
            "d2h_bytes_per_step": wl_h.d2h_bytes(), "steps": Ke, "ms_per_step": e2e_s * 1e3,
-           "path": "ops.*_into(pinned host tensors) -> qpwc_*_host (6-slot H2D/kernel/D2H pipeline)"}
+           "path": "ops.*_into(pinned host tensors) -> qpwc_*_host (6-slot H2D/kernel/D2H pipeline, 128 MiB slices, finest level first)",
+           "host_thread": ("bound to the %d CPUs NVML reports as local to the GPU" % len(os.sched_getaffinity(0)))
+                          if old_affinity is not None else "not bound (NVML affinity unavailable)"}
 
     # ---- roofline of the dominant kernel (finest fused level)
     peak, peak_src = load_peaks()
@@ -454,6 +459,8 @@ def run_native(args):
         }
         del th
 
+    if old_affinity is not None:
+        os.sched_setaffinity(0, old_affinity)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t_cpu, cores, _ = cpu_reference_step(1, repeats=2)

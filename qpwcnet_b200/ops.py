@@ -752,3 +752,31 @@ def get_corr_engine() -> str:
 
 def library_version() -> int:
     return int(lib().qpwc_version())
+
+
+def bind_host_thread_near(device=None):
+    """Pin the calling thread to the CPUs NVML reports as local to ``device`` (its NUMA node), so that
+    pinned host buffers allocated afterwards are first-touched next to the GPU's PCIe root.  Host-buffer
+    throughput (``*_host`` entry points) drops 2-3x when the staging pages land on the other socket.
+    Best effort: returns the previous affinity set (pass it to ``os.sched_setaffinity(0, ...)`` to undo),
+    or None when NVML / the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(idx).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None

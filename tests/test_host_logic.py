@@ -119,3 +119,16 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "libqpwc_emu" not in src and "libqpwc_oracle" not in src, f
+
+
+def test_bind_host_thread_near_is_best_effort():
+    """No GPU / no NVML: the affinity helper must return None and leave the affinity untouched."""
+    import os
+
+    from qpwcnet_b200 import ops
+    before = os.sched_getaffinity(0)
+    old = ops.bind_host_thread_near(0)
+    assert old is None or isinstance(old, set)
+    if old is not None:
+        os.sched_setaffinity(0, old)
+    assert os.sched_getaffinity(0) == before

@@ -13,5 +13,6 @@ for _ in range(10):
     wl.step()
     _ = float(wl.outputs[0][0, 0, 0, 0])
     ts.append(time.perf_counter() - t0)
+print(" ".join(f"{t*1e3:.1f}" for t in ts))
 ts.sort()
 print(f"slice {os.environ.get('QPWC_HOST_SLICE_MB', '8')} MiB: median {ts[5]*1e3:.2f} ms  min {ts[0]*1e3:.2f} ms  -> {8/ts[5]:.0f} pairs/s")
