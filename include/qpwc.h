@@ -68,6 +68,10 @@ const char* qpwc_last_error(void);
  * registers (the faster one on B200); 2: per-tile pre-aggregation in shared memory before the global
  * atomics (C % 32 == 0; measured 2.5x slower: shared-memory float atomics retire ~1 lane/clk/SM). */
 #define QPWC_OPT_WARP_BWD 1
+/* QPWC_OPT_CORR_BWD: cost-volume gradient kernels -- 0 auto (register-tiled kernel where its domain allows:
+   d == 4, C % 4 == 0, 16-byte aligned tensors) / 1: the shape-generic untiled kernels everywhere (a second
+   summation order of the same sums; used by the tests). */
+#define QPWC_OPT_CORR_BWD 2
 int qpwc_set_option(int key, int value);
 int qpwc_get_option(int key); /* -1 for an unknown key */
 

@@ -81,6 +81,9 @@ static int check_mode(const char* fn, int mode, int H, int W) {
 // kernels only (plain fp32 arithmetic), 2 = tensor cores (3xTF32 split) or fail
 static std::atomic<int> g_corr_engine{0};
 void set_warp_bwd_variant(int);   // qpwc_warp.cu
+static std::atomic<int> g_corr_bwd_variant{0};   // QPWC_OPT_CORR_BWD
+void set_corr_bwd_variant(int v) { g_corr_bwd_variant.store(v); }
+int get_corr_bwd_variant() { return g_corr_bwd_variant.load(std::memory_order_relaxed); }
 int get_warp_bwd_variant();
 
 // Engine policy.  AUTO takes the tensor-core kernels for search range 4 only: range 8 runs there as four
@@ -315,9 +318,12 @@ int qpwc_version(void) { return 200; /* 0.2.0 */ }
 int qpwc_set_option(int key, int value) {
   if (key == QPWC_OPT_CORR_ENGINE && value >= 0 && value <= 2) { g_corr_engine.store(value); return QPWC_OK; }
   if (key == QPWC_OPT_WARP_BWD && value >= 0 && value <= 2) { set_warp_bwd_variant(value); return QPWC_OK; }
+  if (key == QPWC_OPT_CORR_BWD && value >= 0 && value <= 1) { set_corr_bwd_variant(value); return QPWC_OK; }
   return set_error(QPWC_ERR_INVALID, "qpwc_set_option: unknown key %d or value %d", key, value);
 }
-int qpwc_get_option(int key) { return key == QPWC_OPT_CORR_ENGINE ? g_corr_engine.load() : (key == QPWC_OPT_WARP_BWD ? get_warp_bwd_variant() : -1); }
+int qpwc_get_option(int key) {
+  return key == QPWC_OPT_CORR_ENGINE ? g_corr_engine.load() : (key == QPWC_OPT_WARP_BWD ? get_warp_bwd_variant() : (key == QPWC_OPT_CORR_BWD ? get_corr_bwd_variant() : -1));
+}
 int qpwc_host_set_deferred(int on) { g_host_deferred = on != 0; return QPWC_OK; }
 int qpwc_host_sync(int device) { return host_sync(device); }
 const char* qpwc_last_error(void) { return g_err; }

@@ -250,6 +250,8 @@ corr_bwd_tiled_kernel(const float* __restrict__ prv, const float* __restrict__ n
 }
 #endif  // !QPWC_EMU
 
+int get_corr_bwd_variant();   // qpwc_api.cu (QPWC_OPT_CORR_BWD: 0 auto, 1 untiled kernels everywhere)
+
 int launch_corr_bwd_tiled(const float* prv, const float* nxt, const float* out, const float* g_out,
                           float* g_prv, float* g_nxt, int B, int H, int W, int C, int d, float slope,
                           long long ops, cudaStream_t stream) {
@@ -258,8 +260,7 @@ int launch_corr_bwd_tiled(const float* prv, const float* nxt, const float* out, 
   if (d != 4 || (C & 3) || C < 4) return QPWC_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(prv) | reinterpret_cast<uintptr_t>(nxt) |
        reinterpret_cast<uintptr_t>(g_prv) | reinterpret_cast<uintptr_t>(g_nxt)) & 15) return QPWC_ERR_UNSUPPORTED;
-  const char* var = getenv("QPWC_CORR_BWD_VARIANT");  // dev/tests: "direct" forces the untiled kernels
-  if (var && var[0] == 'd') return QPWC_ERR_UNSUPPORTED;
+  if (get_corr_bwd_variant() == 1) return QPWC_ERR_UNSUPPORTED;  // QPWC_OPT_CORR_BWD: untiled kernels forced
   const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH), ncb = cdiv(C, CB);
   if (ncb > 65535 || B > 65535) return QPWC_ERR_UNSUPPORTED;
   if (((long long)(TH - 1) * W + XW) * ops + Q >= (1LL << GOFF_BITS)) return QPWC_ERR_UNSUPPORTED;  // table entry range

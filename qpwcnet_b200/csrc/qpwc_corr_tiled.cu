@@ -475,15 +475,15 @@ static void bind_primary_context() {
 // called in a loop with the same tensors pays the two driver calls once, and there is no shared state.
 struct TmapKey { const void* base; int d[7]; };
 struct TmapEntry { TmapKey key; TensorMap tm; bool valid; };
-static thread_local TmapEntry g_tmap_cache[8];
+static thread_local TmapEntry g_tmap_cache[32];   // a pyramid step encodes 15 distinct maps (3 per cost volume)
 static thread_local unsigned g_tmap_next = 0;
 static bool tmap_lookup(const TmapKey& k, TensorMap* tm, int) {
-  for (int e = 0; e < 8; ++e)
+  for (int e = 0; e < 32; ++e)
     if (g_tmap_cache[e].valid && memcmp(&g_tmap_cache[e].key, &k, sizeof(k)) == 0) { *tm = g_tmap_cache[e].tm; return true; }
   return false;
 }
 static void tmap_store(const TmapKey& k, const TensorMap* tm, int) {
-  TmapEntry& slot = g_tmap_cache[g_tmap_next++ & 7u];
+  TmapEntry& slot = g_tmap_cache[g_tmap_next++ & 31u];
   slot.key = k; slot.tm = *tm; slot.valid = true;
 }
 

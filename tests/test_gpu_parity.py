@@ -169,8 +169,14 @@ def test_cost_volume_backward_tiled_matches_direct(monkeypatch):
     out = ops.cost_volume(prv, nxt, 4)
     g = dev(r.standard_normal((B, H, W, 81)))
     gp, gn = ops._corr_bwd(prv, nxt, out, g, 4, 0.1)
-    monkeypatch.setenv("QPWC_CORR_BWD_VARIANT", "direct")
-    gp2, gn2 = ops._corr_bwd(prv, nxt, out, g, 4, 0.1)
+    from qpwcnet_b200 import _cabi
+    L = _cabi.lib()
+    assert L.qpwc_set_option(2, 1) == 0          # QPWC_OPT_CORR_BWD: the untiled kernels everywhere
+    try:
+        gp2, gn2 = ops._corr_bwd(prv, nxt, out, g, 4, 0.1)
+    finally:
+        L.qpwc_set_option(2, 0)
+    assert L.qpwc_get_option(2) == 0
     for a, b in ((gp, gp2), (gn, gn2)):
         assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())
 

@@ -34,16 +34,17 @@ def _shapes(seed, n, cmul):
     return out
 
 
-@pytest.mark.parametrize("variant", ["default", "packed", "rowpair"])
-def test_random_cost_volume_forward(variant, monkeypatch):
-    monkeypatch.setenv("QPWC_CORR_VARIANT", variant)
+@pytest.mark.parametrize("engine", ["auto", "ffma"])
+def test_random_cost_volume_forward(engine):
+    ops.set_corr_engine(engine)
     for (B, H, W, C) in _shapes(11, 14, 4) + _shapes(12, 6, 1):
         r = np.random.default_rng(B * 7 + H * 13 + W * 17 + C)
         prv = r.standard_normal((B, H, W, C)).astype(np.float32)
         nxt = r.standard_normal((B, H, W, C)).astype(np.float32)
         ref = oracle.cost_volume(prv.astype(np.float64), nxt.astype(np.float64), 4)
         got = host(ops.cost_volume(dev(prv), dev(nxt), 4))
-        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max(), (variant, B, H, W, C)
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max(), (engine, B, H, W, C)
+    ops.set_corr_engine("auto")
 
 
 def test_random_cost_volume_backward():
