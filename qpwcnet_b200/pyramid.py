@@ -184,17 +184,22 @@ class PyramidWorkload:
                 self.step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph()
         if concurrent:
             self._streams = [torch.cuda.Stream() for _ in self.levels]
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(graph):
             if concurrent:
                 self.step_concurrent(self._streams)
             else:
                 self.step()
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        self._graphs["branches" if concurrent else "serial"] = graph
+        self._graph = graph
         return self
 
-    def replay(self):
-        self._graph.replay()
+    def replay(self, which=None):
+        """Replay the most recently captured graph, or the one named 'serial' / 'branches'."""
+        (self._graph if which is None else self._graphs[which]).replay()
         return self.outputs
 

@@ -138,6 +138,25 @@ def test_tensor_core_copy_out_routes(W, C):
     assert np.abs(got - want).max() <= 4e-6 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("B,H,W,C", [(8, 224, 512, 32), (8, 112, 256, 64), (3, 100, 200, 24)])
+def test_tensor_core_kernels_are_deterministic_under_repetition(B, H, W, C):
+    """Race detector for the barrier protocol of the tensor-core kernels (operand rings, two staging
+    images, TMEM hand-over): 25 launches on the same inputs, interleaved with launches on other inputs,
+    must produce bit-identical outputs."""
+    ops.set_corr_engine("tc")
+    g = torch.Generator(device=DEV).manual_seed(B * H + C)
+    prv = torch.randn((B, H, W, C), device=DEV, generator=g)
+    nxt = torch.randn((B, H, W, C), device=DEV, generator=g)
+    other = torch.randn((B, H, W, C), device=DEV, generator=g)
+    first = ops.cost_volume(prv, nxt, 4)
+    scratch = torch.empty_like(first)
+    for it in range(25):
+        if it % 3 == 0:
+            ops.cost_volume_into(scratch, other, prv, 4)
+        again = ops.cost_volume(prv, nxt, 4)
+        assert torch.equal(first, again), f"iteration {it}: outputs differ"
+
+
 @pytest.mark.parametrize("B,H,W,C,d", [(4, 32, 64, 3, 4), (1, 28, 64, 256, 4), (1, 40, 72, 32, 4),
                                        (1, 17, 19, 16, 4), (1, 9, 9, 5, 4), (1, 12, 13, 6, 2),
                                        (1, 20, 30, 32, 8),
