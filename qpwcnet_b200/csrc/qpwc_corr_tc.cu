@@ -42,9 +42,9 @@ namespace qpwc {
 // hand-over points of its first QPWC_TRACE_TILES tiles: g_tc_trace[tile * 24 + event]
 #define QPWC_TRACE_TILES 40
 __device__ long long* g_tc_trace = nullptr;
-__device__ __forceinline__ void tc_stamp(uint32_t tile, int ev) {
-  long long* t = g_tc_trace;
-  if (t != nullptr && blockIdx.x == 0 && tile < QPWC_TRACE_TILES) t[tile * 24 + ev] = clock64();
+// (`t` = g_tc_trace read ONCE per thread at kernel start: a load per stamp stalled the issuing threads ~40 clk each)
+__device__ __forceinline__ void tc_stamp(long long* t, uint32_t tile, int ev) {
+  if (t != nullptr && tile < QPWC_TRACE_TILES) t[tile * 24 + ev] = clock64();
 }
 
 // dev (QPWC_ABLATE bit 9): spin instead of parking on the role hand-over barriers
@@ -181,7 +181,7 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
                                                  uint32_t tcount, int q, int part, int ew, int lane,
                                                  float* __restrict__ out, int b, int i0, int j0, int H, int W,
                                                  long long ops, float inv_c, float slope, int ablate, int chb, int qo,
-                                                 const TensorMap* tmO, int nstg) {
+                                                 const TensorMap* tmO, int nstg, long long* trace) {
   // chb / qo: first output channel and channel pitch of a displacement row.  d = 4: (0, 9), the 81
   // results of a pixel are contiguous.  d = 8 runs as four 9x9 windows of the 17x17 range: qo = 17,
   // chb = (oi + 4) * 17 + (oj + 4) for the window offset (oi, oj) in {-4, +4}^2.
@@ -199,7 +199,7 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
   const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((rb * 4 + y0) * Cfg::NCOL + cb * 8);
   tc_wait(&tfull[h], tcount & 1u, spin);
   tc_fence_after();
-  if (ew == 0) tc_stamp(tcount, 10); else if (ew == 8) tc_stamp(tcount, 15);
+  if (ew == 0) tc_stamp(trace, tcount, 10); else if (ew == 8) tc_stamp(trace, tcount, 15);
   // all four rows of this warp's share into registers first: the accumulator half is released as soon
   // as the loads have landed, before the shifting and staging work
   uint32_t u[4][16];
@@ -211,7 +211,7 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(&tempty[h]);        // this half of the accumulator may be overwritten
-  if (ew == 0) tc_stamp(tcount, 11); else if (ew == 8) tc_stamp(tcount, 16);
+  if (ew == 0) tc_stamp(trace, tcount, 11); else if (ew == 8) tc_stamp(trace, tcount, 16);
   // the bulk stores of the previous tile must have finished reading the staging image (waited for
   // here, after the accumulator loads, so that the engine's reads overlap the wait for the MMAs)
   // (one lane issues and tracks the stores; the others learn through `sfree`, so a warp that has its
@@ -221,7 +221,7 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
     mbar_arrive(sfree);
   }
   mbar_wait(sfree, tcount & 1u);
-  if (ew == 0) tc_stamp(tcount, 12);
+  if (ew == 0) tc_stamp(trace, tcount, 12);
   if (!(ablate & 1)) {
 #pragma unroll
     for (int yy = 0; yy < 4; ++yy) {
@@ -248,9 +248,9 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
     }
   }
   fence_proxy_async();                           // staging stores -> bulk-store (async proxy) reads
-  if (ew == 0) tc_stamp(tcount, 13); else if (ew == 8) tc_stamp(tcount, 17);
+  if (ew == 0) tc_stamp(trace, tcount, 13); else if (ew == 8) tc_stamp(trace, tcount, 17);
   named_bar_sync(2, Cfg::NEPI * 32);             // all pixel blocks staged
-  if (ew == 0) tc_stamp(tcount, 14);
+  if (ew == 0) tc_stamp(trace, tcount, 14);
   if (ablate & 16) return;
   const int wv = min(Cfg::TW, W - j0);
   const bool bulk = ops == Cfg::NDISP && qo == 9 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
@@ -469,7 +469,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int tx = tile % tiles_x, rest = tile / tiles_x, ty = rest % tiles_y, b = rest / tiles_y;
       tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, tcount, q, part, ew, lane, out, b, ty * Cfg::TH, tx * Cfg::TW,
-                       H, W, ops, inv_c, slope, ablate, chb, qo, tstore ? &tmO : nullptr, 1);
+                       H, W, ops, inv_c, slope, ablate, chb, qo, tstore ? &tmO : nullptr, 1, nullptr);
     }
   }
   tc_teardown(tmem, warp);
@@ -512,6 +512,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* staging = reinterpret_cast<float*>(smem + Cfg::R_OFF_STAGING);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, spin = (ablate >> 9) & 1;
+  long long* const trace = blockIdx.x == 0 ? g_tc_trace : nullptr;
   const int nks = C / 8;           // K steps (<= 4); channels C..31 of the 128-byte rows are TMA zero fill
   const uint32_t tmem = tc_prologue(bars, 14, 5, 2, tmem_slot, smem, tid, warp);
 #define QPWC_ABUF (smem + Cfg::R_OFF_A)
@@ -542,7 +543,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
       int top = 0, bot = 0, ltop = 0, lbot = 0;
       QPWC_FOR_UNITS
         tc_wait(arawfree, (T & 1u) ^ 1u, spin);  // the landing buffer has been moved to TMEM
-        tc_stamp(T, 0);
+        tc_stamp(trace, T, 0);
         if (ablate & 8) mbar_arrive(afull);
         else {
           mbar_arrive_expect_tx(afull, Cfg::RA_BYTES);
@@ -555,7 +556,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
           const int p = hb ? bot : top;
           tc_wait(&bfree[p], QPWC_PAR(ub, p) ^ 1u, spin);
           ub ^= 1u << p;
-          if (hb) tc_stamp(T, 1);
+          if (hb) tc_stamp(trace, T, 1);
           if (ablate & 8) { mbar_arrive(&bfull[p]); continue; }
           mbar_arrive_expect_tx(&bfull[p], Cfg::RB_BYTES);
           tma_load_4d(QPWC_BRAW(p), &tmN, &bfull[p], 0, j0 - 4 + oj, i0 - 4 + oi + hb * 8, b);
@@ -574,7 +575,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
         if (k == 0) { mbar_wait(&blo[ltop], QPWC_PAR(mb, ltop)); mb ^= 1u << ltop; }  // k > 0: waited for as `bot` of tile k-1
         mbar_wait(&tempty[0], (T & 1u) ^ 1u);
         tc_fence_after();
-        tc_stamp(T, 6);
+        tc_stamp(trace, T, 6);
         {
           const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_BRAW(top))), d_lo = umma_desc<PXB>(smem_u32(QPWC_BLO(ltop)));
           if (!(ablate & 4))
@@ -583,13 +584,13 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
           umma_commit(&tfull[0]);
           umma_commit(&bfree[top]);     // the upper block is dead once these MMAs have read it
           umma_commit(&lofree[ltop]);
-          tc_stamp(T, 7);
+          tc_stamp(trace, T, 7);
         }
         mbar_wait(&blo[lbot], QPWC_PAR(mb, lbot));
         mb ^= 1u << lbot;
         mbar_wait(&tempty[1], (T & 1u) ^ 1u);
         tc_fence_after();
-        tc_stamp(T, 8);
+        tc_stamp(trace, T, 8);
         {
           const uint64_t d_raw = umma_desc<PXB>(smem_u32(QPWC_BRAW(bot))), d_lo = umma_desc<PXB>(smem_u32(QPWC_BLO(lbot)));
           if (!(ablate & 4))
@@ -598,7 +599,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
           umma_commit(&tfull[1]);
           umma_commit(&afree[a]);
           if (k == nt - 1) { umma_commit(&bfree[bot]); umma_commit(&lofree[lbot]); }  // end of the segment: nobody inherits the lower block
-          tc_stamp(T, 9);
+          tc_stamp(trace, T, 9);
         }
       }}
     }
@@ -613,7 +614,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
     QPWC_FOR_UNITS
       const int a = (int)(T & 1u);
       tc_wait(afull, T & 1u, spin);
-      if (warp == Cfg::W_SPLIT) tc_stamp(T, 2);
+      if (warp == Cfg::W_SPLIT) tc_stamp(trace, T, 2);
       tc_wait(&afree[a], QPWC_PAR(jf, a) ^ 1u, spin);  // the MMAs of two tiles ago have finished reading TMEM buffer a
       jf ^= 1u << a;
       tc_fence_after();
@@ -622,19 +623,19 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(arawfree); mbar_arrive(&alo[a]); }
-      if (warp == Cfg::W_SPLIT) tc_stamp(T, 3);
+      if (warp == Cfg::W_SPLIT) tc_stamp(trace, T, 3);
       for (int hb = (k == 0 ? 0 : 1); hb < 2; ++hb) {
         const int p = hb ? bot : top, l = hb ? lbot : ltop;
         tc_wait(&bfull[p], QPWC_PAR(jb, p), spin);
         jb ^= 1u << p;
         tc_wait(&lofree[l], QPWC_PAR(jl, l) ^ 1u, spin);  // the block that held this lo slot (two allocations ago) is dead
         jl ^= 1u << l;
-        if (warp == Cfg::W_SPLIT && hb) tc_stamp(T, 4);
+        if (warp == Cfg::W_SPLIT && hb) tc_stamp(trace, T, 4);
         if (!(ablate & 2)) split_block(QPWC_BRAW(p), QPWC_BLO(l), Cfg::RB_BYTES, st);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&blo[l]);
-        if (warp == Cfg::W_SPLIT && hb) tc_stamp(T, 5);
+        if (warp == Cfg::W_SPLIT && hb) tc_stamp(trace, T, 5);
       }
     }}
   } else {  // --------------------------------------------------------------------------- epilogue
@@ -645,7 +646,7 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
     int top = 0, bot = 0, ltop = 0, lbot = 0;
     if (tstore && ew == 0 && lane == 0) tma_prefetch_desc(&tmO);
     QPWC_FOR_UNITS
-      tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, T, q, part, ew, lane, out, b, i0, j0, H, W, ops, inv_c, slope, ablate, chb, qo, tstore ? &tmO : nullptr, Cfg::NSTG);
+      tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, T, q, part, ew, lane, out, b, i0, j0, H, W, ops, inv_c, slope, ablate, chb, qo, tstore ? &tmO : nullptr, Cfg::NSTG, trace);
     }}
     (void)top; (void)bot;
   }
