@@ -182,7 +182,8 @@ static int warp_corr_fwd_l2(const float* prv, const float* nxt, const float* flo
   for (int b0 = 0; b0 < B && rc == QPWC_OK; b0 += per) {
     const int nb = B - b0 < per ? B - b0 : per;
     rc = launch_warp_fwd_ex(nxt + item * b0, flow + fitem * b0, nullptr, nullptr, scratch, nb, H, W, C, mode, 1.f, C, st, up_scale);
-    if (rc == QPWC_OK) rc = launch_corr_fwd_tc(prv + item * b0, scratch, out + (size_t)H * W * ops * b0, nb, H, W, C, d, slope, ops, st);
+    // (cost volume of the scratch: tensor cores inside their domain, the FFMA kernels elsewhere)
+    if (rc == QPWC_OK) rc = corr_fwd_any(prv + item * b0, scratch, nullptr, 0, out + (size_t)H * W * ops * b0, nb, H, W, C, d, slope, ops, st);
   }
   e = scratch_free(scratch, st);
   if (rc == QPWC_OK && e != cudaSuccess) rc = set_error(QPWC_ERR_CUDA, "warp_corr_fwd: scratch free: %s", cudaGetErrorString(e));
@@ -192,8 +193,12 @@ static int warp_corr_fwd_l2(const float* prv, const float* nxt, const float* flo
 static int warp_corr_fwd_any(const float* prv, const float* nxt, const float* flow, int mode, float* out, int B,
                              int H, int W, int C, int d, float slope, long long ops, cudaStream_t st, float up_scale = 0.f) {
   const int engine = g_corr_engine.load(std::memory_order_relaxed);
-  if (tc_wanted(engine, d) && tc_domain(prv, nxt, C, d)) return warp_corr_fwd_l2(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);
-  if (engine == 2) return set_error(QPWC_ERR_UNSUPPORTED, "warp_corr_fwd: tensor-core engine needs search_range 4 or 8, C %% 8 == 0 and 16-byte aligned inputs");
+  if (engine == 2 && !(tc_wanted(engine, d) && tc_domain(prv, nxt, C, d)))
+    return set_error(QPWC_ERR_UNSUPPORTED, "warp_corr_fwd: tensor-core engine needs search_range 4 or 8, C %% 8 == 0 and 16-byte aligned inputs");
+  // AUTO: warp kernel + cost-volume kernel through the call's scratch at every shape -- the in-kernel FFMA
+  // fusion is slower than the pair of kernels at every level measured (profiles/r02b_levels.txt; 48 vs 22 us
+  // at 8x7x16x196, profiles/r02c_cfg4_sweep.json) and stays the pair of the explicitly selected FFMA engine
+  if (engine != 1) return warp_corr_fwd_l2(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);
   return corr_fwd_any(prv, nxt, flow, mode, out, B, H, W, C, d, slope, ops, st, up_scale);  // in-kernel fusion (FFMA)
 }
 
@@ -254,7 +259,7 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
   HostStage& hs = g_stage[device];
   std::lock_guard<std::mutex> lock(hs.mu);
   int rc = QPWC_OK, slot = hs.next_slot;
-  const bool l2pair = kind == 2 && tc_wanted(g_corr_engine.load(std::memory_order_relaxed), d) && (d == 4 || d == 8) && C >= 8 && (C & 7) == 0;
+  const bool l2pair = kind == 2 && g_corr_engine.load(std::memory_order_relaxed) != 1;  // warp kernel + cost-volume kernel (see warp_corr_fwd_any)
   const size_t n_w = l2pair ? n_a : 0;  // warped second frame of a slice (tensor-core engine: warp + cost volume)
   const size_t slot_floats = pad4(n_a * per) + pad4(n_b * per) + pad4(n_f * per) + pad4(n_o * per) + pad4(n_w * per);
   for (int b0 = 0, nb = 0; b0 < B && rc == QPWC_OK; b0 += nb, slot = (slot + 1) % HostStage::NSLOT) {
@@ -276,7 +281,7 @@ static int run_host(int kind, const float* a, const float* b, const float* f, fl
     else if (kind == 1) rc = launch_warp_fwd(da, df, dout, nb, H, W, C, mode, st);
     else if (l2pair) {
       rc = launch_warp_fwd(db, df, dw, nb, H, W, C, mode, st);
-      if (rc == QPWC_OK) rc = launch_corr_fwd_tc(da, dw, dout, nb, H, W, C, d, slope, (long long)D, st);
+      if (rc == QPWC_OK) rc = corr_fwd_any(da, dw, nullptr, 0, dout, nb, H, W, C, d, slope, (long long)D, st);
     } else rc = corr_fwd_any(da, db, df, mode, dout, nb, H, W, C, d, slope, (long long)D, st);
     if (rc != QPWC_OK) break;
     e = cudaMemcpyAsync(out + n_o * b0, dout, n_o * nb * sizeof(float), cudaMemcpyDeviceToHost, st);

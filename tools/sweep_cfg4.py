@@ -38,11 +38,22 @@ for d in (4, 8):
             for _ in range(2):
                 run()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # n launches recorded into one CUDA graph: device time, not the host's launch latency (the coarse
+            # levels take less time on the GPU than one Python -> C-ABI call takes on the host)
             n = 5 if d == 8 else 10
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    for _ in range(n):
+                        run()
+            torch.cuda.current_stream().wait_stream(side)
+            graph.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(n):
-                run()
+            graph.replay()
             e1.record()
             torch.cuda.synchronize()
             res[how] = e0.elapsed_time(e1) / n * 1e-3
