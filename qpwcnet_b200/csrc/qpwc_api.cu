@@ -86,21 +86,23 @@ void set_corr_bwd_variant(int v) { g_corr_bwd_variant.store(v); }
 int get_corr_bwd_variant() { return g_corr_bwd_variant.load(std::memory_order_relaxed); }
 int get_warp_bwd_variant();
 
-// Engine policy.  AUTO takes the tensor-core kernels for search range 4 only: range 8 runs there as four
-// 9x9 windows whose results leave through a strided scalar copy (36-byte runs at a 1156-byte pixel pitch admit
-// neither bulk stores nor a tensor-map store: the 68-byte displacement-row pitch is not a multiple of 16),
-// measured 1192 vs 978 us at 8x218x512x16 (profiles/r02_tc_d8.txt).  Forcing the engine still selects them.
+// Engine policy.  AUTO takes the tensor-core kernels for search range 4, and for search range 8 from 32
+// channels up.  Range 8 runs on either engine as four 9x9 windows whose results leave as 36-byte runs at a
+// 1156-byte pixel pitch (no bulk / tensor-map store: the 68-byte displacement-row pitch is not a multiple of
+// 16); with the window index running fastest in the tile order the runs of a pixel meet in L2
+// (profiles/r02c_tc_d8.txt, B = 8: 218x512x16 ffma 730 / tc 834 us, 109x256x32 248 / 240, 224x512x32 952 / 856,
+// 56x128x64 110 / 78).  Forcing an engine selects it at every shape of its domain.
 #ifdef QPWC_EMU
-static bool tc_wanted(int, int) { return false; }   // the emulation harness has no tensor-core stand-in
+static bool tc_wanted(int, int, int = 0) { return false; }   // the emulation harness has no tensor-core stand-in
 #else
-static bool tc_wanted(int engine, int d) { return engine == 2 || (engine == 0 && d == 4); }
+static bool tc_wanted(int engine, int d, int C = 1 << 30) { return engine == 2 || (engine == 0 && (d == 4 || (d == 8 && C >= 32))); }
 #endif
 
 static int corr_fwd_any(const float* prv, const float* nxt, const float* flow, int mode, float* out,
                         int B, int H, int W, int C, int d, float slope, long long ops, cudaStream_t st,
                         float up_scale = 0.f) {
   const int engine = g_corr_engine.load(std::memory_order_relaxed);
-  if (!flow && tc_wanted(engine, d)) {
+  if (!flow && tc_wanted(engine, d, C)) {
     const int rt = launch_corr_fwd_tc(prv, nxt, out, B, H, W, C, d, slope, ops, st);
     if (rt != QPWC_ERR_UNSUPPORTED) return rt;
     if (engine == 2) return set_error(QPWC_ERR_UNSUPPORTED, "corr_fwd: tensor-core engine needs search_range 4 or 8, C %% 8 == 0 and 16-byte aligned inputs");

@@ -273,6 +273,9 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
     }
   } else {
     // strided / unaligned output: 8 rows x 3 thirds = 24 items over the 12 warps, coalesced scalar copies
+    // (measured alternative: a thread per displacement walking the pixels with immediate offsets has a third
+    // of the instructions and is 20 % SLOWER at search range 8 -- a warp that writes a run of pixels one after
+    // the other lets their 36-byte runs combine on the way to L2)
     const int n = wv * Cfg::NDISP;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
@@ -325,8 +328,12 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem, int warp) {
 __global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
 corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
                           const __grid_constant__ TensorMap tmO, int tstore, float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
-                          int tiles_x, int tiles_y, int ntiles, int ablate, int oi, int oj, int chb, int qo) {
-  // (oi, oj): window offset of the second-frame tile (0 for d = 4; +-4 for the four windows of d = 8)
+                          int tiles_x, int tiles_y, int ntiles, int ablate, int nwin, int qo) {
+  // nwin = 1: the 9x9 window is the whole search range (d = 4).  nwin = 4 (d = 8): a tile index also selects
+  // one of the four 9x9 windows of the 17x17 range -- window offset (oi, oj) = (+-4, +-4) of the second-frame
+  // tile, first output channel chb.  The window index runs FASTEST, so the four windows of a tile are
+  // written by neighbouring CTAs at about the same time and their 36-byte runs merge into whole sectors
+  // in L2 (one launch per window cost a DRAM read-modify-write per run: the image is as large as L2).
   // ablate (dev, QPWC_ABLATE): bit0 no accumulator drain, bit1 no operand split, bit2 no MMAs, bit3 no loads,
   // bit4 no copy-out, bit5 force the streaming kernel, bit6 per-row bulk copies instead of the tensor store, bit7 no L2 prefetch
   using Cfg = TcCfg;
@@ -359,17 +366,18 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
       constexpr int PF = 2 * Cfg::NST;
       const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
       const int nitems = my_tiles * nstages;
-      auto coords = [&](int n, int& c, int& i0, int& j0, int& b) {
+      auto coords = [&](int n, int& c, int& i0, int& j0, int& b, int& oi, int& oj) {   // second-frame tile origin: (i0 - 4 + oi, j0 - 4 + oj)
         const int tl = n / nstages;
         c = n - tl * nstages;
-        const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+        const int tw = (int)blockIdx.x + tl * (int)gridDim.x, win = tw % nwin, tile = tw / nwin;
         const int tx = tile % tiles_x, rest = tile / tiles_x, ty = rest % tiles_y;
         b = rest / tiles_y; i0 = ty * Cfg::TH; j0 = tx * Cfg::TW;
+        oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4); oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4);
       };
       auto prefetch = [&](int n) {
         if (n >= nitems || (ablate & (8 | 128))) return;
-        int c, i0, j0, b;
-        coords(n, c, i0, j0, b);
+        int c, i0, j0, b, oi, oj;
+        coords(n, c, i0, j0, b, oi, oj);
         tma_prefetch_l2_4d(&tmP, c * Cfg::S_KC, j0, i0, b);
         tma_prefetch_l2_4d(&tmP, c * Cfg::S_KC, j0 + 8, i0, b);
         tma_prefetch_l2_4d(&tmN, c * Cfg::S_KC, j0 - 4 + oj, i0 - 4 + oi, b);
@@ -378,8 +386,8 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
       for (int n = 0; n < PF; ++n) prefetch(n);
       for (int n = 0; n < nitems; ++n) {
         const uint32_t g = (uint32_t)n;
-        int c, i0, j0, b;
-        coords(n, c, i0, j0, b);
+        int c, i0, j0, b, oi, oj;
+        coords(n, c, i0, j0, b, oi, oj);
         {
           const int s = (int)(g % Cfg::NST);
           tc_wait(&stage_free[s], ((g / Cfg::NST) & 1u) ^ 1u, spin);
@@ -466,8 +474,10 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
     const float inv_c = (C & (C - 1)) == 0 ? 1.f : 1.f / (float)C;  // power-of-two C: folded into the first-frame operand
     uint32_t tcount = 0;
     if (tstore && ew == 0 && lane == 0) tma_prefetch_desc(&tmO);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    for (int tw = blockIdx.x; tw < ntiles; tw += gridDim.x, ++tcount) {
+      const int win = tw % nwin, tile = tw / nwin;
       const int tx = tile % tiles_x, rest = tile / tiles_x, ty = rest % tiles_y, b = rest / tiles_y;
+      const int chb = nwin == 1 ? 0 : ((win >> 1) * 8) * qo + (win & 1) * 8;
       tc_epilogue_tile(staging, tmem, tfull, tempty, sfree, tcount, q, part, ew, lane, out, b, ty * Cfg::TH, tx * Cfg::TW,
                        H, W, ops, inv_c, slope, ablate, chb, qo, tstore ? &tmO : nullptr, 1, nullptr);
     }
@@ -493,7 +503,7 @@ corr_fwd_tc_stream_kernel(const __grid_constant__ TensorMap tmP, const __grid_co
 __global__ void __launch_bounds__(TcCfg::NTHREADS, 1)
 corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_constant__ TensorMap tmN,
                        const __grid_constant__ TensorMap tmO, int tstore, float* __restrict__ out, int B, int H, int W, int C, float slope, long long ops,
-                       int tiles_x, int tiles_y, int seg, int nseg, int nunits, int ablate, int oi, int oj, int chb, int qo) {
+                       int tiles_x, int tiles_y, int seg, int nseg, int nunits, int ablate, int nwin, int qo) {
   using Cfg = TcCfg;
   constexpr int PXB = Cfg::R_PXB;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -523,7 +533,11 @@ corr_fwd_tc_res_kernel(const __grid_constant__ TensorMap tmP, const __grid_const
   // inherits its top from the previous tile's bot and takes one fresh block
 #define QPWC_FOR_UNITS                                                                           \
   for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {                                \
-    const int tx = unit % tiles_x, rest_ = unit / tiles_x, sg = rest_ % nseg, b = rest_ / nseg;  \
+    const int win = unit % nwin, uu_ = unit / nwin;   /* window fastest (see the streaming kernel) */ \
+    const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4); \
+    const int chb = nwin == 1 ? 0 : (oi + 4) * qo + (oj + 4);                                    \
+    (void)oi; (void)oj; (void)chb;                                                               \
+    const int tx = uu_ % tiles_x, rest_ = uu_ / tiles_x, sg = rest_ % nseg, b = rest_ / nseg;    \
     const int ty0 = sg * seg, nt = min(seg, tiles_y - ty0), j0 = tx * Cfg::TW;                   \
     (void)b; (void)j0;                                                                           \
     for (int k = 0; k < nt; ++k, ++T) {                                                          \
@@ -701,18 +715,16 @@ int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, in
   const int nseg = cdiv(tiles_y, seg);
   const int nunits = tiles_x * B * nseg, ntiles = (int)nt;
   const int nwin = d == 8 ? 4 : 1, qo = 2 * d + 1;
-  for (int win = 0; win < nwin; ++win) {
-    const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4);
-    const int chb = nwin == 1 ? 0 : (oi + 4) * qo + (oj + 4);
-    if (resident)
-      corr_fwd_tc_res_kernel<<<nunits < sms ? nunits : sms, Cfg::NTHREADS, smem, stream>>>(
-          tmP, tmN, tmO, tstore, out, B, H, W, C, slope, ops, tiles_x, tiles_y, seg, nseg, nunits, ablate, oi, oj, chb, qo);
-    else
-      corr_fwd_tc_stream_kernel<<<ntiles < sms ? ntiles : sms, Cfg::NTHREADS, smem, stream>>>(
-          tmP, tmN, tmO, tstore, out, B, H, W, C, slope, ops, tiles_x, tiles_y, ntiles, ablate, oi, oj, chb, qo);
-    const int rc = check_launch(resident ? "corr_fwd_tc_res" : "corr_fwd_tc_stream");
-    if (rc != QPWC_OK) return rc;
-  }
+  if ((long long)nunits * nwin >= (1LL << 31) || nt * nwin >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
+  const int nu = nunits * nwin, ntw = ntiles * nwin;
+  if (resident)
+    corr_fwd_tc_res_kernel<<<nu < sms ? nu : sms, Cfg::NTHREADS, smem, stream>>>(
+        tmP, tmN, tmO, tstore, out, B, H, W, C, slope, ops, tiles_x, tiles_y, seg, nseg, nu, ablate, nwin, qo);
+  else
+    corr_fwd_tc_stream_kernel<<<ntw < sms ? ntw : sms, Cfg::NTHREADS, smem, stream>>>(
+        tmP, tmN, tmO, tstore, out, B, H, W, C, slope, ops, tiles_x, tiles_y, ntw, ablate, nwin, qo);
+  const int rc = check_launch(resident ? "corr_fwd_tc_res" : "corr_fwd_tc_stream");
+  if (rc != QPWC_OK) return rc;
   return QPWC_OK;
 }
 

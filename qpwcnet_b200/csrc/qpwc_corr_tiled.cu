@@ -88,9 +88,12 @@ struct TapsEntry { int o00, o01, o10, o11; float w00, w01, w10, w11; };  // 32 b
 // new warped rows are produced per tile instead of TH+2D.
 #define QPWC_FOR_TILES_BEGIN                                                                     \
   for (int segi = blockIdx.x; segi < nsegs; segi += gridDim.x) {                                 \
-    const int tx = segi % tiles_x, rest_ = segi / tiles_x; /* tile column fastest: concurrent   */ \
-    const int sy = rest_ % segs_per_strip, bw = rest_ / segs_per_strip; /* CTAs share image rows */ \
-    const int b = bw / nwin, win = bw - b * nwin;                                                \
+    /* the window index runs fastest: the four windows of a tile (search range 8) are written by    */ \
+    /* neighbouring CTAs at the same time, so their 36-byte runs merge into whole sectors in L2      */ \
+    /* instead of each costing a DRAM read-modify-write one image (~L2 size) later                  */ \
+    const int win = segi % nwin, segw_ = segi / nwin;                                            \
+    const int tx = segw_ % tiles_x, rest_ = segw_ / tiles_x; /* then tile column: concurrent     */ \
+    const int sy = rest_ % segs_per_strip, b = rest_ / segs_per_strip; /* CTAs share image rows  */ \
     const int oi = nwin == 1 ? 0 : ((win >> 1) * 8 - 4), oj = nwin == 1 ? 0 : ((win & 1) * 8 - 4); \
     const int seg_ = Cfg::WARP ? seg : 1; /* plain variants: compile-time single-tile segments */ \
     for (int tseg = 0; tseg < seg_; ++tseg) {                                                    \
