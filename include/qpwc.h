@@ -55,10 +55,11 @@ int qpwc_version(void);
 const char* qpwc_last_error(void);
 
 /* Process-wide options.  QPWC_OPT_CORR_ENGINE selects the arithmetic of the cost-volume forward
- * kernels: QPWC_ENGINE_AUTO (default) = tensor cores where they win (search_range 4,
- * C % 8 == 0): fp32 operands split into tf32 hi + lo, three tcgen05.mma passes, fp32 accumulation,
+ * kernels: QPWC_ENGINE_AUTO (default) = tensor cores where they win (search_range 4 with
+ * C % 8 == 0; search_range 8 with C % 8 == 0 and C >= 32): fp32 operands split into tf32 hi + lo, three tcgen05.mma passes, fp32 accumulation,
  * measured error <= 8e-7 * mean|prv*nxt| (the reference contract is 1e-5); QPWC_ENGINE_FFMA = plain
- * fp32 FFMA kernels only; QPWC_ENGINE_TC = tensor cores (search_range 4, or 8 as
+ * fp32 FFMA kernels only (the UpFlow pair is then the in-kernel fusion; under AUTO it is the warp
+ * kernel followed by the cost-volume kernel through a scratch owned by the call); QPWC_ENGINE_TC = tensor cores (search_range 4, or 8 as
  * four 9x9 windows; C % 8 == 0) or QPWC_ERR_UNSUPPORTED. */
 #define QPWC_OPT_CORR_ENGINE 0
 #define QPWC_ENGINE_AUTO 0
