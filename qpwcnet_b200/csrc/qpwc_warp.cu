@@ -10,6 +10,7 @@
 //           scatter-adds its channel vector into the four taps (vector red.global.add) and the
 //           flow gradient is reduced across the group with xor-shuffles in a fixed order.
 #include <atomic>
+#include <stdlib.h>
 
 #include "qpwc_upsample.cuh"
 
@@ -133,7 +134,10 @@ template <int MODE>
 __global__ void __launch_bounds__(256) warp_fwd_nchw_kernel(const float* __restrict__ img,
                                                             const float* __restrict__ flow,
                                                             float* __restrict__ out, int C, int H, int W,
-                                                            float scale) {
+                                                            float scale, int nsplit, int Ctot) {
+  // blockIdx.z = (batch item, channel split): this thread samples planes [cs*C, cs*C + C) of the Ctot planes
+  // of its batch item (the chain over the planes is serial per thread, so levels with few pixels and many
+  // planes are split over more threads).
   // block = 32 columns x 8 rows: a warp is one 128-byte row segment, and vertically adjacent pixels
   // (whose taps share source rows) sit in the same block, i.e. the same L1
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -141,13 +145,28 @@ __global__ void __launch_bounds__(256) warp_fwd_nchw_kernel(const float* __restr
   if (j >= W || i >= H) return;
   const size_t plane = (size_t)H * W;
   const size_t pix = (size_t)i * W + j;
-  const float* fb = flow + (size_t)blockIdx.z * 2 * plane;
+  const int bz = (int)blockIdx.z / nsplit, cs = (int)blockIdx.z - bz * nsplit;
+  const float* fb = flow + (size_t)bz * 2 * plane;
   const float fx = __fmul_rn(scale, __ldg(fb + pix)), fy = __fmul_rn(scale, __ldg(fb + plane + pix));
   const Taps t = make_taps<MODE>(i, j, fx, fy, H, W);
-  const float* src = img + (size_t)blockIdx.z * C * plane;
-  float* dst = out + (size_t)blockIdx.z * C * plane + pix;
-#pragma unroll 4
-  for (int c = 0; c < C; ++c, src += plane, dst += plane)
+  const float* src = img + ((size_t)bz * Ctot + (size_t)cs * C) * plane;
+  float* dst = out + ((size_t)bz * Ctot + (size_t)cs * C) * plane + pix;
+  // eight planes at a time, all 32 gathers issued before the first blend: left to the unroller the loads of
+  // a plane were issued only after the store of the plane before (~6 k clk per four planes; ncu: issue
+  // slots 22 % busy, nothing saturated): the per-thread chain over the planes is what bounds this kernel
+  constexpr int G = 8;
+  int c = 0;
+  for (; c + G <= C; c += G, src += G * plane, dst += G * plane) {
+    float v[G][4];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const float* sp = src + (size_t)k * plane;
+      v[k][0] = __ldg(sp + t.o00); v[k][1] = __ldg(sp + t.o01); v[k][2] = __ldg(sp + t.o10); v[k][3] = __ldg(sp + t.o11);
+    }
+#pragma unroll
+    for (int k = 0; k < G; ++k) dst[(size_t)k * plane] = blend<MODE>(t, v[k][0], v[k][1], v[k][2], v[k][3]);
+  }
+  for (; c < C; ++c, src += plane, dst += plane)
     *dst = blend<MODE>(t, __ldg(src + t.o00), __ldg(src + t.o01), __ldg(src + t.o10), __ldg(src + t.o11));
 }
 
@@ -155,13 +174,18 @@ int launch_warp_fwd_nchw(const float* img, const float* flow, float* out, int B,
                          int mode, float scale, cudaStream_t stream) {
   if ((long long)B * C * H * W == 0) return QPWC_OK;
   if (H > 8 * 65535 || B > 65535) return set_error(QPWC_ERR_UNSUPPORTED, "warp_fwd_nchw: H > 524280 or B > 65535");
-  const dim3 grid((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), (unsigned)B);
+  // planes per thread: all of them while the pixels alone fill the machine a few times over, else a divisor of C
+  int cpt = C;
+  const long long px = (long long)B * H * W;
+  while (cpt >= 16 && cpt % 2 == 0 && px * (C / cpt) < 600000 && (long long)B * (C / cpt) * 2 <= 65535) cpt /= 2;
+  const int nsplit = C / cpt;
+  const dim3 grid((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), (unsigned)(B * nsplit));
   if (mode == QPWC_MODE_TF) {
     auto k = warp_fwd_nchw_kernel<QPWC_MODE_TF>;
-    QPWC_LAUNCH(k, grid, 256, 0, stream, img, flow, out, C, H, W, scale);
+    QPWC_LAUNCH(k, grid, 256, 0, stream, img, flow, out, cpt, H, W, scale, nsplit, C);
   } else {
     auto k = warp_fwd_nchw_kernel<QPWC_MODE_TFA>;
-    QPWC_LAUNCH(k, grid, 256, 0, stream, img, flow, out, C, H, W, scale);
+    QPWC_LAUNCH(k, grid, 256, 0, stream, img, flow, out, cpt, H, W, scale, nsplit, C);
   }
   return check_launch("warp_fwd_nchw");
 }
@@ -177,13 +201,16 @@ __global__ void __launch_bounds__(256) warp_bwd_nchw_kernel(const float* __restr
                                                             const float* __restrict__ g_out,
                                                             float* __restrict__ g_img,
                                                             float* __restrict__ g_flow, int C, int H, int W,
-                                                            float scale) {
+                                                            float scale, int nsplit, int Ctot) {
+  // blockIdx.z = (batch item, channel split), as in the forward kernel; with nsplit > 1 the flow gradient
+  // (a sum over the planes) is accumulated with atomics on a pre-zeroed g_flow
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= W) return;
   const int i = blockIdx.y;
   const size_t plane = (size_t)H * W;
   const size_t pix = (size_t)i * W + j;
-  const float* fb = flow + (size_t)blockIdx.z * 2 * plane;
+  const int bz = (int)blockIdx.z / nsplit, cs = (int)blockIdx.z - bz * nsplit;
+  const float* fb = flow + (size_t)bz * 2 * plane;
   const float fx = __fmul_rn(scale, __ldg(fb + pix)), fy = __fmul_rn(scale, __ldg(fb + plane + pix));
   bool px = true, py = true;
   Taps t;
@@ -198,9 +225,10 @@ __global__ void __launch_bounds__(256) warp_bwd_nchw_kernel(const float* __restr
   }
   const bool dupx = (MODE == QPWC_MODE_TF) && (t.o00 == t.o01);
   const bool dupy = (MODE == QPWC_MODE_TF) && (t.o00 == t.o10);
-  const float* src = img + (size_t)blockIdx.z * C * plane;
-  const float* gsrc = g_out + (size_t)blockIdx.z * C * plane + pix;
-  float* gi = g_img + (size_t)blockIdx.z * C * plane;
+  const size_t cbase = ((size_t)bz * Ctot + (size_t)cs * C) * plane;
+  const float* src = img + cbase;
+  const float* gsrc = g_out + cbase + pix;
+  float* gi = g_img + cbase;
   float gx = 0.f, gy = 0.f;
 #pragma unroll 2
   for (int c = 0; c < C; ++c, src += plane, gsrc += plane, gi += plane) {
@@ -235,9 +263,14 @@ __global__ void __launch_bounds__(256) warp_bwd_nchw_kernel(const float* __restr
     if (!dupy) atomicAdd(gi + t.o10, a10);
     if (!dupx && !dupy) atomicAdd(gi + t.o11, a11);
   }
-  float* gf = g_flow + (size_t)blockIdx.z * 2 * plane + pix;
-  gf[0] = px ? __fmul_rn(scale, gx) : 0.f;
-  gf[plane] = py ? __fmul_rn(scale, gy) : 0.f;
+  float* gf = g_flow + (size_t)bz * 2 * plane + pix;
+  if (nsplit == 1) {
+    gf[0] = px ? __fmul_rn(scale, gx) : 0.f;
+    gf[plane] = py ? __fmul_rn(scale, gy) : 0.f;
+  } else {
+    if (px) atomicAdd(gf, __fmul_rn(scale, gx));
+    if (py) atomicAdd(gf + plane, __fmul_rn(scale, gy));
+  }
 }
 
 int launch_warp_bwd_nchw(const float* img, const float* flow, const float* g_out, float* g_img,
@@ -247,13 +280,22 @@ int launch_warp_bwd_nchw(const float* img, const float* flow, const float* g_out
   if (H > 65535 || B > 65535) return set_error(QPWC_ERR_UNSUPPORTED, "warp_bwd_nchw: H or B > 65535");
   cudaError_t e = cudaMemsetAsync(g_img, 0, sizeof(float) * (size_t)n, stream);
   if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "warp_bwd_nchw: memset g_img: %s", cudaGetErrorString(e));
-  const dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)B);
+  // planes per thread as in the forward launcher; a split needs g_flow zeroed (partial sums are added atomically)
+  int cpt = C;
+  const long long px = (long long)B * H * W;
+  while (cpt >= 16 && cpt % 2 == 0 && px * (C / cpt) < 600000 && (long long)B * (C / cpt) * 2 <= 65535) cpt /= 2;
+  const int nsplit = C / cpt;
+  if (nsplit > 1) {
+    e = cudaMemsetAsync(g_flow, 0, sizeof(float) * 2 * (size_t)px, stream);
+    if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "warp_bwd_nchw: memset g_flow: %s", cudaGetErrorString(e));
+  }
+  const dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)(B * nsplit));
   if (mode == QPWC_MODE_TF) {
     auto k = warp_bwd_nchw_kernel<QPWC_MODE_TF>;
-    QPWC_LAUNCH(k, grid, 128, 0, stream, img, flow, g_out, g_img, g_flow, C, H, W, scale);
+    QPWC_LAUNCH(k, grid, 128, 0, stream, img, flow, g_out, g_img, g_flow, cpt, H, W, scale, nsplit, C);
   } else {
     auto k = warp_bwd_nchw_kernel<QPWC_MODE_TFA>;
-    QPWC_LAUNCH(k, grid, 128, 0, stream, img, flow, g_out, g_img, g_flow, C, H, W, scale);
+    QPWC_LAUNCH(k, grid, 128, 0, stream, img, flow, g_out, g_img, g_flow, cpt, H, W, scale, nsplit, C);
   }
   return check_launch("warp_bwd_nchw");
 }
