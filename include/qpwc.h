@@ -83,8 +83,9 @@ int qpwc_corr_fwd(const float* prv, const float* nxt, float* out, int B, int H, 
 
 /* The same layer with data_format='channels_first' (layers.py:83-85; the reference's training
  * layout, pre_train.py:34), natively: prv, nxt (B,C,H,W) -> out (B,(2d+1)^2,H,W), all dense.
- * Returns QPWC_ERR_UNSUPPORTED (nothing launched) unless search_range == 4, W % 4 == 0 and the
- * tensors are 16-byte aligned; the caller then transposes and uses qpwc_corr_fwd. */
+ * search_range == 4, W % 4 == 0 and 16-byte aligned tensors take the tiled TMA kernel; every other
+ * shape (any search range, any W, any alignment) a shape-generic NCHW kernel -- no caller ever
+ * needs to transpose. */
 int qpwc_corr_fwd_nchw(const float* prv, const float* nxt, float* out, int B, int C, int H, int W,
                        int search_range, float leaky_slope, void* stream);
 
@@ -139,10 +140,9 @@ int qpwc_warp_bwd_ex(const float* img, const float* flow, const float* g_out, fl
 int qpwc_upsample2x_fwd(const float* src, float* dst, int B, int H, int W, int C, float scale, void* stream);
 int qpwc_upsample2x_bwd(const float* g_dst, float* g_src, int B, int H, int W, int C, float scale, void* stream);
 
-/* Gradients of qpwc_corr_fwd_nchw (autodiff of the channels_first layer): out / g_out (B,81,H,W),
- * g_prv / g_nxt (B,C,H,W), every element written exactly once (no atomics, no zero-init).  Same
- * domain as the forward kernel (search_range 4, W % 4 == 0, 16-byte aligned tensors); returns
- * QPWC_ERR_UNSUPPORTED otherwise (transpose to NHWC and call qpwc_corr_bwd). */
+/* Gradients of qpwc_corr_fwd_nchw (autodiff of the channels_first layer): out / g_out (B,(2d+1)^2,H,W),
+ * g_prv / g_nxt (B,C,H,W), every element written exactly once (no atomics, no zero-init).  Tiled
+ * kernels inside the forward kernel's tiled domain, shape-generic NCHW kernel elsewhere. */
 int qpwc_corr_bwd_nchw(const float* prv, const float* nxt, const float* out, const float* g_out,
                        float* g_prv, float* g_nxt, int B, int C, int H, int W, int search_range,
                        float leaky_slope, void* stream);

@@ -211,16 +211,61 @@ static int run_bwd_nchw(const float* x, const float* out, const float* g_out, fl
   return QPWC_OK;
 }
 
+// Shape-generic channels_first gradients (any search range / W / alignment; see corr_fwd_nchw_generic_kernel):
+// one thread per gradient element (b, c, i, j) gathers its (2d+1)^2 terms of both gradients, every access a
+// coalesced row segment:  g_prv += G'[(i,j),e] * nxt[i+di,j+dj],   g_nxt += G'[(i-di,j-dj),e] * prv[i-di,j-dj]
+// with G' = g_out * (out > 0 ? 1 : slope) / C.
+__global__ void __launch_bounds__(256) corr_bwd_nchw_generic_kernel(const float* __restrict__ prv, const float* __restrict__ nxt,
+                                                                    const float* __restrict__ out, const float* __restrict__ g_out,
+                                                                    float* __restrict__ g_prv, float* __restrict__ g_nxt,
+                                                                    int C, int H, int W, int d, float slope, long long total) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int q = 2 * d + 1, D = q * q;
+  const int j = (int)(idx % W);
+  long long r = idx / W;
+  const int i = (int)(r % H); r /= H;
+  const int c = (int)(r % C);
+  const long long b = r / C;
+  const size_t plane = (size_t)H * W;
+  const float* gb = g_out + (size_t)b * D * plane;
+  const float* ob = out + (size_t)b * D * plane;
+  const float* pc = prv + ((size_t)b * C + c) * plane;
+  const float* nc = nxt + ((size_t)b * C + c) * plane;
+  const float pos = 1.f / (float)C, neg = slope / (float)C;
+  float gp = 0.f, gn = 0.f;
+  for (int e = 0; e < D; ++e) {
+    const int di = e / q - d, dj = e % q - d;
+    const int ia = i + di, ja = j + dj;          // second-frame pixel this first-frame pixel was matched with
+    if (ia >= 0 && ia < H && ja >= 0 && ja < W) {
+      const size_t o = (size_t)e * plane + (size_t)i * W + j;
+      gp = fmaf(__ldg(gb + o) * (__ldg(ob + o) > 0.f ? pos : neg), __ldg(nc + (size_t)ia * W + ja), gp);
+    }
+    const int is = i - di, js = j - dj;          // first-frame pixel that matched this second-frame pixel at e
+    if (is >= 0 && is < H && js >= 0 && js < W) {
+      const size_t o = (size_t)e * plane + (size_t)is * W + js;
+      gn = fmaf(__ldg(gb + o) * (__ldg(ob + o) > 0.f ? pos : neg), __ldg(pc + (size_t)is * W + js), gn);
+    }
+  }
+  g_prv[idx] = gp;
+  g_nxt[idx] = gn;
+}
+
 int launch_corr_bwd_nchw(const float* prv, const float* nxt, const float* out, const float* g_out,
                          float* g_prv, float* g_nxt, int B, int C, int H, int W, int d, float slope,
                          cudaStream_t stream) {
-  // domain: d == 4, W a multiple of 4 (TMA strides are multiples of 16 bytes; 8-byte loads/stores of
-  // pixel pairs), 16-byte aligned inputs, 8-byte aligned out / g_out / gradients
-  if (d != 4 || (W & 3) || C < 1) return QPWC_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15)) return QPWC_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(g_out) & 7) ||
-      (reinterpret_cast<uintptr_t>(g_prv) & 7) || (reinterpret_cast<uintptr_t>(g_nxt) & 7))
-    return QPWC_ERR_UNSUPPORTED;
+  // tiled kernels: d == 4, W a multiple of 4 (TMA strides are multiples of 16 bytes; 8-byte loads/stores of
+  // pixel pairs), 16-byte aligned inputs, 8-byte aligned out / g_out / gradients; everything else is generic
+  if (d < 1 || C < 1) return QPWC_ERR_UNSUPPORTED;
+  if (d != 4 || (W & 3) || (reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(g_out) & 7) ||
+      (reinterpret_cast<uintptr_t>(g_prv) & 7) || (reinterpret_cast<uintptr_t>(g_nxt) & 7)) {
+    const long long total = (long long)B * C * H * W;
+    if (total == 0) return QPWC_OK;
+    if (cdivll(total, 256) >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
+    QPWC_LAUNCH(corr_bwd_nchw_generic_kernel, (unsigned)cdivll(total, 256), 256, 0, stream, prv, nxt, out, g_out, g_prv, g_nxt, C, H, W, d, slope, total);
+    return check_launch("corr_bwd_nchw_generic");
+  }
   // few tiles (coarse pyramid levels): 2-row tiles double the number of busy SMs
   const long long tiles4 = (long long)cdiv(W, 128) * cdiv(H, 4) * B;
   int rc;

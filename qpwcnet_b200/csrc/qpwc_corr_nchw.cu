@@ -214,13 +214,46 @@ static int run_nchw(const float* prv, const float* nxt, float* out, int B, int C
   return check_launch("corr_fwd_nchw");
 }
 
+// Shape-generic channels_first kernel (any search range, any W, any alignment): one thread per output element
+// (b, displacement, i, j), consecutive lanes = consecutive columns, so every plane access is a coalesced row
+// segment.  It serves the shapes outside the tiled kernel's domain -- W % 4 != 0 (TMA strides are multiples of
+// 16 bytes: e.g. the 8x14 level of a 256x448 training crop), search ranges other than 4 -- so that no
+// channels_first shape falls back to transposing the tensors.
+__global__ void __launch_bounds__(256) corr_fwd_nchw_generic_kernel(const float* __restrict__ prv, const float* __restrict__ nxt,
+                                                                    float* __restrict__ out, int C, int H, int W, int d,
+                                                                    float slope, long long total) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int q = 2 * d + 1, D = q * q;
+  const int j = (int)(idx % W);
+  long long r = idx / W;
+  const int i = (int)(r % H); r /= H;
+  const int e = (int)(r % D);
+  const long long b = r / D;
+  const int ii = i + e / q - d, jj = j + e % q - d;
+  float acc = 0.f;
+  if (ii >= 0 && ii < H && jj >= 0 && jj < W) {   // ZeroPadding2D: products with the padding are zero
+    const size_t plane = (size_t)H * W;
+    const float* p = prv + (size_t)b * C * plane + (size_t)i * W + j;
+    const float* n = nxt + (size_t)b * C * plane + (size_t)ii * W + jj;
+    for (int c = 0; c < C; ++c, p += plane, n += plane) acc = fmaf(__ldg(p), __ldg(n), acc);
+  }
+  out[idx] = lrelu(acc * (1.f / (float)C), slope);
+}
+
 int launch_corr_fwd_nchw(const float* prv, const float* nxt, float* out, int B, int C, int H, int W,
                          int d, float slope, cudaStream_t stream) {
-  // domain: d == 4, W a multiple of 4 (TMA strides are multiples of 16 bytes; 8-byte output stores),
-  // 16-byte aligned inputs, 8-byte aligned output
-  if (d != 4 || (W & 3) || C < 1) return QPWC_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15) || (reinterpret_cast<uintptr_t>(out) & 7))
-    return QPWC_ERR_UNSUPPORTED;
+  // tiled kernel: d == 4, W a multiple of 4 (TMA strides are multiples of 16 bytes; 8-byte output stores),
+  // 16-byte aligned inputs, 8-byte aligned output; everything else takes the generic kernel
+  if (d < 1 || C < 1) return QPWC_ERR_UNSUPPORTED;
+  if (d != 4 || (W & 3) || (reinterpret_cast<uintptr_t>(prv) & 15) || (reinterpret_cast<uintptr_t>(nxt) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 7)) {
+    const long long total = (long long)B * (2 * d + 1) * (2 * d + 1) * H * W;
+    if (total == 0) return QPWC_OK;
+    if (cdivll(total, 256) >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
+    QPWC_LAUNCH(corr_fwd_nchw_generic_kernel, (unsigned)cdivll(total, 256), 256, 0, stream, prv, nxt, out, C, H, W, d, slope, total);
+    return check_launch("corr_fwd_nchw_generic");
+  }
   // few tiles (coarse pyramid levels): 2-row tiles double the number of busy SMs
   const long long tiles4 = (long long)cdiv(W, 120) * cdiv(H, 4) * B;
   if (tiles4 * 2 <= sm_count_cached()) return run_nchw<NchwCfg<2>>(prv, nxt, out, B, C, H, W, slope, stream);

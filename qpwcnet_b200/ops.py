@@ -230,30 +230,24 @@ class _CostVolume(torch.autograd.Function):
 
 
 def _corr_fwd_nchw(prv, nxt, d, slope):
-    """Native channels_first forward; returns None when the library declines the shape (the caller
-    then takes the transposing NHWC route -- still CUDA, never a CPU path)."""
-    from ._cabi import QpwcError, QPWC_ERR_UNSUPPORTED
+    """Native channels_first forward (tiled kernel for d == 4, W % 4 == 0; shape-generic NCHW kernel elsewhere)."""
     B, C, H, W = prv.shape
     out = torch.empty((B, (2 * d + 1) ** 2, H, W), dtype=torch.float32, device=prv.device)
+    if out.numel() == 0:
+        return out
     vp, vn = _views(prv, nxt)
     with _on_device(prv.device):
-        rc = lib().qpwc_corr_fwd_nchw(vp.ptr, vn.ptr, out.data_ptr(), B, C, H, W, d, slope, _stream_ptr(prv.device))
-    if rc == QPWC_ERR_UNSUPPORTED:
-        return None
-    check(rc)
+        check(lib().qpwc_corr_fwd_nchw(vp.ptr, vn.ptr, out.data_ptr(), B, C, H, W, d, slope, _stream_ptr(prv.device)))
     return out
 
 
 class _CostVolumeNCHW(torch.autograd.Function):
-    """channels_first cost volume: native NCHW forward and gradient kernels; shapes outside their
-    domain take the transposing route through the NHWC kernels (still CUDA)."""
+    """channels_first cost volume: native NCHW forward and gradient kernels at every shape -- no layout
+    transposes (qpwcnet/core/layers.py:83-85 transposes around a channels_last op instead)."""
 
     @staticmethod
     def forward(ctx, prv, nxt, d, slope):
         out = _corr_fwd_nchw(prv, nxt, d, slope)
-        if out is None:
-            out = _corr_fwd(prv.permute(0, 2, 3, 1).contiguous(), nxt.permute(0, 2, 3, 1).contiguous(), d,
-                            slope).permute(0, 3, 1, 2).contiguous()
         ctx.save_for_backward(prv, nxt, out)
         ctx.cfg = (d, slope)
         return out
@@ -262,20 +256,15 @@ class _CostVolumeNCHW(torch.autograd.Function):
     def backward(ctx, g_out):
         prv, nxt, out = ctx.saved_tensors
         d, slope = ctx.cfg
-        from ._cabi import QPWC_ERR_UNSUPPORTED
         B, C, H, W = prv.shape
         g_out = g_out.contiguous()
         g_prv, g_nxt = torch.empty_like(prv), torch.empty_like(nxt)
-        with _on_device(prv.device):
-            rc = lib().qpwc_corr_bwd_nchw(prv.data_ptr(), nxt.data_ptr(), out.data_ptr(), g_out.data_ptr(),
-                                          g_prv.data_ptr(), g_nxt.data_ptr(), B, C, H, W, d, slope,
-                                          _stream_ptr(prv.device))
-        if rc != QPWC_ERR_UNSUPPORTED:
-            check(rc)
-            return g_prv, g_nxt, None, None
-        nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
-        g_prv, g_nxt = _corr_bwd(nhwc(prv), nhwc(nxt), nhwc(out), nhwc(g_out), d, slope)
-        return g_prv.permute(0, 3, 1, 2).contiguous(), g_nxt.permute(0, 3, 1, 2).contiguous(), None, None
+        if prv.numel():
+            with _on_device(prv.device):
+                check(lib().qpwc_corr_bwd_nchw(prv.data_ptr(), nxt.data_ptr(), out.data_ptr(), g_out.data_ptr(),
+                                               g_prv.data_ptr(), g_nxt.data_ptr(), B, C, H, W, d, slope,
+                                               _stream_ptr(prv.device)))
+        return g_prv, g_nxt, None, None
 
 
 class _WarpNCHW(torch.autograd.Function):

@@ -257,3 +257,25 @@ def test_emu_corr_bwd_nchw(B, C, H, W):
     assert not np.isnan(gp2).any() and not np.isnan(gn2).any()      # every element written
     assert np.abs(nhwc(gp2) - gp).max() <= 1e-5 * np.abs(gp).max()
     assert np.abs(nhwc(gn2) - gn).max() <= 1e-5 * np.abs(gn).max()
+
+
+@pytest.mark.parametrize("B,C,H,W,d", [(2, 7, 8, 14, 4), (1, 5, 6, 7, 2), (1, 3, 9, 10, 8), (2, 4, 5, 9, 1)])
+def test_emu_corr_nchw_generic_shapes(B, C, H, W, d):
+    """Shape-generic channels_first kernels (W % 4 != 0, search ranges other than 4): forward and both
+    gradients against the fp64 oracle -- no shape is left to a transposing route."""
+    r = rng(95 + C + W)
+    prv = r.standard_normal((B, C, H, W)).astype(np.float32)
+    nxt = r.standard_normal((B, C, H, W)).astype(np.float32)
+    nhwc = lambda a: np.ascontiguousarray(a.transpose(0, 2, 3, 1))
+    nchw = lambda a: np.ascontiguousarray(a.transpose(0, 3, 1, 2))
+    ref = oracle.cost_volume(nhwc(prv).astype(np.float64), nhwc(nxt).astype(np.float64), d)
+    got = emu_lib.corr_fwd_nchw(prv, nxt, d)
+    assert not np.isnan(got).any()
+    assert np.abs(nhwc(got) - ref).max() <= 1e-5 * np.abs(ref).max()
+    g = r.standard_normal(ref.shape).astype(np.float32)
+    gp, gn = oracle.cost_volume_bwd(nhwc(prv).astype(np.float64), nhwc(nxt).astype(np.float64), nhwc(got).astype(np.float64),
+                                    g.astype(np.float64), d)
+    gp2, gn2 = emu_lib.corr_bwd_nchw(prv, nxt, got, nchw(g), d)
+    assert not np.isnan(gp2).any() and not np.isnan(gn2).any()
+    assert np.abs(nhwc(gp2) - gp).max() <= 1e-5 * np.abs(gp).max()
+    assert np.abs(nhwc(gn2) - gn).max() <= 1e-5 * np.abs(gn).max()

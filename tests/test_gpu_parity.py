@@ -384,10 +384,39 @@ def test_cost_volume_channels_first_native(B, C, H, W):
                                     host(out).transpose(0, 2, 3, 1).astype(np.float64), g.transpose(0, 2, 3, 1).astype(np.float64), 4)
     assert_rel(host(gp).transpose(0, 2, 3, 1), rp)
     assert_rel(host(gn).transpose(0, 2, 3, 1), rn)
-    # shapes the native kernel declines (W % 4 != 0) fall back to the transposing route
+    # W % 4 != 0: the shape-generic NCHW kernel (no transposes either)
     o2 = layers.CostVolume(search_range=4, data_format="channels_first")((tp.detach()[..., :W - 1].contiguous(), tn.detach()[..., :W - 1].contiguous()))
     ref2 = oracle.cost_volume(prv[..., :W - 1].transpose(0, 2, 3, 1).astype(np.float64), nxt[..., :W - 1].transpose(0, 2, 3, 1).astype(np.float64), 4)
     assert_rel(host(o2).transpose(0, 2, 3, 1), ref2)
+
+
+@pytest.mark.parametrize("B,C,H,W,d", [(8, 256, 8, 14, 4), (2, 12, 9, 11, 4), (1, 5, 7, 20, 2), (1, 16, 12, 16, 8), (2, 3, 6, 7, 1)])
+def test_cost_volume_channels_first_generic_shapes(B, C, H, W, d, monkeypatch):
+    """channels_first shapes outside the tiled NCHW kernels' domain (W % 4 != 0 -- the 8x14 level of a
+    256x448 training crop --, search ranges other than 4): the shape-generic NCHW kernels, forward and
+    both gradients against the oracle, with torch.Tensor.permute made to fail during the layer call
+    (no transposing route)."""
+    from qpwcnet_b200.core import layers
+    r = rng(900 + C + W)
+    prv = r.standard_normal((B, C, H, W)).astype(np.float32)
+    nxt = r.standard_normal((B, C, H, W)).astype(np.float32)
+    D = (2 * d + 1) ** 2
+    g = r.standard_normal((B, D, H, W)).astype(np.float32)
+    tp, tn, tg = dev(prv).requires_grad_(), dev(nxt).requires_grad_(), dev(g)
+    nh = lambda a: a.transpose(0, 2, 3, 1).astype(np.float64)
+
+    def boom(*a, **k):
+        raise AssertionError("permute() reached under channels_first")
+    monkeypatch.setattr(torch.Tensor, "permute", boom)
+    out = layers.CostVolume(search_range=d, data_format="channels_first")((tp, tn))
+    gp, gn = torch.autograd.grad(out, (tp, tn), tg)
+    monkeypatch.undo()
+    assert tuple(out.shape) == (B, D, H, W)
+    ref = oracle.cost_volume(nh(prv), nh(nxt), d)
+    assert_rel(host(out).transpose(0, 2, 3, 1), ref)
+    rp, rn = oracle.cost_volume_bwd(nh(prv), nh(nxt), nh(host(out)), nh(g), d)
+    assert_rel(host(gp).transpose(0, 2, 3, 1), rp)
+    assert_rel(host(gn).transpose(0, 2, 3, 1), rn)
 
 
 @pytest.mark.parametrize("mode", ["tf", "tfa"])
