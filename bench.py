@@ -312,9 +312,12 @@ def run_native(args):
         wl_h.step()
     barrier()
     t0 = time.perf_counter()
+    e2e_steps = []
     for _ in range(Ke):
+        ts = time.perf_counter()
         wl_h.step()
         _ = float(wl_h.outputs[0][0, 0, 0, 0])      # host-side read of the step's result
+        e2e_steps.append((time.perf_counter() - ts) * 1e3)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / Ke)
     barrier()
@@ -347,6 +350,7 @@ def run_native(args):
                     "note": "floor = the larger of the step's H2D / D2H bytes at the full-duplex rate of the FASTEST rank, "
                             "measured in this run with every rank copying at once"},
            "d2h_bytes_per_step": wl_h.d2h_bytes(), "steps": Ke, "ms_per_step": e2e_s * 1e3,
+           "step_ms_rank0": [round(t, 2) for t in e2e_steps],
            "path": "ops.*_into(pinned host tensors) -> qpwc_*_host (6-slot H2D/kernel/D2H pipeline, 128 MiB slices, finest level first)",
            "host_thread": ("bound to the %d CPUs NVML reports as local to the GPU" % len(os.sched_getaffinity(0)))
                           if old_affinity is not None else "not bound (NVML affinity unavailable)"}
