@@ -212,6 +212,8 @@ struct HostStage {
   cudaStream_t stream[NSLOT] = {};
   float* buf[NSLOT] = {};
   size_t cap[NSLOT] = {};
+  size_t want = 0;    // largest slot size requested so far: every (re)allocation is made at this size, so that the
+                      // slots stop growing after the first pass over a workload (cudaFree/cudaMalloc synchronise the device)
   int next_slot = 0;  // keeps rotating across calls: consecutive deferred calls overlap (guarded by mu)
   std::mutex mu;
 };
@@ -225,12 +227,13 @@ static int stage_reserve(HostStage& hs, int slot, size_t bytes) {
     const cudaError_t e = cudaStreamCreateWithFlags(&hs.stream[slot], cudaStreamNonBlocking);
     if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "host stage: stream create: %s", cudaGetErrorString(e));
   }
+  if (bytes > hs.want) hs.want = bytes;
   if (hs.cap[slot] < bytes) {
     if (hs.buf[slot]) cudaFree(hs.buf[slot]);
     hs.buf[slot] = nullptr; hs.cap[slot] = 0;
-    const cudaError_t e = cudaMalloc(&hs.buf[slot], bytes);
-    if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "host stage: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
-    hs.cap[slot] = bytes;
+    const cudaError_t e = cudaMalloc(&hs.buf[slot], hs.want);
+    if (e != cudaSuccess) return set_error(QPWC_ERR_CUDA, "host stage: cudaMalloc(%zu): %s", hs.want, cudaGetErrorString(e));
+    hs.cap[slot] = hs.want;
   }
   return QPWC_OK;
 }
