@@ -1,3 +1,5 @@
+# ROUND-1 RECORD: the batch that produced profiles/r01_*; some of the variants it switches between
+# (QPWC_CORR_VARIANT=rowpair/packed, tools/ablate_rp.py) were removed in round 2.  Current batch: tools/final_capture_r02c.sh
 set -x
 cd $GRAFT_REPO_ROOT
 python bench.py --steps 500 --warmup 20 > gpurun_out/bench_n1_r01.json 2> gpurun_out/bench_n1_r01.err
