@@ -688,8 +688,7 @@ int launch_corr_fwd_tc(const float* prv, const float* nxt, float* out, int B, in
   const int tiles_x = cdiv(W, Cfg::TW), tiles_y = cdiv(H, Cfg::TH);
   const long long nt = (long long)tiles_x * tiles_y * B;
   if (nt >= (1LL << 31)) return QPWC_ERR_UNSUPPORTED;
-  static int ablate = -1;
-  if (ablate < 0) { const char* ev = getenv("QPWC_ABLATE"); ablate = ev ? atoi(ev) : 0; }
+  static const int ablate = [] { const char* ev = getenv("QPWC_ABLATE"); return ev ? atoi(ev) : 0; }();  // dev switches, read once (thread-safe)
   const int sms = sm_count_cached();
   const bool resident = C <= 32 && !(ablate & 32);
   TensorMap tmP, tmN;

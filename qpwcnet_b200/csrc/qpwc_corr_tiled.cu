@@ -560,8 +560,7 @@ int sm_count_cached() { return sm_count(); }
 
 // QPWC_ABLATE (dev only): bit0 skip FFMA loop, bit1 skip epilogue, bit2 skip loads+pipeline
 static int ablate_flags() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("QPWC_ABLATE"); v = e ? atoi(e) : 0; }
+  static const int v = [] { const char* e = getenv("QPWC_ABLATE"); return e ? atoi(e) : 0; }();  // read once, thread-safe
   return v;
 }
 
@@ -580,8 +579,7 @@ static int run_tiled(const float* prv, const float* nxt, const float* flow, floa
   if (Cfg::WARP && nwin == 1 && cdiv(C, Cfg::KC) <= Cfg::NST) {
     seg = 8;
     while (seg > 2 && (long long)tiles_x * B * cdiv(tiles_y, seg) < 3LL * sm_count()) seg >>= 1;
-    static int forced = -1;  // QPWC_SEG (dev/tests): force the segment length
-    if (forced < 0) { const char* e = getenv("QPWC_SEG"); forced = e ? atoi(e) : 0; }
+    static const int forced = [] { const char* e = getenv("QPWC_SEG"); return e ? atoi(e) : 0; }();  // dev/tests: force the segment length
     if (forced > 0) seg = forced;
   }
   const int segs_per_strip = cdiv(tiles_y, seg);
