@@ -169,11 +169,12 @@ int qpwc_warp_corr_fwd_up(const float* prv, const float* nxt, const float* flow_
                           long long out_pixel_stride, float up_scale, void* stream);
 
 /* UpFlow's  CostVolumeV2((prv, WarpV2((nxt, flo))))  -- qpwcnet/core/non_layers.py:377-380
- * (layers.py:478-481) as ONE call in which the warped second frame never makes the round trip through
- * HBM.  Tensor-core engine (default where the shape allows): the warp kernel and the cost-volume kernel
- * run back to back on chunks of frame pairs through a stream-ordered scratch buffer that stays resident
- * in the 126 MB L2 and is reused chunk after chunk.  FFMA engine / other shapes: one kernel, the warped
- * tile lives in shared memory only. */
+ * (layers.py:478-481) as ONE call without caller workspace.  AUTO / tensor-core engine: the warp kernel and
+ * the cost-volume kernel run back to back on chunks of frame pairs through a stream-ordered scratch buffer
+ * owned by the call and reused chunk after chunk (what stays in L2 between the two kernels depends on the
+ * chunk size against the 126 MB L2: the coarse levels fit, the finest config-2 level largely does not --
+ * 1.27x the algorithmic DRAM bytes there).  FFMA engine: one kernel, the warped tile lives in shared
+ * memory only (fewer DRAM bytes, slower: DESIGN.md 4.3). */
 int qpwc_warp_corr_fwd(const float* prv, const float* nxt, const float* flow, float* out, int B,
                        int H, int W, int C, int search_range, float leaky_slope, int mode,
                        long long out_pixel_stride, void* stream);
