@@ -16,7 +16,7 @@ namespace qpwc {
 // kernels (qpwc_warp.cu, qpwc_corr_direct.cu, qpwc_corr_tiled.cu)
 int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
-int launch_warp_fwd_ex(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f, int row_off = 0, int Hfull = 0);
+int launch_warp_fwd_ex(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, long long, cudaStream_t, float up_scale = 0.f, int row_off = 0, int Hfull = 0, int keep_l2 = 0);
 int launch_upsample2x_fwd(const float*, float*, int, int, int, int, float, cudaStream_t);
 int launch_warp_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
 int launch_corr_fwd_nchw(const float*, const float*, float*, int, int, int, int, int, float, cudaStream_t);
@@ -183,7 +183,8 @@ static int warp_corr_fwd_l2(const float* prv, const float* nxt, const float* flo
   cudaError_t e;
   for (int b0 = 0; b0 < B && rc == QPWC_OK; b0 += per) {
     const int nb = B - b0 < per ? B - b0 : per;
-    rc = launch_warp_fwd_ex(nxt + item * b0, flow + fitem * b0, nullptr, nullptr, scratch, nb, H, W, C, mode, 1.f, C, st, up_scale);
+    static const int keep = [] { const char* ev = getenv("QPWC_NO_L2_KEEP"); return ev && ev[0] == '1' ? 0 : 1; }();   // dev switch
+    rc = launch_warp_fwd_ex(nxt + item * b0, flow + fitem * b0, nullptr, nullptr, scratch, nb, H, W, C, mode, 1.f, C, st, up_scale, 0, 0, keep);
     // (cost volume of the scratch: tensor cores inside their domain, the FFMA kernels elsewhere)
     if (rc == QPWC_OK) rc = corr_fwd_any(prv + item * b0, scratch, nullptr, 0, out + (size_t)H * W * ops * b0, nb, H, W, C, d, slope, ops, st);
   }

@@ -259,7 +259,10 @@ __device__ __forceinline__ void tc_epilogue_tile(float* staging, uint32_t tmem, 
     // tensor store, clipped at the image edge (eight per-row bulk copies cost the issuing lane ~1100 clk
     // per tile, on the critical chain stores -> staging free -> next tile staged: profiles/r02_tc_trace.txt)
     if (ew == 0 && lane == 0) {
-      tma_store_4d(tmO, staging, 0, (j0 >> 4) * 6, i0, b);
+      // the cost volume is written once and not read again by this kernel: evict-first, so that the 297 MB output
+      // stream does not push the operands (the warped frame the warp kernel has just left in L2) out
+      if (ablate & 1024) tma_store_4d(tmO, staging, 0, (j0 >> 4) * 6, i0, b);
+      else tma_store_4d_hint(tmO, staging, 0, (j0 >> 4) * 6, i0, b, l2_policy_evict_first());
       bulk_commit();
     }
   } else if (bulk) {

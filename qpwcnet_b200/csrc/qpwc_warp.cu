@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ flow2,
                                                        float* __restrict__ out, int H, int W, int C,
                                                        int bsplit, float scale, long long ops,
-                                                       float up_scale, int row_off, int Hfull) {
+                                                       float up_scale, int row_off, int Hfull, int keep_l2) {
+  // keep_l2: the output is the scratch of the UpFlow pair, read back by the cost-volume kernel that follows on
+  // the stream -- stored with an evict-last L2 policy
   // row_off / Hfull (row-sharded frames, qpwcnet_b200/sharded.py): `img` is rows [row_off, row_off + H) of
   // an image Hfull rows tall.  The sampling coordinate, truncation and clamping use the ABSOLUTE row --
   // the reference adds the flow to the absolute pixel index in fp32, so its rounding depends on it --
@@ -121,6 +123,16 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
   for (int n = 0; n < NV; ++n) {
 #pragma unroll
     for (int k = 0; k < V; ++k) o[n][k] = blend<MODE>(t, v00[n][k], v01[n][k], v10[n][k], v11[n][k]);
+#ifndef QPWC_EMU
+    if (V == 4 && keep_l2) {
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                   ::"l"(dst + n * CV * V), "f"(o[n][0]), "f"(o[n][V > 1 ? 1 : 0]), "f"(o[n][V > 2 ? 2 : 0]), "f"(o[n][V > 3 ? 3 : 0]),
+                     "l"(pol) : "memory");
+      continue;
+    }
+#endif
     vstore<V>(dst + n * CV * V, o[n]);
   }
 }
@@ -561,30 +573,30 @@ static int pick_vec(int C, const void* a, const void* b, const void* c = nullptr
 template <int MODE, int V, int NV>
 static void run_warp_fwd_nv(const float* img, const float* flow, const float* img2, const float* flow2,
                             float* out, int B, int H, int W, int C, float scale, long long ops,
-                            float up_scale, cudaStream_t stream, int row_off, int Hfull);
+                            float up_scale, cudaStream_t stream, int row_off, int Hfull, int keep);
 
 template <int MODE, int V>
 static void run_warp_fwd(const float* img, const float* flow, const float* img2, const float* flow2,
                          float* out, int B, int H, int W, int C, float scale, long long ops,
-                         float up_scale, cudaStream_t stream, int row_off, int Hfull) {
+                         float up_scale, cudaStream_t stream, int row_off, int Hfull, int keep) {
   const int block = 256;
   if (V == 4 && C % 8 == 0) {  // two 16-byte vectors per thread
-    run_warp_fwd_nv<MODE, V, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
+    run_warp_fwd_nv<MODE, V, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull, keep);
     return;
   }
-  run_warp_fwd_nv<MODE, V, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
+  run_warp_fwd_nv<MODE, V, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull, keep);
 }
 
 template <int MODE, int V, int NV>
 static void run_warp_fwd_nv(const float* img, const float* flow, const float* img2, const float* flow2,
                             float* out, int B, int H, int W, int C, float scale, long long ops,
-                            float up_scale, cudaStream_t stream, int row_off, int Hfull) {
+                            float up_scale, cudaStream_t stream, int row_off, int Hfull, int keep) {
   const int block = 256;
   const int CV = C / (V * NV);
   auto k = warp_fwd_kernel<MODE, V, NV>;
   if (img2) {  // pair: grid.z = 2B (B <= 32767 checked by the caller)
     const dim3 grid((unsigned)cdiv(W * CV, block / WARP_FWD_ROWS), (unsigned)cdiv(H, WARP_FWD_ROWS), (unsigned)(2 * B));
-    QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, img2, flow2, out, H, W, C, B, scale, ops, up_scale, row_off, Hfull);
+    QPWC_LAUNCH(k, grid, block, 0, stream, img, flow, img2, flow2, out, H, W, C, B, scale, ops, up_scale, row_off, Hfull, keep);
     return;
   }
   // gridDim.y/z are limited to 65535: chunk the batch (and refuse absurd heights upstream)
@@ -594,14 +606,14 @@ static void run_warp_fwd_nv(const float* img, const float* flow, const float* im
     const size_t off = (size_t)b0 * H * W;
     const size_t foff = up_scale != 0.f ? (size_t)b0 * (H / 2) * (W / 2) * 2 : off * 2;
     QPWC_LAUNCH(k, grid, block, 0, stream, img + off * C, flow + foff, img2, flow2, out + off * ops, H, W, C,
-                nb, scale, ops, up_scale, row_off, Hfull);
+                nb, scale, ops, up_scale, row_off, Hfull, keep);
   }
 }
 
 // img2/flow2 != nullptr: two warps in one launch, the second writing channels [C, 2C) of each pixel
 int launch_warp_fwd_ex(const float* img, const float* flow, const float* img2, const float* flow2,
                        float* out, int B, int H, int W, int C, int mode, float scale, long long ops,
-                       cudaStream_t stream, float up_scale, int row_off, int Hfull) {
+                       cudaStream_t stream, float up_scale, int row_off, int Hfull, int keep_l2) {
   if (Hfull <= 0) Hfull = H;
   int V = pick_vec(C, img, out, img2);
   while (V > 1 && ops % V) V >>= 1;
@@ -609,20 +621,20 @@ int launch_warp_fwd_ex(const float* img, const float* flow, const float* img2, c
   if (H > 65535 || (long long)W * (C / V) >= (1LL << 31)) return set_error(QPWC_ERR_UNSUPPORTED, "warp_fwd: H > 65535 or W*C too large");
   if (img2 && B > 32767) return set_error(QPWC_ERR_UNSUPPORTED, "warp_pair_fwd: B > 32767");
   if (mode == QPWC_MODE_TF) {
-    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
-    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
-    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
+    if (V == 4) run_warp_fwd<QPWC_MODE_TF, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull, keep_l2);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TF, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull, keep_l2);
+    else run_warp_fwd<QPWC_MODE_TF, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull, keep_l2);
   } else {
-    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
-    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
-    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull);
+    if (V == 4) run_warp_fwd<QPWC_MODE_TFA, 4>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull, keep_l2);
+    else if (V == 2) run_warp_fwd<QPWC_MODE_TFA, 2>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull, keep_l2);
+    else run_warp_fwd<QPWC_MODE_TFA, 1>(img, flow, img2, flow2, out, B, H, W, C, scale, ops, up_scale, stream, row_off, Hfull, keep_l2);
   }
   return check_launch("warp_fwd");
 }
 
 int launch_warp_fwd(const float* img, const float* flow, float* out, int B, int H, int W, int C,
                     int mode, cudaStream_t stream) {
-  return launch_warp_fwd_ex(img, flow, nullptr, nullptr, out, B, H, W, C, mode, 1.f, C, stream, 0.f, 0, 0);
+  return launch_warp_fwd_ex(img, flow, nullptr, nullptr, out, B, H, W, C, mode, 1.f, C, stream, 0.f, 0, 0, 0);
 }
 
 template <int MODE, int V>
