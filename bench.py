@@ -278,14 +278,18 @@ def run_native(args):
     Kd = min(K, 200)
     dom_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kd)]
     nlev = len(wl.levels)
+    # (one small graph per level when graphs are in use: the host's launch latency does not sit between the
+    # warp kernel and the cost-volume kernel of the timed level)
+    level_graphs = wl.capture_levels() if use_graph else None
     for s in range(Kd):
         for k in range(nlev):
+            run_k = (lambda kk=k: level_graphs[kk].replay()) if level_graphs else (lambda kk=k: wl.run_level(kk))
             if k == dom:
                 dom_ev[s][0].record()
-                wl.run_level(k)
+                run_k()
                 dom_ev[s][1].record()
             else:
-                wl.run_level(k)
+                run_k()
     torch.cuda.synchronize()
     note = None
     if len(sampler.samples) < 5:

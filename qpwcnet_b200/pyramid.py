@@ -198,6 +198,24 @@ class PyramidWorkload:
         self._graph = graph
         return self
 
+    def capture_levels(self):
+        """One small CUDA graph per level (same kernels as step()): lets a caller time a single level between
+        events without the host's launch latency sitting between its warp and cost-volume kernels."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for k in range(len(self.levels)):
+                self.run_level(k)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._level_graphs = []
+        for k in range(len(self.levels)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run_level(k)
+            self._level_graphs.append(g)
+        return self._level_graphs
+
     def replay(self, which=None):
         """Replay the most recently captured graph, or the one named 'serial' / 'branches'."""
         (self._graph if which is None else self._graphs[which]).replay()
